@@ -1,0 +1,192 @@
+/*
+ * iss_b200.h -- C ABI of the B200 read-pair generation engine (libiss_b200.so).
+ *
+ * The reference (InSilicoSeq 2.0.1) is pure Python and has no FFI; its boundary for this path is
+ * Python-level.  Each entry point below names the reference interface it replaces:
+ *
+ *   iss_ctx_set_genome   <- the SeqRecord objects pickled to every worker       iss/app.py:99-106,
+ *                           (FASTA records parsed by SeqIO.parse)               iss/generator.py:270
+ *   iss_ctx_set_model    <- the ErrorModel object pickled to every worker       iss/error_models/kde.py:24-50
+ *                           (attribute set of KDErrorModel / Basic / Perfect)   iss/error_models/basic.py, perfect.py
+ *   iss_ctx_submit       <- pool.starmap(worker_iterator, work chunks)          iss/app.py:99-106
+ *                           one iss_work_item == one (record, n_pairs, mode)     iss/generator.py:223-251,333-352
+ *   iss_ctx_next/release <- the per-worker temp files {prefix}_R1.fastq,         iss/generator.py:227-229,
+ *                           _R2.fastq, .vcf that the parent concatenates          iss/app.py:123-133
+ *   iss_comm_* / bcast   <- multiprocessing's pickle scatter of genome + model   iss/app.py:99-106
+ *
+ * Everything is plain C: pointers + sizes, int status codes (0 = ok), iss_last_error() for text.
+ * Host arrays passed in are copied before the call returns.  Device memory, streams, pinned ring
+ * buffers and the NCCL communicator are owned by the context.  One host thread per context.
+ *
+ * Random numbers: Philox4x32-10, slot schedule "RNG contract v1" (DESIGN.md section 3).  All model
+ * tables are integer thresholds on 32/64-bit Philox words, so the device path has no floating point.
+ */
+#ifndef ISS_B200_H
+#define ISS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISS_ABI_VERSION 1
+
+/* status codes */
+#define ISS_OK 0
+#define ISS_E_CUDA 1      /* a CUDA / NCCL call failed (text in iss_last_error) */
+#define ISS_E_ARG 2       /* invalid argument */
+#define ISS_E_STATE 3     /* call out of order (e.g. submit before set_model) */
+#define ISS_E_CHAR 4      /* sequence character outside the reference's alphabet (ACGT + IUPAC, either case) */
+#define ISS_E_SHORT 5     /* record not longer than the read length (reference: AssertionError, generator.py:130) */
+#define ISS_E_DEVICE 6    /* device-side failure flag (negative window, empty quality bin ...) */
+#define ISS_E_NOMEM 7
+
+typedef struct iss_ctx iss_ctx;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int iss_abi_version(void);
+const char *iss_last_error(void);
+int iss_device_count(int *count);
+int iss_ctx_create(int device, iss_ctx **out);
+void iss_ctx_destroy(iss_ctx *ctx);
+
+/* ---- genome (replaces the pickled SeqRecords) ---------------------------------------------- */
+typedef struct {
+    const uint8_t *seq;  /* ASCII bases, as Bio.SeqIO.parse(...,"fasta") yields them (case preserved) */
+    uint64_t len;
+    const char *name;    /* record.id (first whitespace-delimited token of the FASTA title) */
+    uint32_t name_len;
+    uint32_t reserved;
+} iss_record;
+
+/* Copies + encodes the records: pure upper-case ACGT records are 2-bit packed, anything else
+ * (lower case, IUPAC codes) is kept as bytes so case and ambiguity codes survive exactly as in
+ * the reference.  Characters outside util.rev_comp's dictionary (iss/util.py:57-88) -> ISS_E_CHAR. */
+int iss_ctx_set_genome(iss_ctx *ctx, const iss_record *records, uint32_t n_records);
+
+/* ---- error model (replaces the pickled ErrorModel) ------------------------------------------ */
+/* Integer-threshold lowering of the model's f64 tables.  With w a 32-bit Philox word, u = w * 2^-32:
+ *   searchsorted(cdf, u, 'left')  == #{j : w >  G[j]},  G[j] = min(floor(cdf[j] * 2^32), 2^32 - 1)
+ *   choice / searchsorted 'right' == #{j : w >= H[j]},  H[j] = ceil(cdf[j] * 2^32)        (uint64)
+ *   u <  p                        == nz && w <= D,       C = ceil(p * 2^32), nz = C > 0, D = C - 1
+ *   u >  P                        == w >  floor(P * 2^32)
+ * Orientation index 0 = forward, 1 = reverse.  Base index: A=0, C=1, T=2, G=3 ((ascii >> 1) & 3). */
+#define ISS_QROW 64  /* quality rows are padded to 64 thresholds with 0xFFFFFFFF */
+#define ISS_MAX_ALT 4
+
+#define ISS_QUAL_KDE 0    /* per-position CDF rows selected by a per-read quality bin   kde.py:52-86 */
+#define ISS_QUAL_CONST 1  /* constant phred                                             perfect.py:35-42 */
+#define ISS_QUAL_TABLE 2  /* position-independent table on the 32-bit draw              basic.py:41-53 */
+
+typedef struct {
+    uint32_t read_length;          /* L */
+    uint32_t qual_mode;            /* ISS_QUAL_* */
+    uint32_t n_insert;             /* entries of insert_thr; 0 => fixed_insert is used */
+    int32_t fixed_insert;          /* basic.py:19 / perfect.py:18 insert_size */
+    uint32_t frag_mode;            /* 1: --fragment-length/--fragment-length-sd given (generator.py:121-123) */
+    uint32_t n_frag;
+    int64_t frag_lo;               /* fragment length = frag_lo + #{k : r64 >= frag_thr[k]} */
+    uint32_t const_phred;
+    uint32_t n_basic;              /* ISS_QUAL_TABLE: phred = basic_val[#{k : w >= basic_thr[k]}] */
+    uint32_t store_mutations;
+    uint32_t reserved;
+    const uint64_t *frag_thr;      /* [n_frag] */
+    const uint32_t *insert_thr;    /* [n_insert]                G */
+    const uint64_t *bin_thr;       /* [2][4]                    H */
+    const uint8_t *bin_valid;      /* [2][4] 1 when the bin has >= L CDF rows */
+    const uint32_t *qual_thr;      /* [2][4][L][ISS_QROW]       G, padded */
+    const uint32_t *err_thr;       /* [ISS_QROW]                floor(phred_to_prob(q) * 2^32) */
+    const uint8_t *subst_n;        /* [2][L][4] alternatives per original base */
+    const uint64_t *subst_thr;     /* [2][L][4][ISS_MAX_ALT]    H */
+    const uint8_t *subst_alt;      /* [2][L][4][ISS_MAX_ALT]    ASCII */
+    const uint32_t *ins_thr;       /* [2][L][4]                 D, lanes in the model dict's key order */
+    const uint8_t *ins_nz;         /* [2][L] bit lane set when that lane's probability is > 0 */
+    const uint8_t *ins_base;       /* [2][L][4] ASCII */
+    const uint32_t *del_thr;       /* [2][L][4]                 D, indexed by base */
+    const uint8_t *del_nz;         /* [2][L] bit b set when base b's probability is > 0 */
+    const uint32_t *basic_thr;     /* [n_basic] sorted */
+    const uint8_t *basic_val;      /* [n_basic + 1] */
+} iss_model;
+
+int iss_ctx_set_model(iss_ctx *ctx, const iss_model *model);
+
+/* ---- multi-GPU: genome + model are broadcast once, then ranks never talk again --------------- */
+#define ISS_UNIQUE_ID_BYTES 128
+int iss_comm_unique_id(uint8_t id[ISS_UNIQUE_ID_BYTES]);                 /* rank 0, then share out of band */
+int iss_comm_init_rank(iss_ctx *ctx, int nranks, int rank, const uint8_t id[ISS_UNIQUE_ID_BYTES]);
+int iss_comm_init_all(iss_ctx **ctxs, int n);                           /* one process, n devices */
+/* ncclBroadcast of the packed genome blob and the model blob from `root`; non-root contexts need no
+ * prior set_genome/set_model.  Rank mode: every rank calls it.  Group mode: pass all contexts. */
+int iss_ctx_bcast(iss_ctx *ctx, int root);
+int iss_ctx_bcast_all(iss_ctx **ctxs, int n, int root);
+
+/* ---- work (replaces starmap(worker_iterator, chunks)) --------------------------------------- */
+typedef struct {
+    uint32_t record;      /* index into the records passed to iss_ctx_set_genome */
+    uint32_t cpu_number;  /* chunk index: goes into read ids and the Philox key (generator.py:150,234-236) */
+    uint64_t n_pairs;     /* pairs of this work item handled by THIS submit: i = i0 .. i0+n_pairs-1 */
+    uint64_t i0;          /* first pair index (0 unless an item is split across submits / GPUs) */
+    uint64_t item_base;   /* pairs of the preceding work items of the same worker (RNG contract: P = item_base + i) */
+    uint64_t key;         /* Philox key = (seed + cpu_number) mod 2^64 */
+} iss_work_item;
+
+#define ISS_SEQ_METAGENOMICS 0
+#define ISS_SEQ_AMPLICON 1
+
+typedef struct {
+    uint32_t sequence_type;   /* ISS_SEQ_* (generator.py:134-139,164-171) */
+    uint32_t gc_bias;         /* generator.py:82-92 */
+    uint64_t batch_pairs;     /* pairs per ring slot; 0 = default */
+    uint32_t n_slots;         /* ring depth (>= 2); 0 = default */
+    uint32_t device_only;     /* 1: keep FASTQ in HBM (no D2H) -- kernel-throughput measurements */
+} iss_gen_opts;
+
+/* Starts asynchronous generation of all items (order preserved).  Records with len <= L are the
+ * caller's to skip (reference logs a warning, generator.py:77-80); passing one -> ISS_E_SHORT. */
+int iss_ctx_submit(iss_ctx *ctx, const iss_work_item *items, uint64_t n_items, const iss_gen_opts *opts);
+
+typedef struct {
+    const uint8_t *r1;        /* pinned host memory (device memory when device_only) */
+    const uint8_t *r2;
+    uint64_t nbytes;          /* bytes in r1 (== bytes in r2: the two records of a pair have equal length) */
+    const uint8_t *vcf;       /* store_mutations: VCF lines of this batch in reference order, else NULL */
+    uint64_t vcf_bytes;
+    uint64_t n_pairs;
+    uint64_t first_item;      /* index of the first work item contributing to this batch */
+    uint64_t batch_index;
+    uint32_t slot;
+    float kernel_ms;          /* device time of this batch's kernels (CUDA events on the launch stream) */
+} iss_batch;
+
+/* Blocks until the next batch (in submit order) is complete in host memory.  Returns ISS_OK and
+ * sets *have = 1, or *have = 0 when the submit is exhausted.  The batch stays valid until
+ * iss_ctx_release, which also lets the engine launch the next batch into that slot. */
+int iss_ctx_next(iss_ctx *ctx, iss_batch *batch, int *have);
+int iss_ctx_release(iss_ctx *ctx, const iss_batch *batch);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t pairs;            /* pairs generated since context creation */
+    uint64_t fastq_bytes;      /* R1 + R2 bytes produced */
+    uint64_t d2h_bytes;
+    uint64_t h2d_bytes;
+    uint64_t kernel_launches;
+    double kernel_ms;          /* sum of per-batch kernel device time */
+    uint64_t slow_reads;       /* reads that took the sequential indel replay */
+    uint64_t subst_errors;     /* substitution events */
+    uint64_t genome_bytes_device;
+    uint64_t model_bytes_device;
+} iss_stats;
+int iss_ctx_stats(iss_ctx *ctx, iss_stats *out);
+
+/* FASTQ bytes of pairs i0..i1-1 of one read file: sum of len("@{name}_{i}_{cpu}/1\n{seq}\n+\n{qual}\n") */
+uint64_t iss_fastq_bytes(uint32_t name_len, uint64_t cpu_number, uint32_t read_length, uint64_t i0, uint64_t i1);
+
+/* Philox4x32-10 on the device (one block), for known-answer tests of the device generator. */
+int iss_ctx_philox(iss_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISS_B200_H */

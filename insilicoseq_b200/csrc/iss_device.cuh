@@ -1,0 +1,195 @@
+// iss_device.cuh -- device-side data layout shared by the kernels and the host runtime.
+//
+// HBM layout (one allocation each, so that one ncclBroadcast moves each):
+//   genome blob : [GenomeHeader][DevRecord x n][names][64 B pad][2-bit words ...][64 B pad][ascii bytes ...][64 B pad]
+//   model blob  : [ModelHeader][tables ..., each 16 B aligned]
+// Both blobs are position independent (offsets, not pointers), so a rank that receives them over
+// NCCL rebuilds its pointer view with no host-side data.
+#pragma once
+#include <stdint.h>
+
+#define ISS_QROW 64
+#define ISS_MAX_ALT 4
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11).  Slot schedule: DESIGN.md section 3 / oracle/philox.py.
+// ---------------------------------------------------------------------------------------------
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+#else
+        uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// stream ids of RNG contract v1
+#define ISS_S_PAIR 0u
+#define ISS_K_QUAL 0u
+#define ISS_K_SUBC 1u
+#define ISS_K_DEL 2u
+#define ISS_K_INS 3u
+__host__ __device__ __forceinline__ uint32_t iss_read_stream(uint32_t o, uint32_t k) { return 1u + 4u * o + k; }
+
+// ---------------------------------------------------------------------------------------------
+// genome blob
+// ---------------------------------------------------------------------------------------------
+#define ISS_ENC_2BIT 0u
+#define ISS_ENC_ASCII 1u
+
+struct DevRecord {
+    uint64_t data_off;  // 2-bit: index of the record's first base in the packed word array (multiple of 64)
+                        // ascii: byte offset in the byte array
+    uint64_t len;
+    uint32_t enc;
+    uint32_t name_off;
+    uint32_t name_len;
+    uint32_t pad;
+};
+
+struct GenomeHeader {
+    uint64_t magic;
+    uint64_t total_bytes;
+    uint32_t n_records;
+    uint32_t pad;
+    uint64_t recs_off, names_off, names_bytes, packed_off, packed_bytes, ascii_off, ascii_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------
+// model blob
+// ---------------------------------------------------------------------------------------------
+struct ModelHeader {
+    uint64_t magic;
+    uint64_t total_bytes;
+    uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic, store_mutations;
+    int32_t fixed_insert;
+    uint32_t n_nz[2];      // positions (< L-1) with a non-zero insertion or deletion threshold
+    uint32_t pad;
+    int64_t frag_lo;
+    uint64_t bin_thr[2][4];
+    uint8_t bin_valid[2][4];
+    uint32_t err_thr[ISS_QROW];
+    // offsets (bytes from blob start)
+    uint64_t frag_thr_off, insert_thr_off, qual_thr_off, subst_n_off, subst_thr_off, subst_alt_off, ins_thr_off,
+        ins_nz_off, ins_base_off, del_thr_off, del_nz_off, nzpos_off, basic_thr_off, basic_val_off;
+};
+
+// pointer view built on each device from the blob base
+struct DevModel {
+    const ModelHeader *h;
+    const uint64_t *frag_thr;
+    const uint32_t *insert_thr;
+    const uint32_t *qual_thr;   // [2][4][L][64]
+    const uint8_t *subst_n;     // [2][L][4]
+    const uint64_t *subst_thr;  // [2][L][4][4]
+    const uint8_t *subst_alt;   // [2][L][4][4]
+    const uint32_t *ins_thr;    // [2][L][4]
+    const uint8_t *ins_nz;      // [2][L]
+    const uint8_t *ins_base;    // [2][L][4]
+    const uint32_t *del_thr;    // [2][L][4]
+    const uint8_t *del_nz;      // [2][L]
+    const uint16_t *nzpos;      // [2][L]
+    const uint32_t *basic_thr;
+    const uint8_t *basic_val;
+};
+
+struct DevGenome {
+    const DevRecord *recs;
+    const char *names;
+    const uint32_t *packed;  // 2-bit words; 16 bases per word, base m of a word at bits [2m, 2m+2)
+    const uint8_t *ascii;
+    uint32_t n_records;
+};
+
+// One segment = a run of consecutive pairs of one work item inside a batch.
+struct DevSegment {
+    uint64_t pair_start;  // batch-local index of the segment's first pair
+    uint64_t n;           // pairs in the segment
+    uint64_t i0;          // pair index i of the first pair
+    uint64_t item_base;   // P = item_base + i
+    uint64_t key;         // Philox key
+    uint64_t out_base;    // byte offset of pair i in the batch stream = out_base + cf(i)  (mod 2^64)
+    uint32_t rec;
+    uint32_t cpu;
+    uint32_t fixed_len;   // record bytes without the digits of i: 2L + 6 + name_len + 2 + digits(cpu) + 2
+    uint32_t cpu_digits;
+};
+
+// cumulative FASTQ bytes of pairs 0..i-1 of a segment: cf(i) = i*(fixed_len+1) + sum_k max(0, i - 10^k)
+__host__ __device__ __forceinline__ uint32_t iss_digits(uint64_t v) {
+    uint32_t d = 1;
+    uint64_t p = 10;
+#pragma unroll 1
+    for (int k = 1; k < 20; ++k) {
+        if (v >= p) d++; else break;
+        p *= 10;  // 10^19 < 2^64; the loop ends before 10^20
+    }
+    return d;
+}
+__host__ __device__ __forceinline__ uint64_t iss_cf(uint64_t i, uint32_t fixed_len) {
+    uint64_t s = i * (uint64_t)(fixed_len + 1u);
+    uint64_t p = 10;
+#pragma unroll 1
+    for (int k = 1; k < 20; ++k) {
+        if (i > p) s += i - p; else break;
+        p *= 10;
+    }
+    return s;
+}
+
+#define ISS_QUAL_KDE_MODE 0u
+#define ISS_QUAL_CONST_MODE 1u
+#define ISS_QUAL_TABLE_MODE 2u
+
+struct GenParams {
+    DevModel m;
+    DevGenome g;
+    // model scalars (copied from the ModelHeader so that they sit in the constant bank)
+    uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic;
+    int32_t fixed_insert;
+    int64_t frag_lo;
+    uint32_t n_nz[2];
+    uint64_t bin_thr[2][4];
+    uint8_t bin_valid[2][4];
+    uint32_t err_thr[ISS_QROW];
+    const DevSegment *segs;
+    uint32_t nseg;
+    uint32_t tile_pairs;      // T: pairs per tile; blockDim.x == 2T
+    uint64_t total_pairs;
+    uint8_t *out1;
+    uint8_t *out2;
+    uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)
+    uint32_t err_cap;         // entries of the substitution list
+    uint32_t amplicon;
+    uint32_t gc_bias;
+    uint32_t chunk_magic;     // ceil(2^32 / nchunk) for idx / nchunk
+    uint32_t nchunk;          // ceil(L / 16)
+    uint8_t *scratch;         // slow-path scratch: gridDim.x * ISS_SLOW_SLOTS * scratch_stride bytes
+    uint32_t scratch_stride;  // >= 5L + 8
+    uint32_t gc_thr;          // accept iff w < gc_thr  (ceil(0.90 * 2^32))
+    unsigned long long *counters;  // [0] slow reads [1] substitution events [2] error flags
+};
+
+#define ISS_SLOW_SLOTS 16
+#define ISS_DEVERR_RANGE 1u
+#define ISS_DEVERR_QUALBIN 2u
+#define ISS_DEVERR_CHAR 4u

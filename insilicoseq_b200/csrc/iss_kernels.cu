@@ -1,0 +1,560 @@
+// iss_kernels.cu -- sm_100a kernels of the read-pair generation hot path.
+//
+// One persistent kernel (iss_generate_kernel) produces finished FASTQ text for a batch of read pairs:
+//
+//   tile = T pairs (2T reads), blockDim = 2T, thread <-> read, warps are orientation-uniform
+//   phase 1  pair setup        insert size, window positions, quality bins        generator.py:121-177, kde.py:72-97
+//   phase 2  headers + gather  2-bit (or byte) genome windows -> ASCII in smem     generator.py:146-153,179-183, util.py:48-92
+//   phase 3  indel scan        Bernoulli tests in the no-event world; a read with  error_models/__init__.py:187-224
+//            + replay          any hit replays the reference's list semantics
+//   phase 4  phred sampling    per-position CDF search + error test                kde.py:82-85, __init__.py:94
+//   phase 5  substitutions     compacted list, parallel                            __init__.py:95-109
+//   phase 6  copy-out          smem image -> HBM with one cp.async.bulk per stream generator.py:64-65
+//
+// The FASTQ image of a tile is assembled in shared memory at the same 16-byte phase as its place in
+// the output stream, so the aligned middle leaves through the TMA bulk-copy engine
+// (cp.async.bulk.global.shared::cta) while the CTA starts the next tile.
+//
+// All randomness is Philox4x32-10 addressed by (key, pair ordinal, stream, block) -- "RNG contract v1".
+// No floating point anywhere: model tables are integer thresholds (include/iss_b200.h).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "iss_device.cuh"
+#include "iss_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// A, C, G, T in either case (bits 0, 2, 6, 19 of the letter index)
+__device__ __forceinline__ bool is_acgt(uint32_t c) {
+    uint32_t u = (c & 0xDFu) - 65u;
+    return u < 26u && ((0x00080045u >> u) & 1u);
+}
+// base index A=0 C=1 T=2 G=3 (works for both cases); complement = code ^ 2
+__device__ __forceinline__ uint32_t base_code(uint32_t c) { return (c >> 1) & 3u; }
+__device__ __forceinline__ uint32_t code_to_ascii(uint32_t code) { return __byte_perm(0x47544341u, 0u, code) & 0xFFu; }
+
+// iss/util.py:57-88 complement dictionary, case preserved.  Letters outside it were rejected at load.
+//                                       @   A    B    C    D   E  F   G    H   I  J   K   L   M    N   O  P  Q   R    S    T   U   V    W   X   Y
+__device__ __constant__ char kComplement[32] = {0, 'T', 'V', 'G', 'H', 0, 0, 'C', 'D', 0, 0, 'M', 0, 'K', 'N', 0, 0, 0, 'Y', 'S', 'A', 0, 'B', 'W', 0, 'R', 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ uint32_t complement_ascii(uint32_t c) { return (uint32_t)kComplement[c & 31u] | (c & 0x20u); }
+
+__device__ __forceinline__ uint32_t pick(const Philox4 &w, uint32_t j) {
+    return j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
+}
+__device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// #{j < 64 : w > row[j]} on a nondecreasing, 0xFFFFFFFF-padded row (searchsorted 'left')
+__device__ __forceinline__ uint32_t qrow_search(const uint32_t *__restrict__ row, uint32_t w) {
+    uint32_t lo = 0;
+    lo += (w > __ldg(row + 31)) ? 32u : 0u;
+    lo += (w > __ldg(row + lo + 15)) ? 16u : 0u;
+    lo += (w > __ldg(row + lo + 7)) ? 8u : 0u;
+    lo += (w > __ldg(row + lo + 3)) ? 4u : 0u;
+    lo += (w > __ldg(row + lo + 1)) ? 2u : 0u;
+    lo += (w > __ldg(row + lo)) ? 1u : 0u;
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
+    if (enc == ISS_ENC_2BIT) {
+        uint32_t w = __ldg(g.packed + (abs_pos >> 4));
+        return code_to_ascii((w >> ((uint32_t)(abs_pos & 15u) * 2u)) & 3u);
+    }
+    return __ldg(g.ascii + abs_pos);
+}
+
+struct TileSmem {
+    uint8_t *img[2];
+    uint64_t *sP;       // [T] pair ordinal
+    uint64_t *sKey;     // [T]
+    uint64_t *sOff;     // [T] byte offset of the pair's record in the batch stream
+    uint64_t *sWabs;    // [2T] absolute index (base or byte) of the window start in the genome array
+    uint64_t *sRecLen;  // [T] record length
+    uint64_t *sWin;     // [2T] window start inside the record (fs / rs)
+    uint32_t *sSeg;     // [T]
+    uint32_t *sAtt;     // [T]
+    uint32_t *sQrow;    // [2T] element offset of the read's quality rows
+    uint32_t *sSeqOff;  // [2T] offset of the sequence line inside the stream image
+    uint32_t *sEnc;     // [2T]
+    uint32_t *sSlow;    // [2T]
+    uint32_t *sErr;     // [err_cap]
+    uint32_t *sErrThr;  // [64]
+    uint32_t *sCtl;     // [8]: 0 nErr, 1 nSlow, 2 tileBytes
+};
+
+__device__ __forceinline__ TileSmem carve(uint8_t *base, const GenParams &p) {
+    TileSmem s;
+    const uint32_t T = p.tile_pairs;
+    uint8_t *q = base;
+    s.img[0] = q; q += p.img_cap;
+    s.img[1] = q; q += p.img_cap;
+    s.sP = (uint64_t *)q; q += 8u * T;
+    s.sKey = (uint64_t *)q; q += 8u * T;
+    s.sOff = (uint64_t *)q; q += 8u * T;
+    s.sRecLen = (uint64_t *)q; q += 8u * T;
+    s.sWabs = (uint64_t *)q; q += 16u * T;
+    s.sWin = (uint64_t *)q; q += 16u * T;
+    s.sSeg = (uint32_t *)q; q += 4u * T;
+    s.sAtt = (uint32_t *)q; q += 4u * T;
+    s.sQrow = (uint32_t *)q; q += 8u * T;
+    s.sSeqOff = (uint32_t *)q; q += 8u * T;
+    s.sEnc = (uint32_t *)q; q += 8u * T;
+    s.sSlow = (uint32_t *)q; q += 8u * T;
+    s.sErr = (uint32_t *)q; q += 4u * p.err_cap;
+    s.sErrThr = (uint32_t *)q; q += 4u * ISS_QROW;
+    s.sCtl = (uint32_t *)q;
+    return s;
+}
+
+// bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
+
+// ---- substitution of one (read, position) ---------------------------------------------------------
+__device__ __forceinline__ void apply_substitution(const GenParams &p, const TileSmem &s, uint32_t rd, uint32_t pos) {
+    const uint32_t T = p.tile_pairs, L = p.L;
+    const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
+    uint8_t *seq = s.img[o] + s.sSeqOff[rd];
+    const uint32_t c = seq[pos];
+    if (!is_acgt(c)) return;  // "RYWSMKHBVDN" are never substituted (__init__.py:94)
+    const uint32_t code = base_code(c);
+    const uint64_t P = s.sP[pair], key = s.sKey[pair];
+    const Philox4 w = philox4x32_10(pos >> 2, iss_read_stream(o, ISS_K_SUBC) | (s.sAtt[pair] << 8), (uint32_t)P,
+                                    (uint32_t)(P >> 32), (uint32_t)key, (uint32_t)(key >> 32));
+    const uint64_t r = pick(w, pos & 3u);
+    const uint32_t e = ((o * L + pos) << 2) + code;
+    const uint32_t na = p.m.subst_n[e];
+    const uint64_t *thr = p.m.subst_thr + (size_t)e * ISS_MAX_ALT;
+    uint32_t idx = 0;
+    for (uint32_t j = 0; j < na; ++j) idx += (r >= __ldg(thr + j)) ? 1u : 0u;
+    if (idx >= na) idx = na - 1u;
+    seq[pos] = p.m.subst_alt[(size_t)e * ISS_MAX_ALT + idx];
+}
+
+// ---- sequential replay of introduce_indels + adjust_seq_length for one read ---------------------------
+// Reference list semantics (error_models/__init__.py:187-226) restated as a stream:
+//   seq = out[0..nucl) ++ [cur] ++ future,   future = LIFO of inserted bases on top of the unread original.
+//   insertion at index nucl+1  == push on the LIFO (a later lane lands in front of an earlier one)
+//   pop(nucl)                  == drop cur; the next element takes index nucl WITHOUT being examined
+//   IndexError at seq[nucl]    == the stream is exhausted: nothing further is drawn
+__device__ void replay_indels(const GenParams &p, const TileSmem &s, uint32_t rd, uint8_t *scratch) {
+    const uint32_t T = p.tile_pairs, L = p.L;
+    const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
+    uint8_t *seq = s.img[o] + s.sSeqOff[rd];
+    uint8_t *orig = scratch;
+    uint8_t *stk = scratch + L;
+    for (uint32_t k = 0; k < L; ++k) orig[k] = seq[k];
+    const uint64_t P = s.sP[pair], key = s.sKey[pair];
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), att8 = s.sAtt[pair] << 8;
+    const uint32_t sIns = iss_read_stream(o, ISS_K_INS) | att8, sDel = iss_read_stream(o, ISS_K_DEL) | att8;
+    uint32_t sp = 0, k = 0, outlen = 0;
+    for (uint32_t nucl = 0; nucl + 1 < L; ++nucl) {
+        uint32_t cur;
+        if (sp) cur = stk[--sp]; else if (k < L) cur = orig[k++]; else break;
+        if (!is_acgt(cur)) { seq[outlen++] = (uint8_t)cur; continue; }
+        const uint32_t tb = o * L + nucl;
+        const uint32_t m = p.m.ins_nz[tb];
+        if (m) {
+            const Philox4 w = philox4x32_10(nucl, sIns, (uint32_t)P, (uint32_t)(P >> 32), k0, k1);
+            for (uint32_t lane = 0; lane < 4; ++lane)
+                if (((m >> lane) & 1u) && pick(w, lane) <= p.m.ins_thr[tb * 4 + lane]) stk[sp++] = p.m.ins_base[tb * 4 + lane];
+        }
+        const uint32_t code = base_code(cur);
+        bool del = false;
+        if ((p.m.del_nz[tb] >> code) & 1u) {
+            const Philox4 w = philox4x32_10(nucl >> 2, sDel, (uint32_t)P, (uint32_t)(P >> 32), k0, k1);
+            del = pick(w, nucl & 3u) <= p.m.del_thr[tb * 4 + code];
+        }
+        if (del) {
+            uint32_t x;
+            if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;
+            seq[outlen++] = (uint8_t)x;
+        } else {
+            seq[outlen++] = (uint8_t)cur;
+        }
+    }
+    while (outlen < L) {  // the part of the list behind the loop position, truncated to L (:136-139)
+        uint32_t x;
+        if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;
+        seq[outlen++] = (uint8_t)x;
+    }
+    if (outlen < L) {  // extension from the reference sequence (:141-155)
+        const uint32_t enc = s.sEnc[rd];
+        const uint64_t win = s.sWin[rd], reclen = s.sRecLen[pair];
+        const uint64_t rec_abs = s.sWabs[rd] - win;  // absolute index of the record's first base
+        uint32_t e = 0;
+        while (outlen < L) {
+            uint32_t ch;
+            if (o == 0) {
+                const uint64_t g = win + L + e;  // read_end + i
+                ch = (g >= reclen) ? (uint32_t)'A' : genome_ascii(p.g, enc, rec_abs + g);
+            } else {
+                if (win < (uint64_t)e + 1u) ch = (uint32_t)'A';  // read_start - 1 - i < 0
+                else ch = complement_ascii(genome_ascii(p.g, enc, rec_abs + (win - 1u - e)));
+            }
+            seq[outlen++] = (uint8_t)ch;
+            ++e;
+        }
+    }
+}
+
+}  // namespace
+
+extern __shared__ __align__(16) uint8_t iss_smem[];
+
+__global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant__ GenParams p) {
+    const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
+    const TileSmem s = carve(iss_smem, p);
+    if (tid < ISS_QROW) s.sErrThr[tid] = p.err_thr[tid];
+    const uint64_t ntiles = (p.total_pairs + T - 1) / T;
+    bool store_pending = false;
+    const uint32_t o = tid >= T ? 1u : 0u, pair = tid - o * T;
+
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t gp0 = tile * T;
+        const uint32_t npairs = (uint32_t)((p.total_pairs - gp0 < (uint64_t)T) ? (p.total_pairs - gp0) : (uint64_t)T);
+        const bool valid = pair < npairs;
+
+        // ---- phase 0: the previous tile's bulk stores must have finished READING shared memory
+        if (tid == 0) {
+            if (store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            s.sCtl[0] = 0; s.sCtl[1] = 0;
+        }
+        __syncthreads();
+
+        // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97)
+        if (tid < npairs) {
+            const uint64_t gp = gp0 + tid;
+            uint32_t lo = 0, hi = p.nseg;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (p.segs[mid].pair_start <= gp) lo = mid; else hi = mid;
+            }
+            const DevSegment *sg = p.segs + lo;
+            const uint64_t i = sg->i0 + (gp - sg->pair_start);
+            const uint64_t P = sg->item_base + i, key = sg->key;
+            const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
+            const DevRecord *rec = p.g.recs + sg->rec;
+            const int64_t len = (int64_t)rec->len;
+            uint32_t att = 0;
+            Philox4 b0;
+            for (;;) {  // --gc_bias: re-simulate the pair until the accept draw passes (generator.py:82-92)
+                b0 = philox4x32_10(0, ISS_S_PAIR | (att << 8), Plo, Phi, k0, k1);
+                if (!p.gc_bias || b0.w < p.gc_thr) break;
+                ++att;
+            }
+            const uint32_t a8 = att << 8;
+            Philox4 b2;
+            bool have_b2 = false;
+            int64_t insert;
+            if (p.frag_mode) {  // int(np.random.normal(mu, sd)) by inversion on the integer table
+                b2 = philox4x32_10(2, ISS_S_PAIR | a8, Plo, Phi, k0, k1);
+                have_b2 = true;
+                const uint64_t r64 = u64of(b2.z, b2.w);
+                uint32_t a = 0, b = p.n_frag;
+                while (a < b) { const uint32_t mid = (a + b) >> 1; if (r64 >= p.m.frag_thr[mid]) a = mid + 1; else b = mid; }
+                insert = p.frag_lo + (int64_t)a - 2 * (int64_t)L;
+            } else if (p.n_insert == 0) {
+                insert = p.fixed_insert;
+            } else {  // np.searchsorted(i_size_cdf, u): the CDF index is the insert size (kde.py:97)
+                uint32_t a = 0, b = p.n_insert;
+                while (a < b) { const uint32_t mid = (a + b) >> 1; if (b0.x > __ldg(p.m.insert_thr + mid)) a = mid + 1; else b = mid; }
+                insert = (int64_t)a;
+            }
+            const int64_t frag = insert + 2 * (int64_t)L;
+            const Philox4 b1 = philox4x32_10(1, ISS_S_PAIR | a8, Plo, Phi, k0, k1);
+            int64_t fs;
+            if (p.amplicon) fs = 0;
+            else {
+                const int64_t width = len - frag;
+                if (width > 0) fs = (int64_t)__umul64hi(u64of(b1.x, b1.y), (uint64_t)width);
+                else fs = (int64_t)__umul64hi(u64of(b1.z, b1.w), (uint64_t)(len - (int64_t)L));  // ValueError fallback
+            }
+            const int64_t fe = fs + (int64_t)L;
+            int64_t rs, re;
+            if (p.amplicon) { rs = len - (int64_t)L; re = len; }
+            else { rs = fe + insert; re = rs + (int64_t)L; }
+            if (re > len) {  // generator.py:172-176
+                if (!have_b2) b2 = philox4x32_10(2, ISS_S_PAIR | a8, Plo, Phi, k0, k1);
+                re = (int64_t)L + (int64_t)__umul64hi(u64of(b2.x, b2.y), (uint64_t)(len - (int64_t)L));
+                rs = re - (int64_t)L;
+            }
+            if (rs < 0 || fe > len) { atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_RANGE); rs = 0; if (fe > len) fs = 0; }
+            uint32_t binf = 0, binr = 0;
+            if (p.qual_mode == ISS_QUAL_KDE_MODE) {  // np.random.choice(range(4), p=norm_mean)
+                for (int j = 0; j < 4; ++j) {
+                    binf += ((uint64_t)b0.y >= p.bin_thr[0][j]) ? 1u : 0u;
+                    binr += ((uint64_t)b0.z >= p.bin_thr[1][j]) ? 1u : 0u;
+                }
+                if (binf == 4) binf = 3;
+                if (binr == 4) binr = 3;
+                if (!p.bin_valid[0][binf] || !p.bin_valid[1][binr]) atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_QUALBIN);
+            }
+            s.sQrow[tid] = (binf * L) * ISS_QROW;
+            s.sQrow[T + tid] = ((4u + binr) * L) * ISS_QROW;
+            s.sP[tid] = P;
+            s.sKey[tid] = key;
+            s.sSeg[tid] = lo;
+            s.sAtt[tid] = att;
+            s.sRecLen[tid] = (uint64_t)len;
+            s.sWin[tid] = (uint64_t)fs;
+            s.sWin[T + tid] = (uint64_t)rs;
+            s.sWabs[tid] = rec->data_off + (uint64_t)fs;
+            s.sWabs[T + tid] = rec->data_off + (uint64_t)rs;
+            s.sEnc[tid] = rec->enc;
+            s.sEnc[T + tid] = rec->enc;
+            const uint64_t off = sg->out_base + iss_cf(i, sg->fixed_len);
+            s.sOff[tid] = off;
+            if (tid == npairs - 1) s.sCtl[3] = sg->fixed_len + iss_digits(i);  // bytes of the last record
+        }
+        __syncthreads();
+        const uint64_t g0 = s.sOff[0];
+        const uint32_t a0 = (uint32_t)(g0 & 15u);
+        const uint32_t tile_bytes = (uint32_t)(s.sOff[npairs - 1] - g0) + s.sCtl[3];
+
+        // ---- phase 2a: record skeleton, one thread per read:  "@{name}_{i}_{cpu}/{1|2}\n" ... "\n+\n" ... "\n"
+        if (valid) {
+            const DevSegment *sg = p.segs + s.sSeg[pair];
+            uint8_t *img = s.img[o] + a0 + (uint32_t)(s.sOff[pair] - g0);
+            const uint64_t i = s.sP[pair] - sg->item_base;
+            const DevRecord *rec = p.g.recs + sg->rec;
+            uint32_t w = 0;
+            img[w++] = '@';
+            const char *nm = p.g.names + rec->name_off;
+            for (uint32_t k = 0; k < rec->name_len; ++k) img[w++] = (uint8_t)nm[k];
+            img[w++] = '_';
+            {
+                const uint32_t nd = iss_digits(i);
+                uint64_t v = i;
+                for (int d = (int)nd - 1; d >= 0; --d) { img[w + d] = (uint8_t)('0' + (uint32_t)(v % 10u)); v /= 10u; }
+                w += nd;
+            }
+            img[w++] = '_';
+            {
+                uint32_t v = sg->cpu;
+                const uint32_t nd = sg->cpu_digits;
+                for (int d = (int)nd - 1; d >= 0; --d) { img[w + d] = (uint8_t)('0' + v % 10u); v /= 10u; }
+                w += nd;
+            }
+            img[w++] = '/';
+            img[w++] = (uint8_t)('1' + o);
+            img[w++] = '\n';
+            s.sSeqOff[tid] = (uint32_t)(img - s.img[o]) + w;
+            img[w + L] = '\n';
+            img[w + L + 1] = '+';
+            img[w + L + 2] = '\n';
+            img[w + 2 * L + 3] = '\n';
+        }
+        __syncthreads();
+
+        // ---- phase 2b: gather the windows, flattened over (read, 16-base chunk)
+        {
+            const uint32_t nitems = 2u * T * p.nchunk;
+            for (uint32_t idx = tid; idx < nitems; idx += blockDim.x) {
+                const uint32_t rd = __umulhi(idx, p.chunk_magic);
+                const uint32_t j = idx - rd * p.nchunk;
+                const uint32_t ro = rd >= T ? 1u : 0u, rp = rd - ro * T;
+                if (rp >= npairs) continue;
+                uint8_t *seq = s.img[ro] + s.sSeqOff[rd];
+                const uint64_t wabs = s.sWabs[rd];
+                if (s.sEnc[rd] == ISS_ENC_2BIT) {
+                    const uint64_t q = ro ? (wabs + L - 16u * j - 16u) : (wabs + 16u * j);
+                    const uint32_t wi = (uint32_t)(q >> 4), sh = ((uint32_t)q & 15u) * 2u;
+                    const uint32_t w0 = __ldg(p.g.packed + wi), w1 = __ldg(p.g.packed + wi + 1);
+                    uint32_t w = __funnelshift_r(w0, w1, sh);
+                    if (ro) w ^= 0xAAAAAAAAu;  // complement every base: code ^ 2
+#pragma unroll
+                    for (uint32_t m = 0; m < 16; ++m) {
+                        const uint32_t k = ro ? (16u * j + 15u - m) : (16u * j + m);
+                        if (k < L) seq[k] = (uint8_t)code_to_ascii((w >> (2u * m)) & 3u);
+                    }
+                } else {
+#pragma unroll 4
+                    for (uint32_t m = 0; m < 16; ++m) {
+                        const uint32_t k = 16u * j + m;
+                        if (k < L) {
+                            if (ro) seq[k] = (uint8_t)complement_ascii(__ldg(p.g.ascii + wabs + (L - 1u - k)));
+                            else seq[k] = __ldg(p.g.ascii + wabs + k);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: indel scan in the no-event world (error_models/__init__.py:187-224)
+        const uint64_t P = valid ? s.sP[pair] : 0, key = valid ? s.sKey[pair] : 0;
+        const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
+        const uint32_t att8 = valid ? (s.sAtt[pair] << 8) : 0;
+        uint8_t *seq = s.img[o] + (valid ? s.sSeqOff[tid] : 0);
+        const uint32_t nnz = p.n_nz[o];
+        if (valid && nnz) {
+            const uint32_t sIns = iss_read_stream(o, ISS_K_INS) | att8, sDel = iss_read_stream(o, ISS_K_DEL) | att8;
+            bool fired = false;
+            uint32_t cached = 0xFFFFFFFFu;
+            Philox4 dblk = {0, 0, 0, 0};
+            for (uint32_t n = 0; n < nnz && !fired; ++n) {
+                const uint32_t pos = p.m.nzpos[o * L + n];
+                const uint32_t c = seq[pos];
+                if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
+                const uint32_t tb = o * L + pos;
+                const uint32_t m = p.m.ins_nz[tb];
+                if (m) {
+                    const Philox4 w = philox4x32_10(pos, sIns, Plo, Phi, k0, k1);
+                    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.ins_thr) + tb);
+                    fired |= ((m & 1u) && w.x <= t.x) | ((m & 2u) && w.y <= t.y) | ((m & 4u) && w.z <= t.z) | ((m & 8u) && w.w <= t.w);
+                }
+                const uint32_t code = base_code(c);
+                if ((p.m.del_nz[tb] >> code) & 1u) {
+                    if ((pos >> 2) != cached) { cached = pos >> 2; dblk = philox4x32_10(cached, sDel, Plo, Phi, k0, k1); }
+                    fired |= pick(dblk, pos & 3u) <= __ldg(p.m.del_thr + tb * 4 + code);
+                }
+            }
+            if (fired) s.sSlow[atomicAdd(&s.sCtl[1], 1u)] = tid;
+        }
+        __syncthreads();
+        {
+            const uint32_t nslow = s.sCtl[1];
+            if (nslow) {  // warp-uniform; rare for real models
+                for (uint32_t base = 0; base < nslow; base += ISS_SLOW_SLOTS) {
+                    if (tid < ISS_SLOW_SLOTS && base + tid < nslow)
+                        replay_indels(p, s, s.sSlow[base + tid],
+                                      p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride);
+                }
+                __syncthreads();
+                if (tid == 0) atomicAdd(p.counters + 0, (unsigned long long)nslow);
+            }
+        }
+
+        // ---- phase 4: phred scores + substitution tests, one thread per read, lanes in lockstep on the position
+        if (valid) {
+            uint8_t *qual = seq + L + 3;
+            const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
+            const uint32_t nblk = (L + 1u) >> 1;
+            if (p.qual_mode == ISS_QUAL_KDE_MODE) {
+                const uint32_t *rows = p.m.qual_thr + s.sQrow[tid];
+                for (uint32_t b = 0; b < nblk; ++b) {
+                    const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
+                    const uint32_t pos = 2u * b;
+                    const uint32_t q0 = qrow_search(rows + (size_t)pos * ISS_QROW, w.x);
+                    qual[pos] = (uint8_t)(q0 + 33u);
+                    if (w.y > s.sErrThr[q0]) {
+                        const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
+                        if (slot < p.err_cap) s.sErr[slot] = (tid << 16) | pos; else apply_substitution(p, s, tid, pos);
+                    }
+                    if (pos + 1u < L) {
+                        const uint32_t q1 = qrow_search(rows + (size_t)(pos + 1u) * ISS_QROW, w.z);
+                        qual[pos + 1u] = (uint8_t)(q1 + 33u);
+                        if (w.w > s.sErrThr[q1]) {
+                            const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
+                            if (slot < p.err_cap) s.sErr[slot] = (tid << 16) | (pos + 1u); else apply_substitution(p, s, tid, pos + 1u);
+                        }
+                    }
+                }
+            } else {
+                for (uint32_t b = 0; b < nblk; ++b) {
+                    const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
+#pragma unroll
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        const uint32_t pos = 2u * b + h;
+                        if (pos >= L) break;
+                        const uint32_t wq = h ? w.z : w.x, wt = h ? w.w : w.y;
+                        uint32_t q;
+                        if (p.qual_mode == ISS_QUAL_CONST_MODE) q = p.const_phred;
+                        else {
+                            uint32_t a = 0, e = p.n_basic;
+                            while (a < e) { const uint32_t mid = (a + e) >> 1; if (wq >= __ldg(p.m.basic_thr + mid)) a = mid + 1; else e = mid; }
+                            q = p.m.basic_val[a];
+                        }
+                        qual[pos] = (uint8_t)(q + 33u);
+                        if (wt > s.sErrThr[q]) {
+                            const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
+                            if (slot < p.err_cap) s.sErr[slot] = (tid << 16) | pos; else apply_substitution(p, s, tid, pos);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 5: substitutions, compacted over the whole tile (error_models/__init__.py:95-109)
+        {
+            const uint32_t nerr_all = s.sCtl[0];
+            const uint32_t nerr = nerr_all < p.err_cap ? nerr_all : p.err_cap;
+            for (uint32_t e = tid; e < nerr; e += blockDim.x) {
+                const uint32_t v = s.sErr[e];
+                apply_substitution(p, s, v >> 16, v & 0xFFFFu);
+            }
+            if (tid == 0 && nerr_all) atomicAdd(p.counters + 1, (unsigned long long)nerr_all);
+        }
+        // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+
+        // ---- phase 6: copy-out.  [g0, g0 + tile_bytes) of each stream; the 16 B aligned middle goes through the
+        //      bulk-copy engine, the ragged head/tail (< 16 B each) through plain byte stores.
+        {
+            uint32_t head = (16u - a0) & 15u;
+            if (head > tile_bytes) head = tile_bytes;
+            const uint32_t mid = (tile_bytes - head) & ~15u;
+            const uint32_t tail = tile_bytes - head - mid;
+            const uint32_t edge = head + tail;
+            for (uint32_t idx = tid; idx < 2u * edge; idx += blockDim.x) {
+                const uint32_t st = idx >= edge ? 1u : 0u;
+                const uint32_t e = idx - st * edge;
+                const uint32_t byte = e < head ? e : (head + mid + (e - head));
+                (st ? p.out2 : p.out1)[g0 + byte] = s.img[st][a0 + byte];
+            }
+#ifndef ISS_NO_BULK_STORE
+            if (tid == 0 && mid) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out1 + g0 + head),
+                             "r"(smem_addr(s.img[0] + a0 + head)), "r"(mid)
+                             : "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out2 + g0 + head),
+                             "r"(smem_addr(s.img[1] + a0 + head)), "r"(mid)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                store_pending = true;
+            }
+#else
+            for (uint32_t idx = tid; idx < 2u * (mid >> 4); idx += blockDim.x) {
+                const uint32_t st = idx >= (mid >> 4) ? 1u : 0u;
+                const uint32_t e = idx - st * (mid >> 4);
+                const uint4 v = *reinterpret_cast<const uint4 *>(s.img[st] + a0 + head + 16u * e);
+                *reinterpret_cast<uint4 *>((st ? p.out2 : p.out1) + g0 + head + 16u * e) = v;
+            }
+#endif
+        }
+        // the next iteration's phase-0 barrier orders these reads before any new write to the images
+    }
+    if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+__global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
+    const Philox4 w = philox4x32_10(c0, c1, c2, c3, k0, k1);
+    out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = w.w;
+}
+
+// ---- host-visible launch helpers --------------------------------------------------------------------
+size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) {
+    return 2ull * img_cap + 8ull * T * 4 + 16ull * T * 2 + 4ull * T * 2 + 8ull * T * 4 + 4ull * err_cap + 4ull * ISS_QROW + 32;
+}
+
+cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
+    return cudaFuncSetAttribute(iss_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+}
+
+cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
+    iss_generate_kernel<<<grid, 2 * p.tile_pairs, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t iss_occupancy(uint32_t T, size_t smem, int *blocks_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel, (int)(2 * T), smem);
+}
+
+cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {
+    iss_philox_kernel<<<1, 1, 0, stream>>>(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], dev_out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,714 @@
+// iss_runtime.cu -- host runtime behind the C ABI (include/iss_b200.h).
+//
+//   * genome blob   : FASTA records -> 2-bit packed words (pure ACGT) or bytes (anything else), one HBM allocation
+//   * model blob    : integer-threshold tables + the list of positions with non-zero indel thresholds
+//   * batch planner : work items -> batches of <= batch_pairs pairs -> segments with closed-form output offsets
+//   * ring pipeline : n_slots x {device FASTQ buffers, pinned host buffers, stream, events}; kernel of batch k+1
+//                     overlaps the D2H copy of batch k; the consumer drives it through iss_ctx_next/release
+//   * NCCL          : one broadcast of the two blobs at init (rank mode for one-process-per-GPU, group mode for
+//                     one process driving several GPUs); no communication afterwards
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/iss_b200.h"
+#include "iss_device.cuh"
+#include "iss_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ISS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                  \
+    } while (0)
+#define NC(call)                                                                                           \
+    do {                                                                                                   \
+        ncclResult_t r__ = (call);                                                                         \
+        if (r__ != ncclSuccess) return fail(ISS_E_CUDA, std::string(#call) + ": " + ncclGetErrorString(r__)); \
+    } while (0)
+
+constexpr uint64_t kGenomeMagic = 0x31474e4547535349ull;  // "ISSGENG1"
+constexpr uint64_t kModelMagic = 0x314c444f4d535349ull;   // "ISSMODL1"
+constexpr size_t kMaxSmem = 232448;                        // 227 KB opt-in per CTA on sm_100
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+struct Slot {
+    uint8_t *d_out[2] = {nullptr, nullptr};
+    uint8_t *h_out[2] = {nullptr, nullptr};
+    DevSegment *d_segs = nullptr;
+    DevSegment *h_segs = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    int state = 0;  // 0 free, 1 in flight, 2 handed to the consumer
+    uint64_t nbytes = 0, n_pairs = 0, first_item = 0, batch_index = 0;
+};
+
+struct HostRecord {
+    uint64_t len;
+    uint32_t name_len;
+};
+
+}  // namespace
+
+struct iss_ctx {
+    int device = 0;
+    int sm_count = 0;
+    // blobs
+    uint8_t *d_genome = nullptr;
+    uint64_t genome_bytes = 0;
+    uint8_t *d_model = nullptr;
+    uint64_t model_bytes = 0;
+    GenomeHeader gh{};
+    ModelHeader mh{};
+    DevGenome gview{};
+    DevModel mview{};
+    std::vector<HostRecord> recs;
+    bool have_genome = false, have_model = false;
+    // generation state
+    std::vector<iss_work_item> items;
+    iss_gen_opts opts{};
+    uint64_t cur_item = 0, cur_off = 0;  // planner cursor
+    uint64_t batch_pairs = 0, slot_cap = 0, max_rec = 0;
+    uint32_t n_slots = 0, max_segs = 0;
+    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 1024, grid = 0;
+    size_t smem = 0;
+    std::vector<Slot> slots;
+    uint64_t next_launch = 0, next_return = 0;  // batch counters
+    bool active = false, exhausted = false;
+    uint8_t *d_scratch = nullptr;
+    uint64_t scratch_bytes = 0;
+    unsigned long long *d_counters = nullptr;
+    // NCCL
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    iss_stats stats{};
+};
+
+namespace {
+
+int set_device(iss_ctx *c) {
+    CU(cudaSetDevice(c->device));
+    return ISS_OK;
+}
+
+void free_slots(iss_ctx *c) {
+    for (auto &s : c->slots) {
+        if (s.d_out[0]) cudaFree(s.d_out[0]);
+        if (s.d_out[1]) cudaFree(s.d_out[1]);
+        if (s.h_out[0]) cudaFreeHost(s.h_out[0]);
+        if (s.h_out[1]) cudaFreeHost(s.h_out[1]);
+        if (s.d_segs) cudaFree(s.d_segs);
+        if (s.h_segs) cudaFreeHost(s.h_segs);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    c->slots.clear();
+}
+
+int rebuild_views(iss_ctx *c) {
+    if (c->d_genome) {
+        CU(cudaMemcpy(&c->gh, c->d_genome, sizeof(GenomeHeader), cudaMemcpyDeviceToHost));
+        if (c->gh.magic != kGenomeMagic) return fail(ISS_E_STATE, "genome blob: bad magic");
+        c->gview.recs = reinterpret_cast<const DevRecord *>(c->d_genome + c->gh.recs_off);
+        c->gview.names = reinterpret_cast<const char *>(c->d_genome + c->gh.names_off);
+        c->gview.packed = reinterpret_cast<const uint32_t *>(c->d_genome + c->gh.packed_off);
+        c->gview.ascii = c->d_genome + c->gh.ascii_off;
+        c->gview.n_records = c->gh.n_records;
+        std::vector<DevRecord> dr(c->gh.n_records);
+        if (c->gh.n_records)
+            CU(cudaMemcpy(dr.data(), c->d_genome + c->gh.recs_off, sizeof(DevRecord) * dr.size(), cudaMemcpyDeviceToHost));
+        c->recs.resize(dr.size());
+        for (size_t i = 0; i < dr.size(); ++i) c->recs[i] = HostRecord{dr[i].len, dr[i].name_len};
+        c->have_genome = true;
+        c->stats.genome_bytes_device = c->genome_bytes;
+    }
+    if (c->d_model) {
+        CU(cudaMemcpy(&c->mh, c->d_model, sizeof(ModelHeader), cudaMemcpyDeviceToHost));
+        if (c->mh.magic != kModelMagic) return fail(ISS_E_STATE, "model blob: bad magic");
+        const uint8_t *b = c->d_model;
+        const ModelHeader &h = c->mh;
+        c->mview.h = reinterpret_cast<const ModelHeader *>(b);
+        c->mview.frag_thr = reinterpret_cast<const uint64_t *>(b + h.frag_thr_off);
+        c->mview.insert_thr = reinterpret_cast<const uint32_t *>(b + h.insert_thr_off);
+        c->mview.qual_thr = reinterpret_cast<const uint32_t *>(b + h.qual_thr_off);
+        c->mview.subst_n = b + h.subst_n_off;
+        c->mview.subst_thr = reinterpret_cast<const uint64_t *>(b + h.subst_thr_off);
+        c->mview.subst_alt = b + h.subst_alt_off;
+        c->mview.ins_thr = reinterpret_cast<const uint32_t *>(b + h.ins_thr_off);
+        c->mview.ins_nz = b + h.ins_nz_off;
+        c->mview.ins_base = b + h.ins_base_off;
+        c->mview.del_thr = reinterpret_cast<const uint32_t *>(b + h.del_thr_off);
+        c->mview.del_nz = b + h.del_nz_off;
+        c->mview.nzpos = reinterpret_cast<const uint16_t *>(b + h.nzpos_off);
+        c->mview.basic_thr = reinterpret_cast<const uint32_t *>(b + h.basic_thr_off);
+        c->mview.basic_val = b + h.basic_val_off;
+        c->have_model = true;
+        c->stats.model_bytes_device = c->model_bytes;
+    }
+    return ISS_OK;
+}
+
+// util.rev_comp's dictionary (iss/util.py:57-88): ACGT + YRWSKMNBVDH in either case
+bool in_alphabet(uint8_t ch) {
+    const uint32_t u = (uint32_t)(ch & 0xDF) - 65u;
+    // A B C D G H K M N R S T V W Y
+    const uint32_t mask = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) |
+                          (1u << 13) | (1u << 17) | (1u << 18) | (1u << 19) | (1u << 21) | (1u << 22) | (1u << 24);
+    return u < 26u && ((mask >> u) & 1u) && (ch >= 'A');
+}
+
+uint32_t record_fixed_len(uint32_t L, uint32_t name_len, uint32_t cpu) {
+    return 2u * L + 6u + name_len + 2u + iss_digits(cpu) + 2u;
+}
+
+// Plan and launch the next batch into slot `si`.  Returns ISS_OK; sets c->exhausted when no work is left.
+int launch_batch(iss_ctx *c, uint32_t si) {
+    Slot &s = c->slots[si];
+    const uint32_t L = c->mh.L;
+    uint64_t pairs = 0, bytes = 0;
+    uint32_t nseg = 0;
+    const uint64_t first_item = c->cur_item;
+    while (c->cur_item < c->items.size() && pairs < c->batch_pairs && nseg < c->max_segs) {
+        const iss_work_item &it = c->items[c->cur_item];
+        const uint64_t left = it.n_pairs - c->cur_off;
+        if (left == 0) { c->cur_item++; c->cur_off = 0; continue; }
+        const uint64_t take = std::min(left, c->batch_pairs - pairs);
+        const HostRecord &hr = c->recs[it.record];
+        DevSegment &sg = s.h_segs[nseg];
+        sg.pair_start = pairs;
+        sg.n = take;
+        sg.i0 = it.i0 + c->cur_off;
+        sg.item_base = it.item_base;
+        sg.key = it.key;
+        sg.rec = it.record;
+        sg.cpu = it.cpu_number;
+        sg.cpu_digits = iss_digits(it.cpu_number);
+        sg.fixed_len = record_fixed_len(L, hr.name_len, it.cpu_number);
+        const uint64_t cf0 = iss_cf(sg.i0, sg.fixed_len);
+        sg.out_base = bytes - cf0;  // modulo 2^64 on purpose
+        bytes += iss_cf(sg.i0 + take, sg.fixed_len) - cf0;
+        pairs += take;
+        nseg++;
+        c->cur_off += take;
+        if (c->cur_off == it.n_pairs) { c->cur_item++; c->cur_off = 0; }
+    }
+    if (pairs == 0) { c->exhausted = true; return ISS_OK; }
+    if (bytes > c->slot_cap) return fail(ISS_E_STATE, "internal: batch exceeds slot capacity");
+
+    CU(cudaMemcpyAsync(s.d_segs, s.h_segs, sizeof(DevSegment) * nseg, cudaMemcpyHostToDevice, s.stream));
+    GenParams p{};
+    p.m = c->mview;
+    p.g = c->gview;
+    const ModelHeader &h = c->mh;
+    p.L = h.L; p.qual_mode = h.qual_mode; p.n_insert = h.n_insert; p.frag_mode = h.frag_mode; p.n_frag = h.n_frag;
+    p.const_phred = h.const_phred; p.n_basic = h.n_basic; p.fixed_insert = h.fixed_insert; p.frag_lo = h.frag_lo;
+    p.n_nz[0] = h.n_nz[0]; p.n_nz[1] = h.n_nz[1];
+    memcpy(p.bin_thr, h.bin_thr, sizeof p.bin_thr);
+    memcpy(p.bin_valid, h.bin_valid, sizeof p.bin_valid);
+    memcpy(p.err_thr, h.err_thr, sizeof p.err_thr);
+    p.segs = s.d_segs;
+    p.nseg = nseg;
+    p.tile_pairs = c->tile_pairs;
+    p.total_pairs = pairs;
+    p.out1 = s.d_out[0];
+    p.out2 = s.d_out[1];
+    p.img_cap = c->img_cap;
+    p.err_cap = c->err_cap;
+    p.amplicon = c->opts.sequence_type == ISS_SEQ_AMPLICON;
+    p.gc_bias = c->opts.gc_bias;
+    p.nchunk = (L + 15u) / 16u;
+    p.chunk_magic = (uint32_t)((0x100000000ull + p.nchunk - 1) / p.nchunk);
+    p.scratch = c->d_scratch;
+    p.scratch_stride = (uint32_t)align_up(5ull * L + 8, 16);
+    p.gc_thr = 3865470567u;  // ceil(0.90 * 2^32): u < 0.90  <=>  w < gc_thr   (generator.py:88)
+    p.counters = c->d_counters;
+    const uint64_t ntiles = (pairs + c->tile_pairs - 1) / c->tile_pairs;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, c->grid);
+    CU(cudaEventRecord(s.ev_k0, s.stream));
+    CU(iss_launch_generate(p, grid, c->smem, s.stream));
+    CU(cudaEventRecord(s.ev_k1, s.stream));
+    if (!c->opts.device_only) {
+        CU(cudaMemcpyAsync(s.h_out[0], s.d_out[0], bytes, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
+        c->stats.d2h_bytes += 2 * bytes;
+    }
+    CU(cudaEventRecord(s.ev_done, s.stream));
+    s.state = 1;
+    s.nbytes = bytes;
+    s.n_pairs = pairs;
+    s.first_item = first_item;
+    s.batch_index = c->next_launch++;
+    c->stats.h2d_bytes += sizeof(DevSegment) * nseg;
+    c->stats.kernel_launches += 1;
+    c->stats.pairs += pairs;
+    c->stats.fastq_bytes += 2 * bytes;
+    return ISS_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int iss_abi_version(void) { return ISS_ABI_VERSION; }
+const char *iss_last_error(void) { return g_err.c_str(); }
+
+int iss_device_count(int *count) {
+    CU(cudaGetDeviceCount(count));
+    return ISS_OK;
+}
+
+int iss_ctx_create(int device, iss_ctx **out) {
+    if (!out) return fail(ISS_E_ARG, "out is null");
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(ISS_E_ARG, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(ISS_E_CUDA, "this library is built for sm_100a (Blackwell) only");
+    iss_ctx *c = new iss_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(iss_kernel_configure(kMaxSmem));
+    CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+    *out = c;
+    return ISS_OK;
+}
+
+void iss_ctx_destroy(iss_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_slots(c);
+    if (c->d_genome) cudaFree(c->d_genome);
+    if (c->d_model) cudaFree(c->d_model);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->comm) ncclCommDestroy(c->comm);
+    delete c;
+}
+
+int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
+    if (!c || (!records && n)) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    if (c->active) return fail(ISS_E_STATE, "generation in progress");
+    // classify + size
+    std::vector<uint32_t> enc(n);
+    uint64_t names_bytes = 0, packed_bases = 64, ascii_bytes = 64;
+    std::vector<DevRecord> dr(n);
+    for (uint32_t r = 0; r < n; ++r) {
+        const iss_record &rec = records[r];
+        bool pure = true;
+        for (uint64_t k = 0; k < rec.len; ++k) {
+            const uint8_t ch = rec.seq[k];
+            if (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T') continue;
+            pure = false;
+            if (!in_alphabet(ch)) {
+                char buf[160];
+                snprintf(buf, sizeof buf, "record %u: character 0x%02x at position %llu is outside the reference's alphabet", r, ch,
+                         (unsigned long long)k);
+                return fail(ISS_E_CHAR, buf);
+            }
+        }
+        enc[r] = pure ? ISS_ENC_2BIT : ISS_ENC_ASCII;
+        dr[r].len = rec.len;
+        dr[r].enc = enc[r];
+        dr[r].name_off = (uint32_t)names_bytes;
+        dr[r].name_len = rec.name_len;
+        dr[r].pad = 0;
+        names_bytes += rec.name_len;
+        if (pure) { dr[r].data_off = packed_bases; packed_bases = align_up(packed_bases + rec.len, 64); }
+        else { dr[r].data_off = ascii_bytes; ascii_bytes = align_up(ascii_bytes + rec.len, 16); }
+    }
+    packed_bases += 128;  // tail pad: windows may be read up to 31 bases past a record
+    ascii_bytes += 64;
+    GenomeHeader gh{};
+    gh.magic = kGenomeMagic;
+    gh.n_records = n;
+    uint64_t off = align_up(sizeof(GenomeHeader), 16);
+    gh.recs_off = off; off = align_up(off + sizeof(DevRecord) * (uint64_t)n, 16);
+    gh.names_off = off; gh.names_bytes = names_bytes; off = align_up(off + names_bytes, 64);
+    gh.packed_off = off; gh.packed_bytes = packed_bases / 4; off = align_up(off + gh.packed_bytes, 64);
+    gh.ascii_off = off; gh.ascii_bytes = ascii_bytes; off = align_up(off + ascii_bytes, 64);
+    gh.total_bytes = off;
+    std::vector<uint8_t> blob(off, 0);
+    memcpy(blob.data(), &gh, sizeof gh);
+    if (n) memcpy(blob.data() + gh.recs_off, dr.data(), sizeof(DevRecord) * (size_t)n);
+    uint32_t *packed = reinterpret_cast<uint32_t *>(blob.data() + gh.packed_off);
+    for (uint32_t r = 0; r < n; ++r) {
+        const iss_record &rec = records[r];
+        memcpy(blob.data() + gh.names_off + dr[r].name_off, rec.name, rec.name_len);
+        if (enc[r] == ISS_ENC_2BIT) {
+            const uint64_t b0 = dr[r].data_off;  // multiple of 64
+            uint32_t *w = packed + (b0 >> 4);
+            const uint64_t full = rec.len / 16;
+            for (uint64_t q = 0; q < full; ++q) {
+                const uint8_t *sp = rec.seq + q * 16;
+                uint32_t v = 0;
+                for (int m = 0; m < 16; ++m) v |= (uint32_t)((sp[m] >> 1) & 3u) << (2 * m);
+                w[q] = v;
+            }
+            uint32_t v = 0;
+            for (uint64_t k = full * 16; k < rec.len; ++k) v |= (uint32_t)((rec.seq[k] >> 1) & 3u) << (2 * (k & 15));
+            if (rec.len & 15) w[full] = v;
+        } else {
+            memcpy(blob.data() + gh.ascii_off + dr[r].data_off, rec.seq, rec.len);
+        }
+    }
+    if (c->d_genome) { cudaFree(c->d_genome); c->d_genome = nullptr; }
+    CU(cudaMalloc(&c->d_genome, off));
+    CU(cudaMemcpy(c->d_genome, blob.data(), off, cudaMemcpyHostToDevice));
+    c->genome_bytes = off;
+    c->stats.h2d_bytes += off;
+    return rebuild_views(c);
+}
+
+int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
+    if (!c || !m) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    if (c->active) return fail(ISS_E_STATE, "generation in progress");
+    const uint32_t L = m->read_length;
+    if (L < 2 || L > 8192) return fail(ISS_E_ARG, "read_length out of range [2, 8192]");
+    if (m->qual_mode > ISS_QUAL_TABLE) return fail(ISS_E_ARG, "bad qual_mode");
+    ModelHeader h{};
+    h.magic = kModelMagic;
+    h.L = L; h.qual_mode = m->qual_mode; h.n_insert = m->n_insert; h.frag_mode = m->frag_mode; h.n_frag = m->n_frag;
+    h.const_phred = m->const_phred; h.n_basic = m->n_basic; h.store_mutations = m->store_mutations;
+    h.fixed_insert = m->fixed_insert; h.frag_lo = m->frag_lo;
+    if (m->bin_thr) memcpy(h.bin_thr, m->bin_thr, sizeof h.bin_thr);
+    if (m->bin_valid) memcpy(h.bin_valid, m->bin_valid, sizeof h.bin_valid);
+    if (!m->err_thr) return fail(ISS_E_ARG, "err_thr is required");
+    memcpy(h.err_thr, m->err_thr, sizeof h.err_thr);
+    if (!m->subst_n || !m->subst_thr || !m->subst_alt || !m->ins_thr || !m->ins_nz || !m->ins_base || !m->del_thr || !m->del_nz)
+        return fail(ISS_E_ARG, "substitution / indel tables are required");
+    if (m->qual_mode == ISS_QUAL_KDE && (!m->qual_thr || !m->bin_thr || !m->bin_valid)) return fail(ISS_E_ARG, "kde tables missing");
+    if (m->n_insert && !m->insert_thr) return fail(ISS_E_ARG, "insert_thr missing");
+    // positions (< L-1: the indel loop runs over range(L-1)) with any non-zero threshold
+    std::vector<uint16_t> nzpos(2 * (size_t)L, 0);
+    for (int o = 0; o < 2; ++o) {
+        uint32_t cnt = 0;
+        for (uint32_t pos = 0; pos + 1 < L; ++pos)
+            if (m->ins_nz[o * L + pos] | m->del_nz[o * L + pos]) nzpos[o * L + cnt++] = (uint16_t)pos;
+        h.n_nz[o] = cnt;
+    }
+    uint64_t off = align_up(sizeof(ModelHeader), 16);
+    auto place = [&](uint64_t bytes) { uint64_t at = off; off = align_up(off + std::max<uint64_t>(bytes, 16), 16); return at; };
+    const uint64_t qual_bytes = m->qual_mode == ISS_QUAL_KDE ? 2ull * 4 * L * ISS_QROW * 4 : 0;
+    h.frag_thr_off = place(8ull * m->n_frag);
+    h.insert_thr_off = place(4ull * m->n_insert);
+    h.qual_thr_off = place(qual_bytes);
+    h.subst_n_off = place(2ull * L * 4);
+    h.subst_thr_off = place(2ull * L * 4 * ISS_MAX_ALT * 8);
+    h.subst_alt_off = place(2ull * L * 4 * ISS_MAX_ALT);
+    h.ins_thr_off = place(2ull * L * 4 * 4);
+    h.ins_nz_off = place(2ull * L);
+    h.ins_base_off = place(2ull * L * 4);
+    h.del_thr_off = place(2ull * L * 4 * 4);
+    h.del_nz_off = place(2ull * L);
+    h.nzpos_off = place(2ull * L * 2);
+    h.basic_thr_off = place(4ull * m->n_basic);
+    h.basic_val_off = place(1ull * m->n_basic + 1);
+    h.total_bytes = off;
+    std::vector<uint8_t> blob(off, 0);
+    memcpy(blob.data(), &h, sizeof h);
+    auto put = [&](uint64_t at, const void *src, uint64_t bytes) { if (src && bytes) memcpy(blob.data() + at, src, bytes); };
+    put(h.frag_thr_off, m->frag_thr, 8ull * m->n_frag);
+    put(h.insert_thr_off, m->insert_thr, 4ull * m->n_insert);
+    put(h.qual_thr_off, m->qual_thr, qual_bytes);
+    put(h.subst_n_off, m->subst_n, 2ull * L * 4);
+    put(h.subst_thr_off, m->subst_thr, 2ull * L * 4 * ISS_MAX_ALT * 8);
+    put(h.subst_alt_off, m->subst_alt, 2ull * L * 4 * ISS_MAX_ALT);
+    put(h.ins_thr_off, m->ins_thr, 2ull * L * 4 * 4);
+    put(h.ins_nz_off, m->ins_nz, 2ull * L);
+    put(h.ins_base_off, m->ins_base, 2ull * L * 4);
+    put(h.del_thr_off, m->del_thr, 2ull * L * 4 * 4);
+    put(h.del_nz_off, m->del_nz, 2ull * L);
+    put(h.nzpos_off, nzpos.data(), 2ull * L * 2);
+    put(h.basic_thr_off, m->basic_thr, 4ull * m->n_basic);
+    put(h.basic_val_off, m->basic_val, 1ull * m->n_basic + (m->basic_val ? 1 : 0));
+    if (c->d_model) { cudaFree(c->d_model); c->d_model = nullptr; }
+    CU(cudaMalloc(&c->d_model, off));
+    CU(cudaMemcpy(c->d_model, blob.data(), off, cudaMemcpyHostToDevice));
+    c->model_bytes = off;
+    c->stats.h2d_bytes += off;
+    return rebuild_views(c);
+}
+
+// ---- NCCL ------------------------------------------------------------------------------------------
+int iss_comm_unique_id(uint8_t id[ISS_UNIQUE_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) <= ISS_UNIQUE_ID_BYTES, "unique id size");
+    ncclUniqueId u;
+    NC(ncclGetUniqueId(&u));
+    memset(id, 0, ISS_UNIQUE_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return ISS_OK;
+}
+
+int iss_comm_init_rank(iss_ctx *c, int nranks, int rank, const uint8_t id[ISS_UNIQUE_ID_BYTES]) {
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ISS_E_ARG, "bad communicator arguments");
+    if (int rc = set_device(c)) return rc;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NC(ncclCommInitRank(&c->comm, nranks, u, rank));
+    c->nranks = nranks;
+    c->rank = rank;
+    return ISS_OK;
+}
+
+int iss_comm_init_all(iss_ctx **ctxs, int n) {
+    if (!ctxs || n < 1) return fail(ISS_E_ARG, "bad arguments");
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+    NC(ncclCommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; ++i) { ctxs[i]->comm = comms[i]; ctxs[i]->nranks = n; ctxs[i]->rank = i; }
+    return ISS_OK;
+}
+
+int iss_ctx_bcast_all(iss_ctx **ctxs, int n, int root) {
+    if (!ctxs || n < 1 || root < 0) return fail(ISS_E_ARG, "bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (!ctxs[i] || !ctxs[i]->comm) return fail(ISS_E_STATE, "communicator not initialised");
+    // 1. sizes
+    std::vector<uint64_t *> d_sizes(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        iss_ctx *c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        CU(cudaMalloc(&d_sizes[i], 16));
+        const bool is_root = (c->rank == root);
+        if (is_root) {
+            if (!c->have_genome || !c->have_model) return fail(ISS_E_STATE, "root has no genome/model");
+            uint64_t sz[2] = {c->genome_bytes, c->model_bytes};
+            CU(cudaMemcpy(d_sizes[i], sz, 16, cudaMemcpyHostToDevice));
+        }
+    }
+    NC(ncclGroupStart());
+    for (int i = 0; i < n; ++i) {
+        CU(cudaSetDevice(ctxs[i]->device));
+        NC(ncclBroadcast(d_sizes[i], d_sizes[i], 16, ncclUint8, root, ctxs[i]->comm, 0));
+    }
+    NC(ncclGroupEnd());
+    for (int i = 0; i < n; ++i) {
+        iss_ctx *c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(0));
+        uint64_t sz[2];
+        CU(cudaMemcpy(sz, d_sizes[i], 16, cudaMemcpyDeviceToHost));
+        CU(cudaFree(d_sizes[i]));
+        const bool is_root = (c->rank == root);
+        if (!is_root) {
+            if (c->d_genome) { cudaFree(c->d_genome); c->d_genome = nullptr; }
+            if (c->d_model) { cudaFree(c->d_model); c->d_model = nullptr; }
+            CU(cudaMalloc(&c->d_genome, sz[0]));
+            CU(cudaMalloc(&c->d_model, sz[1]));
+            c->genome_bytes = sz[0];
+            c->model_bytes = sz[1];
+        }
+    }
+    // 2. blobs
+    NC(ncclGroupStart());
+    for (int i = 0; i < n; ++i) {
+        iss_ctx *c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        NC(ncclBroadcast(c->d_genome, c->d_genome, c->genome_bytes, ncclUint8, root, c->comm, 0));
+        NC(ncclBroadcast(c->d_model, c->d_model, c->model_bytes, ncclUint8, root, c->comm, 0));
+    }
+    NC(ncclGroupEnd());
+    for (int i = 0; i < n; ++i) {
+        iss_ctx *c = ctxs[i];
+        CU(cudaSetDevice(c->device));
+        CU(cudaStreamSynchronize(0));
+        if (int rc = rebuild_views(c)) return rc;
+    }
+    return ISS_OK;
+}
+
+int iss_ctx_bcast(iss_ctx *c, int root) { return iss_ctx_bcast_all(&c, 1, root); }
+
+// ---- generation ------------------------------------------------------------------------------------
+int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, const iss_gen_opts *opts) {
+    if (!c || (!items && n_items)) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    if (!c->have_genome || !c->have_model) return fail(ISS_E_STATE, "set_genome and set_model (or bcast) first");
+    if (c->active) return fail(ISS_E_STATE, "previous submit not drained");
+    const uint32_t L = c->mh.L;
+    iss_gen_opts o{};
+    if (opts) o = *opts;
+    if (o.batch_pairs == 0) o.batch_pairs = 1u << 18;
+    if (o.n_slots == 0) o.n_slots = 3;
+    if (o.n_slots < 2 && !o.device_only) o.n_slots = 2;
+    if (o.n_slots > 16) o.n_slots = 16;
+    uint64_t max_rec = 0, total = 0;
+    for (uint64_t k = 0; k < n_items; ++k) {
+        const iss_work_item &it = items[k];
+        if (it.record >= c->recs.size()) return fail(ISS_E_ARG, "work item references an unknown record");
+        const HostRecord &hr = c->recs[it.record];
+        if (!(L < hr.len)) return fail(ISS_E_SHORT, "record not longer than the read length (reference: AssertionError)");
+        if (it.n_pairs == 0) continue;
+        const uint64_t rec = record_fixed_len(L, hr.name_len, it.cpu_number) + iss_digits(it.i0 + it.n_pairs - 1);
+        max_rec = std::max(max_rec, rec);
+        total += it.n_pairs;
+    }
+    c->items.assign(items, items + n_items);
+    c->opts = o;
+    c->cur_item = 0; c->cur_off = 0;
+    c->next_launch = 0; c->next_return = 0;
+    c->exhausted = (total == 0);
+    if (total == 0) { c->active = true; return ISS_OK; }
+    const uint64_t batch_pairs = std::min<uint64_t>(o.batch_pairs, total);
+    // tile geometry: T pairs per CTA so that both stream images + bookkeeping fit in shared memory
+    uint32_t T = 64;
+    uint32_t img_cap = 0;
+    size_t smem = 0;
+    for (;; T -= 32) {
+        img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
+        smem = iss_tile_smem_bytes(T, img_cap, c->err_cap);
+        if (smem <= kMaxSmem) break;
+        if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
+    }
+    int bps = 0;
+    CU(iss_occupancy(T, smem, &bps));
+    if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
+    const uint32_t grid = (uint32_t)(c->sm_count * bps);
+    const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
+    const uint32_t max_segs = 1u << 16;
+    const bool realloc = c->slots.size() != o.n_slots || c->slot_cap < slot_cap || c->max_segs != max_segs ||
+                         (bool)c->opts.device_only != (c->slots.size() && c->slots[0].h_out[0] == nullptr);
+    if (realloc) {
+        free_slots(c);
+        c->slots.resize(o.n_slots);
+        for (auto &s : c->slots) {
+            CU(cudaMalloc(&s.d_out[0], slot_cap));
+            CU(cudaMalloc(&s.d_out[1], slot_cap));
+            if (!o.device_only) {
+                CU(cudaMallocHost(&s.h_out[0], slot_cap));
+                CU(cudaMallocHost(&s.h_out[1], slot_cap));
+            }
+            CU(cudaMalloc(&s.d_segs, sizeof(DevSegment) * max_segs));
+            CU(cudaMallocHost(&s.h_segs, sizeof(DevSegment) * max_segs));
+            CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CU(cudaEventCreate(&s.ev_k0));
+            CU(cudaEventCreate(&s.ev_k1));
+            CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        }
+        c->slot_cap = slot_cap;
+        c->max_segs = max_segs;
+    }
+    for (auto &s : c->slots) s.state = 0;
+    const uint64_t scratch = (uint64_t)grid * ISS_SLOW_SLOTS * align_up(5ull * L + 8, 16);
+    if (scratch > c->scratch_bytes) {
+        if (c->d_scratch) cudaFree(c->d_scratch);
+        CU(cudaMalloc(&c->d_scratch, scratch));
+        c->scratch_bytes = scratch;
+    }
+    c->batch_pairs = batch_pairs;
+    c->max_rec = max_rec;
+    c->tile_pairs = T;
+    c->img_cap = img_cap;
+    c->smem = smem;
+    c->grid = grid;
+    c->n_slots = o.n_slots;
+    c->active = true;
+    // prime the ring
+    for (uint32_t si = 0; si < c->n_slots && !c->exhausted; ++si)
+        if (int rc = launch_batch(c, si)) return rc;
+    return ISS_OK;
+}
+
+int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
+    if (!c || !b || !have) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    *have = 0;
+    if (!c->active) return fail(ISS_E_STATE, "no submit in progress");
+    if (c->next_return == c->next_launch) {  // nothing in flight
+        if (c->exhausted) {
+            c->active = false;
+            unsigned long long cnt[4];
+            CU(cudaMemcpy(cnt, c->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));
+            c->stats.slow_reads = cnt[0];
+            c->stats.subst_errors = cnt[1];
+            if (cnt[2]) {
+                CU(cudaMemset(c->d_counters + 2, 0, sizeof(unsigned long long)));
+                char buf[128];
+                snprintf(buf, sizeof buf, "device error flags 0x%llx (1 window out of range, 2 empty quality bin, 4 bad character)", cnt[2]);
+                return fail(ISS_E_DEVICE, buf);
+            }
+            return ISS_OK;
+        }
+        return fail(ISS_E_STATE, "all slots are held by the consumer: release a batch first");
+    }
+    const uint32_t si = (uint32_t)(c->next_return % c->n_slots);
+    Slot &s = c->slots[si];
+    if (s.state != 1 || s.batch_index != c->next_return) return fail(ISS_E_STATE, "internal: ring out of order");
+    CU(cudaEventSynchronize(s.ev_done));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    c->stats.kernel_ms += ms;
+    s.state = 2;
+    b->r1 = c->opts.device_only ? s.d_out[0] : s.h_out[0];
+    b->r2 = c->opts.device_only ? s.d_out[1] : s.h_out[1];
+    b->nbytes = s.nbytes;
+    b->vcf = nullptr;
+    b->vcf_bytes = 0;
+    b->n_pairs = s.n_pairs;
+    b->first_item = s.first_item;
+    b->batch_index = s.batch_index;
+    b->slot = si;
+    b->kernel_ms = ms;
+    c->next_return++;
+    *have = 1;
+    return ISS_OK;
+}
+
+int iss_ctx_release(iss_ctx *c, const iss_batch *b) {
+    if (!c || !b) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    if (b->slot >= c->slots.size() || c->slots[b->slot].state != 2) return fail(ISS_E_STATE, "batch is not held");
+    c->slots[b->slot].state = 0;
+    if (c->active && !c->exhausted) return launch_batch(c, b->slot);
+    return ISS_OK;
+}
+
+int iss_ctx_stats(iss_ctx *c, iss_stats *out) {
+    if (!c || !out) return fail(ISS_E_ARG, "null argument");
+    *out = c->stats;
+    return ISS_OK;
+}
+
+uint64_t iss_fastq_bytes(uint32_t name_len, uint64_t cpu, uint32_t L, uint64_t i0, uint64_t i1) {
+    const uint32_t fixed = record_fixed_len(L, name_len, (uint32_t)cpu);
+    return iss_cf(i1, fixed) - iss_cf(i0, fixed);
+}
+
+int iss_ctx_philox(iss_ctx *c, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!c) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    uint32_t *d = nullptr;
+    CU(cudaMalloc(&d, 16));
+    CU(iss_launch_philox(ctr, key, d, 0));
+    CU(cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost));
+    CU(cudaFree(d));
+    return ISS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+"""Python face of the native engine: one `Engine` == one `iss_ctx` == one GPU.
+
+    eng = Engine(device=0)
+    eng.set_genome([(record_id, sequence_bytes), ...])
+    eng.set_model(KDErrorModel(path))
+    for batch in eng.generate(items):          # finished FASTQ text, in submit order
+        f1.write(batch.r1); f2.write(batch.r2)  # views into the pinned ring slot, valid until the next step
+"""
+import ctypes
+import logging
+
+import numpy as np
+
+from . import _lib
+
+MASK64 = 0xFFFFFFFFFFFFFFFF
+
+
+def philox_key(seed, cpu_number):
+    """Philox key of a worker: the reference seeds worker c with seed + c (iss/generator.py:234-236)."""
+    return (int(seed) + int(cpu_number)) & MASK64
+
+
+class Batch(object):
+    __slots__ = ("r1", "r2", "vcf", "n_pairs", "nbytes", "first_item", "index", "kernel_ms", "_c")
+
+    def __init__(self, c, device_only):
+        self._c = c
+        self.nbytes = int(c.nbytes)
+        self.n_pairs = int(c.n_pairs)
+        self.first_item = int(c.first_item)
+        self.index = int(c.batch_index)
+        self.kernel_ms = float(c.kernel_ms)
+        self.vcf = None
+        if device_only or not self.nbytes:
+            self.r1 = self.r2 = None
+        else:
+            self.r1 = np.ctypeslib.as_array(ctypes.cast(c.r1, _lib.u8p), shape=(self.nbytes,))
+            self.r2 = np.ctypeslib.as_array(ctypes.cast(c.r2, _lib.u8p), shape=(self.nbytes,))
+        if c.vcf and c.vcf_bytes:
+            self.vcf = np.ctypeslib.as_array(ctypes.cast(c.vcf, _lib.u8p), shape=(int(c.vcf_bytes),))
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self._lib.iss_ctx_create(int(device), ctypes.byref(h)))
+        self._h = h
+        self.device = int(device)
+        self.read_length = None
+        self.record_names = []
+        self.record_lengths = []
+        self.logger = logging.getLogger(__name__)
+
+    # -- lifecycle ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.iss_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    # -- inputs ---------------------------------------------------------------------------------------
+    def set_genome(self, records):
+        """records: iterable of (record_id, sequence) with sequence as bytes/str (ASCII, case preserved)."""
+        recs = []
+        keep = []
+        for name, seq in records:
+            if isinstance(seq, str):
+                seq = seq.encode("ascii")
+            if isinstance(name, str):
+                name = name.encode()
+            buf = np.frombuffer(seq, dtype=np.uint8)
+            keep.append((buf, name))
+            recs.append((buf.ctypes.data if len(buf) else None, len(buf), name, len(name)))
+        arr = (_lib.IssRecord * max(len(recs), 1))()
+        for k, (ptr, ln, name, nl) in enumerate(recs):
+            arr[k].seq = ptr
+            arr[k].len = ln
+            arr[k].name = name
+            arr[k].name_len = nl
+        _lib.check(self._lib.iss_ctx_set_genome(self._h, arr, len(recs)))
+        self.record_names = [n.decode() for _, n in keep]
+        self.record_lengths = [len(b) for b, _ in keep]
+
+    def set_model(self, model):
+        tables = model.device_tables()
+        cm = tables.c_struct()
+        _lib.check(self._lib.iss_ctx_set_model(self._h, ctypes.byref(cm)))
+        self.read_length = int(model.read_length)
+        self._tables = tables
+
+    # -- multi-GPU --------------------------------------------------------------------------------------
+    @staticmethod
+    def unique_id():
+        buf = (ctypes.c_uint8 * _lib.ISS_UNIQUE_ID_BYTES)()
+        _lib.check(_lib.load().iss_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init_rank(self, nranks, rank, unique_id):
+        buf = (ctypes.c_uint8 * _lib.ISS_UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _lib.check(self._lib.iss_comm_init_rank(self._h, int(nranks), int(rank), buf))
+
+    def bcast(self, root=0, read_length=None, record_names=None, record_lengths=None):
+        """ncclBroadcast of the genome + model blobs from `root`.  Host-side metadata (names, lengths, L) that a
+        non-root rank needs for planning travels with the caller (it is tiny) -- see parallel.py."""
+        _lib.check(self._lib.iss_ctx_bcast(self._h, int(root)))
+        if read_length is not None:
+            self.read_length = int(read_length)
+        if record_names is not None:
+            self.record_names = list(record_names)
+            self.record_lengths = list(record_lengths)
+
+    @staticmethod
+    def comm_init_all(engines):
+        arr = (ctypes.c_void_p * len(engines))(*[e._h for e in engines])
+        _lib.check(_lib.load().iss_comm_init_all(arr, len(engines)))
+
+    @staticmethod
+    def bcast_all(engines, root=0):
+        arr = (ctypes.c_void_p * len(engines))(*[e._h for e in engines])
+        _lib.check(_lib.load().iss_ctx_bcast_all(arr, len(engines), int(root)))
+        src = engines[root]
+        for e in engines:
+            e.read_length = src.read_length
+            e.record_names = list(src.record_names)
+            e.record_lengths = list(src.record_lengths)
+
+    # -- generation -------------------------------------------------------------------------------------
+    def submit(self, items, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0, device_only=False):
+        """items: iterable of dicts/tuples (record, cpu_number, n_pairs, i0, item_base, key)."""
+        items = list(items)
+        arr = (_lib.IssWorkItem * max(len(items), 1))()
+        for k, it in enumerate(items):
+            rec, cpu, n, i0, base, key = it
+            arr[k].record = rec
+            arr[k].cpu_number = cpu
+            arr[k].n_pairs = n
+            arr[k].i0 = i0
+            arr[k].item_base = base
+            arr[k].key = key & MASK64
+        st = {"metagenomics": 0, "amplicon": 1}
+        if sequence_type not in st:
+            # generator.py:139 raises RuntimeError for the forward read of an unknown sequence type
+            raise RuntimeError("sequence type '%s' is not supported" % sequence_type)
+        opts = _lib.IssGenOpts(st[sequence_type], int(bool(gc_bias)), int(batch_pairs), int(n_slots), int(bool(device_only)))
+        self._device_only = bool(device_only)
+        _lib.check(self._lib.iss_ctx_submit(self._h, arr, len(items), ctypes.byref(opts)))
+
+    def batches(self):
+        b = _lib.IssBatch()
+        have = ctypes.c_int(0)
+        while True:
+            _lib.check(self._lib.iss_ctx_next(self._h, ctypes.byref(b), ctypes.byref(have)))
+            if not have.value:
+                return
+            try:
+                yield Batch(b, self._device_only)
+            finally:
+                _lib.check(self._lib.iss_ctx_release(self._h, ctypes.byref(b)))
+
+    def generate(self, items, **kw):
+        self.submit(items, **kw)
+        return self.batches()
+
+    def stats(self):
+        s = _lib.IssStats()
+        _lib.check(self._lib.iss_ctx_stats(self._h, ctypes.byref(s)))
+        return {k: getattr(s, k) for k, _ in _lib.IssStats._fields_}
+
+    def philox(self, ctr, key):
+        c = (ctypes.c_uint32 * 4)(*ctr)
+        k = (ctypes.c_uint32 * 2)(*key)
+        out = (ctypes.c_uint32 * 4)()
+        _lib.check(self._lib.iss_ctx_philox(self._h, c, k, out))
+        return tuple(int(x) for x in out)
+
+
+def worker_items(work, cpu_number, seed, record_lengths, read_length, logger=None, record_names=None):
+    """Work list of ONE worker [(record_index, n_pairs), ...] -> engine items, reproducing worker_iterator's
+    bookkeeping (iss/generator.py:223-251): P = (pairs of the preceding items) + i; a record that is not longer
+    than the read length is skipped with the reference's two warnings (generator.py:77-80)."""
+    key = philox_key(seed, cpu_number)
+    base = 0
+    items = []
+    for rec, n_pairs in work:
+        n_pairs = int(n_pairs)
+        if not (read_length < record_lengths[rec]):
+            if logger is not None and n_pairs > 0:
+                name = record_names[rec] if record_names else rec
+                logger.warning("%s shorter than read length for this ErrorModel" % name)
+                logger.warning("Skipping %s. You will have less reads than specified" % name)
+        elif n_pairs > 0:
+            items.append((int(rec), int(cpu_number), n_pairs, 0, base, key))
+        base += n_pairs
+    return items

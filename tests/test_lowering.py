@@ -1,0 +1,127 @@
+"""CPU tests of the host logic: exactness of the f64 -> integer-threshold lowering, the closed-form FASTQ
+offsets, the work bookkeeping, and that the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fixtures
+import oracle
+from insilicoseq_b200 import _lib, error_models
+from insilicoseq_b200 import engine as eng_mod
+
+TWO32 = 2.0 ** 32
+
+
+def _words_around(values):
+    """32-bit words at and next to every threshold, plus random ones."""
+    rng = np.random.RandomState(1)
+    v = np.asarray(values, dtype=np.float64).ravel()
+    near = np.concatenate([np.floor(v), np.floor(v) + 1, np.floor(v) - 1, np.ceil(v), np.ceil(v) + 1])
+    near = near[(near >= 0) & (near < TWO32)]
+    return np.unique(np.concatenate([near, rng.randint(0, 2 ** 32, size=2000, dtype=np.uint64).astype(np.float64),
+                                     [0, 1, TWO32 - 1]])).astype(np.uint64)
+
+
+@pytest.mark.parametrize("spec", ["profile:HiSeq", "models/miseq_150.npz", "models/stress20.npz"])
+def test_threshold_lowering_is_exact(spec):
+    path = fixtures.model_path(spec)
+    m = error_models.KDErrorModel(path)
+    t = m.device_tables().arrays
+    om = oracle.OracleModel(path)  # the f64 tables exactly as the reference holds them
+    L = int(m.read_length)
+    # insert size: searchsorted(cdf, u) 'left'
+    cdf = om.table("insert_cdf")
+    for w in _words_around(cdf * TWO32)[::7]:
+        u = float(w) * 2.0 ** -32
+        assert int(np.searchsorted(cdf, u)) == int((np.uint64(w) > t["insert_thr"].astype(np.uint64)).sum())
+    # quality rows (sampled) and the error test
+    qc = om.table("qual_cdf")
+    pp = om.table("phred_prob")
+    rng = np.random.RandomState(2)
+    for _ in range(60):
+        o, b, pos = rng.randint(2), rng.randint(4), rng.randint(L)
+        if not t["bin_valid"][o, b]:
+            continue
+        row = qc[o, b, pos]
+        for w in _words_around(row * TWO32)[::11]:
+            u = float(w) * 2.0 ** -32
+            assert int(np.searchsorted(row, u)) == int((np.uint64(w) > t["qual_thr"][o, b, pos].astype(np.uint64)).sum())
+    for q in range(om.nq + 1):
+        for w in _words_around([pp[q] * TWO32]):
+            assert (float(w) * 2.0 ** -32 > pp[q]) == (int(w) > int(t["err_thr"][q]))
+    # bins and substitution choices: 'right'
+    for o in range(2):
+        cdfb = om.table("bin_cdf")[o]
+        for w in _words_around(cdfb * TWO32):
+            u = float(w) * 2.0 ** -32
+            assert int(np.searchsorted(cdfb, u, side="right")) == int((np.uint64(w) >= t["bin_thr"][o]).sum())
+    # indel Bernoulli tests
+    ins_p = om.table("ins_p")
+    for o in range(2):
+        for pos in range(L):
+            for lane in range(4):
+                p = ins_p[o, pos, lane]
+                nz = (t["ins_nz"][o, pos] >> lane) & 1
+                for w in _words_around([p * TWO32])[:12]:
+                    assert (float(w) * 2.0 ** -32 < p) == bool(nz and int(w) <= int(t["ins_thr"][o, pos, lane]))
+
+
+def test_base_index_and_subst_alt_order():
+    m = error_models.KDErrorModel(fixtures.model_path("profile:NovaSeq"))
+    t = m.device_tables().arrays
+    for c, base in enumerate(error_models.BASES):
+        assert (ord(base) >> 1) & 3 == c and (ord(base.lower()) >> 1) & 3 == c
+        alts, probs = m.subst_choices_for[10][base]
+        assert [chr(x) for x in t["subst_alt"][0, 10, c, :3]] == list(alts)
+
+
+def test_all_bundled_profiles_lower():
+    for f in sorted(os.listdir(error_models.PROFILE_DIR)):
+        m = error_models.KDErrorModel(os.path.join(error_models.PROFILE_DIR, f))
+        t = m.device_tables()
+        assert t.scalars["read_length"] == int(m.read_length)
+        assert t.arrays["qual_thr"].shape == (2, 4, int(m.read_length), 64)
+
+
+def test_fragment_table_matches_oracle_side():
+    import patched_reference as pr
+
+    for mu, sd in [(420, 35), (1000, 10), (450, 0)]:
+        lo_a, t_a = error_models.fragment_table(mu, sd)
+        lo_b, t_b = pr.fragment_table(mu, sd)
+        assert lo_a == lo_b and np.array_equal(t_a, t_b)
+
+
+def test_worker_items_bookkeeping():
+    items = eng_mod.worker_items([(0, 5), (1, 3), (2, 0), (0, 4)], cpu_number=3, seed=7,
+                                 record_lengths=[1000, 100, 1000], read_length=126)
+    # record 1 is too short: skipped, but the pair ordinal still advances (RNG contract v1)
+    assert items == [(0, 3, 5, 0, 0, 10), (0, 3, 4, 0, 8, 10)]
+    assert eng_mod.philox_key(-5, 2) == (2 ** 64 - 3)
+
+
+def test_native_library_exports_every_declared_symbol():
+    L = _lib.load()  # builds in-tree if needed; loading needs no GPU
+    header = open(os.path.join(fixtures.ROOT, "include", "iss_b200.h")).read()
+    declared = set(re.findall(r"\b(iss_[a-z0-9_]+)\s*\(", header))
+    declared -= {"iss_ctx"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.iss_abi_version() == 1
+    for args in [(5, 0, 150, 0, 1234), (11, 17, 301, 95, 10050), (1, 123456, 20, 999990, 1000020)]:
+        assert L.iss_fastq_bytes(*args) == oracle.fastq_bytes(*args)
+
+
+def test_product_fails_loudly_without_gpu():
+    import ctypes
+
+    L = _lib.load()
+    n = ctypes.c_int(0)
+    rc = L.iss_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.NativeError):
+        eng_mod.Engine(0)
