@@ -180,6 +180,13 @@ typedef struct {
 } iss_stats;
 int iss_ctx_stats(iss_ctx *ctx, iss_stats *out);
 
+/* Device-timeline marks for benchmarking (CUDA events): a mark is ordered after ALL work enqueued so far on
+ * every stream of the context.  elapsed = ms between two marks (synchronises on the later one). */
+#define ISS_N_MARKS 4
+int iss_ctx_sync(iss_ctx *ctx);
+int iss_ctx_mark(iss_ctx *ctx, int idx);
+int iss_ctx_elapsed_ms(iss_ctx *ctx, int idx_from, int idx_to, float *ms);
+
 /* FASTQ bytes of pairs i0..i1-1 of one read file: sum of len("@{name}_{i}_{cpu}/1\n{seq}\n+\n{qual}\n") */
 uint64_t iss_fastq_bytes(uint32_t name_len, uint64_t cpu_number, uint32_t read_length, uint64_t i0, uint64_t i1);
 

@@ -75,6 +75,9 @@ EXPORTS = {
     "iss_ctx_next": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssBatch), ctypes.POINTER(ctypes.c_int)]),
     "iss_ctx_release": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssBatch)]),
     "iss_ctx_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssStats)]),
+    "iss_ctx_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "iss_ctx_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "iss_ctx_elapsed_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "iss_fastq_bytes": (ctypes.c_uint64, [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
                                           ctypes.c_uint64]),
     "iss_ctx_philox": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -94,6 +94,9 @@ struct iss_ctx {
     uint8_t *d_scratch = nullptr;
     uint64_t scratch_bytes = 0;
     unsigned long long *d_counters = nullptr;
+    // benchmarking marks
+    cudaStream_t tstream = nullptr;
+    cudaEvent_t marks[ISS_N_MARKS] = {nullptr, nullptr, nullptr, nullptr};
     // NCCL
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
@@ -305,6 +308,8 @@ void iss_ctx_destroy(iss_ctx *c) {
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->comm) ncclCommDestroy(c->comm);
+    for (auto &m : c->marks) if (m) cudaEventDestroy(m);
+    if (c->tstream) cudaStreamDestroy(c->tstream);
     delete c;
 }
 
@@ -686,6 +691,38 @@ int iss_ctx_release(iss_ctx *c, const iss_batch *b) {
     if (b->slot >= c->slots.size() || c->slots[b->slot].state != 2) return fail(ISS_E_STATE, "batch is not held");
     c->slots[b->slot].state = 0;
     if (c->active && !c->exhausted) return launch_batch(c, b->slot);
+    return ISS_OK;
+}
+
+int iss_ctx_sync(iss_ctx *c) {
+    if (!c) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    CU(cudaDeviceSynchronize());
+    return ISS_OK;
+}
+
+int iss_ctx_mark(iss_ctx *c, int idx) {
+    if (!c || idx < 0 || idx >= ISS_N_MARKS) return fail(ISS_E_ARG, "bad mark index");
+    if (int rc = set_device(c)) return rc;
+    if (!c->tstream) CU(cudaStreamCreateWithFlags(&c->tstream, cudaStreamNonBlocking));
+    if (!c->marks[idx]) CU(cudaEventCreate(&c->marks[idx]));
+    for (auto &s : c->slots) {  // order the mark after everything enqueued on the slot streams
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaEventRecord(e, s.stream));
+        CU(cudaStreamWaitEvent(c->tstream, e, 0));
+        CU(cudaEventDestroy(e));
+    }
+    CU(cudaEventRecord(c->marks[idx], c->tstream));
+    return ISS_OK;
+}
+
+int iss_ctx_elapsed_ms(iss_ctx *c, int a, int b, float *ms) {
+    if (!c || !ms || a < 0 || b < 0 || a >= ISS_N_MARKS || b >= ISS_N_MARKS || !c->marks[a] || !c->marks[b])
+        return fail(ISS_E_ARG, "bad mark index");
+    if (int rc = set_device(c)) return rc;
+    CU(cudaEventSynchronize(c->marks[b]));
+    CU(cudaEventElapsedTime(ms, c->marks[a], c->marks[b]));
     return ISS_OK;
 }
 

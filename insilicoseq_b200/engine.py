@@ -180,6 +180,17 @@ class Engine(object):
         _lib.check(self._lib.iss_ctx_stats(self._h, ctypes.byref(s)))
         return {k: getattr(s, k) for k, _ in _lib.IssStats._fields_}
 
+    def sync(self):
+        _lib.check(self._lib.iss_ctx_sync(self._h))
+
+    def mark(self, idx):
+        _lib.check(self._lib.iss_ctx_mark(self._h, int(idx)))
+
+    def elapsed_ms(self, a, b):
+        ms = ctypes.c_float(0)
+        _lib.check(self._lib.iss_ctx_elapsed_ms(self._h, int(a), int(b), ctypes.byref(ms)))
+        return float(ms.value)
+
     def philox(self, ctr, key):
         c = (ctypes.c_uint32 * 4)(*ctr)
         k = (ctypes.c_uint32 * 2)(*key)

@@ -241,6 +241,23 @@ class KDErrorModel(ErrorModel):
         self.del_rev = self.error_profile["del_reverse"]
         self.error_profile = ""  # discard the error profile after reading
 
+    def truncate(self, read_length):
+        """Shorten the model to its first `read_length` positions (the '150 bp' benchmark models of
+        BASELINE.md: read_length=N and every per-position array sliced [:N]; everything else verbatim)."""
+        n = int(read_length)
+        if not 2 <= n <= int(self.read_length):
+            raise ValueError("cannot truncate a %d bp model to %d" % (int(self.read_length), n))
+        self.read_length = np.int64(n)
+        for attr in ("quality_forward", "quality_reverse"):
+            q = getattr(self, attr)
+            out = np.empty(len(q), dtype=object)
+            for b in range(len(q)):
+                out[b] = list(q[b])[:n]
+            setattr(self, attr, out)
+        for attr in ("subst_choices_for", "subst_choices_rev", "ins_for", "ins_rev", "del_for", "del_rev"):
+            setattr(self, attr, getattr(self, attr)[:n])
+        return self
+
     def _lower_quality(self, t):
         L = int(self.read_length)
         ic = np.asarray(self.i_size_cdf, dtype=np.float64)
