@@ -180,20 +180,16 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step (default: the BASELINE workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from insilicoseq_b200 import parallel
+
+    rank, world, local = parallel.env_rank()
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
     if args.warmup < 3:
         args.warmup = 3
 
-    dist = None
-    if world > 1:
-        import torch.distributed as dist  # control plane only (gloo): ids, barriers, max over ranks
-
-        dist.init_process_group("gloo", rank=rank, world_size=world)
+    dist = parallel.init_control_plane(rank, world)  # gloo, control plane only: ids, barriers, max over ranks
 
     from insilicoseq_b200 import engine as eng_mod
     from insilicoseq_b200 import error_models
@@ -204,9 +200,8 @@ def main():
         eng.set_genome([(GENOME_NAME, make_genome())])
         eng.set_model(model)
     if world > 1:
-        uid = [eng_mod.Engine.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init_rank(world, rank, uid[0])
+        uid = parallel.share_from_root(dist, eng_mod.Engine.unique_id() if rank == 0 else None, rank)
+        eng.comm_init_rank(world, rank, uid)
         eng.bcast(0, read_length=READ_LEN, record_names=[GENOME_NAME], record_lengths=[GENOME_LEN])
     L = READ_LEN
     items = eng_mod.worker_items([(0, args.pairs)], rank, SEED, [GENOME_LEN], L)
@@ -224,13 +219,7 @@ def main():
             pass
 
     def reduce_max(x):
-        if dist is None:
-            return x
-        import torch
-
-        t = torch.tensor([x], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
+        return parallel.max_over_ranks(dist, x)
 
     def step_device():
         for _ in eng.generate(items, device_only=True, batch_pairs=2_500_000, n_slots=1):

@@ -1,0 +1,151 @@
+"""CPU tests of the host layer around the hot path: FASTA parsing, work division (against the live reference when
+it is mounted, and against a committed expectation otherwise), abundance draws, CLI parsing, and the
+world_size-2 sharding logic over gloo with the oracle standing in for the GPU."""
+import io
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import fixtures
+from insilicoseq_b200 import abundance, app, fasta, generator, parallel, util
+
+
+class _Model:
+    read_length = 126
+
+
+def _records():
+    return [fasta.Record(fixtures.synth_genome(300 + k, 3000 + 1700 * k).encode(), id="g%d" % k) for k in range(7)]
+
+
+def _chunks(n_reads, cpus, ab):
+    recs = _records()
+    chunk_size = -((n_reads // 2) // -cpus)
+    return [[(r.id, n) for r, n, _ in c]
+            for c in generator.generate_work_divider(recs, None, ab, n_reads, None, None, _Model(), "x", chunk_size)]
+
+
+def test_fasta_parse_roundtrip(tmp_path):
+    p = tmp_path / "a.fa"
+    p.write_text(">id1 some description\nACGT\nacgtNN\n\n>id2\nTTTT\n>\nGG\n")
+    recs = list(fasta.parse(str(p)))
+    assert [(r.id, r.seq) for r in recs] == [("id1", b"ACGTacgtNN"), ("id2", b"TTTT"), ("", b"GG")]
+    assert recs[0].description == "id1 some description"
+    out = io.StringIO()
+    fasta.write(recs[:2], out)
+    assert out.getvalue() == ">id1 some description\nACGTacgtNN\n>id2\nTTTT\n"
+    assert util.count_records(str(p)) == ["id1", "id2", ""]
+
+
+def test_convert_n_reads():
+    assert util.convert_n_reads("1000000") == 1000000
+    assert util.convert_n_reads("0.5M") == 500000
+    assert util.convert_n_reads("2k") == 2000 and util.convert_n_reads("1G") == 10 ** 9
+    with pytest.raises(SystemExit):
+        util.convert_n_reads("12x")
+
+
+def test_work_divider_expected():
+    np.random.seed(42)
+    ab = abundance.lognormal(["g%d" % k for k in range(7)])
+    got = _chunks(5000, 3, ab)
+    exp_path = os.path.join(fixtures.GOLDEN, "work_divider_expected.json")
+    exp = json.load(open(exp_path))
+    assert [[list(x) for x in c] for c in got] == exp["chunks"]
+    assert sum(n for c in got for _, n in c) in (2500, 2501)
+
+
+@pytest.mark.reference
+def test_work_divider_and_abundance_match_live_reference():
+    import patched_reference as pr
+
+    if not pr.reference_available():
+        pytest.skip("reference not mounted")
+    iss = pr.import_reference()
+    from iss import abundance as rab
+    from iss import generator as rgen
+
+    ids = ["g%d" % k for k in range(7)]
+    for name in ("uniform", "halfnormal", "exponential", "lognormal", "zero_inflated_lognormal"):
+        np.random.seed(7)
+        a = getattr(abundance, name)(ids)
+        np.random.seed(7)
+        b = getattr(rab, name)(ids)
+        assert a == b, name
+    np.random.seed(42)
+    ab = abundance.lognormal(ids)
+    recs = _records()
+    ref_recs = [pr.make_record(r.seq.decode(), r.id) for r in recs]
+    for n_reads, cpus in [(5000, 3), (1001, 2), (77, 8)]:
+        chunk_size = -((n_reads // 2) // -cpus)
+        ref = [[(r.id, n) for r, n, _ in c]
+               for c in rgen.generate_work_divider(ref_recs, None, ab, n_reads, None, None, _Model(), "x", chunk_size)]
+        assert _chunks(n_reads, cpus, ab) == ref
+
+
+def test_cli_accepts_the_reference_flags():
+    p = app.build_parser()
+    ns = p.parse_args(["generate", "--genomes", "a.fa", "b.fa", "--model", "NovaSeq", "-n", "1M", "--seed", "42",
+                       "--cpus", "8", "-o", "out", "--gc_bias", "-z", "--sequence_type", "amplicon", "--store_mutations",
+                       "--fragment-length", "400", "--fragment-length-sd", "20", "--abundance", "uniform"])
+    assert ns.genomes == ["a.fa", "b.fa"] and ns.cpus == 8 and ns.gc_bias and ns.compress and ns.store_mutations
+    assert ns.fragment_length == 400 and ns.fragment_length_sd == 20 and ns.sequence_type == "amplicon"
+    with pytest.raises(SystemExit):  # mutually exclusive abundance group, as in the reference
+        p.parse_args(["generate", "-o", "x", "--abundance_file", "a", "--coverage_file", "b"])
+
+
+def test_chunk_to_gpu_mapping_is_a_partition():
+    jobs = [(c, "w%d" % c) for c in range(11)]
+    for world in (1, 2, 3, 8):
+        parts = [parallel.rank_jobs(jobs, world, r) for r in range(world)]
+        assert sorted(j for p in parts for j in p) == jobs
+        merged = parallel.merge_in_chunk_order([[(c, ("%d," % c).encode()) for c, _ in p] for p in parts])
+        assert merged == b"".join(("%d," % c).encode() for c in range(11))
+
+
+GLOO_WORKER = r'''
+import os, sys, json, hashlib
+root = sys.argv[1]
+sys.path[:0] = [root, os.path.join(root, "oracle"), os.path.join(root, "tests")]
+import fixtures, oracle
+from insilicoseq_b200 import parallel, fasta, generator, abundance
+rank, world, _ = parallel.env_rank()
+dist = parallel.init_control_plane(rank, world)
+uid = parallel.share_from_root(dist, b"\x07" * 128 if rank == 0 else None, rank)   # stands in for the NCCL unique id
+assert uid == b"\x07" * 128
+class M: read_length = 126
+recs = [fasta.Record(fixtures.synth_genome(300 + k, 3000 + 1700 * k).encode(), id="g%d" % k) for k in range(4)]
+ab = abundance.uniform([r.id for r in recs])
+cpus, n_reads = 4, 600
+chunks = list(generator.generate_work_divider(recs, None, ab, n_reads, None, None, M(), "x", -((n_reads // 2) // -cpus)))
+jobs = list(enumerate(chunks))
+om = oracle.OracleModel(fixtures.model_path("profile:HiSeq"))
+mine = []
+for cpu, work in parallel.rank_jobs(jobs, world, rank):      # the oracle stands in for the GPU of this rank
+    r1, r2 = oracle.run_worker(om, [(r.id, r.seq, n) for r, n, _ in work], cpu, 11)
+    mine.append((cpu, r1))
+allparts = parallel.gather_to_root(dist, mine, rank, world)
+t = parallel.max_over_ranks(dist, 1.0 + rank)
+assert t == float(world)
+if rank == 0:
+    merged = parallel.merge_in_chunk_order(allparts)
+    single = b"".join(oracle.run_worker(om, [(r.id, r.seq, n) for r, n, _ in work], cpu, 11)[0] for cpu, work in jobs)
+    assert merged == single
+    print("GLOO_OK", hashlib.sha256(merged).hexdigest()[:12], len(merged))
+if dist is not None:
+    dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_sharding_over_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(script), fixtures.ROOT]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "GLOO_OK" in out.stdout
