@@ -284,9 +284,9 @@ def main():
             "vs_baseline": None, "dtype": "u32 (integer thresholds on Philox4x32 words; bytes out)", "data": "synthetic",
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": ms_e / args.steps,
-                    "h2d_bytes_per_step": (e1["h2d_bytes"] - e0["h2d_bytes"]) // args.steps,
-                    "d2h_bytes_per_step": (e1["d2h_bytes"] - e0["d2h_bytes"]) // args.steps,
-                    "d2h_GBps": (e1["d2h_bytes"] - e0["d2h_bytes"]) / (ms_e * 1e-3) / 1e9},
+                    "h2d_bytes_per_step": world * (e1["h2d_bytes"] - e0["h2d_bytes"]) // args.steps,
+                    "d2h_bytes_per_step": world * (e1["d2h_bytes"] - e0["d2h_bytes"]) // args.steps,
+                    "d2h_GBps_per_gpu": (e1["d2h_bytes"] - e0["d2h_bytes"]) / (ms_e * 1e-3) / 1e9},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "iss_generate_kernel",
