@@ -10,6 +10,7 @@
 
 #define ISS_QROW 64
 #define ISS_MAX_ALT 4
+#define ISS_QBT_STRIDE 96  // words per quality row in the device search-tree layout (see iss_kernels.cu)
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Slot schedule: DESIGN.md section 3 / oracle/philox.py.
@@ -98,7 +99,7 @@ struct DevModel {
     const ModelHeader *h;
     const uint64_t *frag_thr;
     const uint32_t *insert_thr;
-    const uint32_t *qual_thr;   // [2][4][L][64]
+    const uint32_t *qual_thr;   // [2][4][L][ISS_QBT_STRIDE] search-tree rows
     const uint8_t *subst_n;     // [2][L][4]
     const uint64_t *subst_thr;  // [2][L][4][4]
     const uint8_t *subst_alt;   // [2][L][4][4]
@@ -173,7 +174,8 @@ struct GenParams {
     uint32_t err_thr[ISS_QROW];
     const DevSegment *segs;
     uint32_t nseg;
-    uint32_t tile_pairs;      // T: pairs per tile; blockDim.x == 2T
+    uint32_t tile_pairs;      // T: pairs per tile (32 or 64); blockDim.x == 4T
+    uint32_t tile_shift;      // log2(T)
     uint64_t total_pairs;
     uint8_t *out1;
     uint8_t *out2;

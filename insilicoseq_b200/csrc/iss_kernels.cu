@@ -2,7 +2,8 @@
 //
 // One persistent kernel (iss_generate_kernel) produces finished FASTQ text for a batch of read pairs:
 //
-//   tile = T pairs (2T reads), blockDim = 2T, thread <-> read, warps are orientation-uniform
+//   tile = T pairs (2T reads), blockDim = 4T: thread <-> (pair, orientation, position half); a warp holds 32
+//   different pairs in the same role, so its lanes walk the model tables in lockstep
 //   phase 1  pair setup        insert size, window positions, quality bins        generator.py:121-177, kde.py:72-97
 //   phase 2  headers + gather  2-bit (or byte) genome windows -> ASCII in smem     generator.py:146-153,179-183, util.py:48-92
 //   phase 3  indel scan        Bernoulli tests in the no-event world; a read with  error_models/__init__.py:187-224
@@ -46,16 +47,20 @@ __device__ __forceinline__ uint32_t pick(const Philox4 &w, uint32_t j) {
 }
 __device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
-// #{j < 64 : w > row[j]} on a nondecreasing, 0xFFFFFFFF-padded row (searchsorted 'left')
-__device__ __forceinline__ uint32_t qrow_search(const uint32_t *__restrict__ row, uint32_t w) {
-    uint32_t lo = 0;
-    lo += (w > __ldg(row + 31)) ? 32u : 0u;
-    lo += (w > __ldg(row + lo + 15)) ? 16u : 0u;
-    lo += (w > __ldg(row + lo + 7)) ? 8u : 0u;
-    lo += (w > __ldg(row + lo + 3)) ? 4u : 0u;
-    lo += (w > __ldg(row + lo + 1)) ? 2u : 0u;
-    lo += (w > __ldg(row + lo)) ? 1u : 0u;
-    return lo;
+// Quality rows are stored as a 3-level 4-ary search tree (ISS_QBT_STRIDE words per row, built by the runtime):
+//   words  0..3   level 1: row[15], row[31], row[47], pad
+//   words  4..19  level 2: for each 16-entry group g: row[16g+3], row[16g+7], row[16g+11], pad
+//   words 32..95  the 64 leaves (0xFFFFFFFF padded)
+// #{j < 64 : w > row[j]} = 16*c1 + 4*c2 + c3 on a nondecreasing row: three dependent 16-byte loads.
+__device__ __forceinline__ uint32_t cnt3(uint32_t w, const uint4 &t) {
+    return (w > t.x ? 1u : 0u) + (w > t.y ? 1u : 0u) + (w > t.z ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t qbt_finish(const uint32_t *__restrict__ row, const uint4 &lvl1, uint32_t w) {
+    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
+    const uint32_t c1 = cnt3(w, lvl1);
+    const uint32_t c2 = cnt3(w, __ldg(r4 + 1 + c1));
+    const uint32_t c3 = cnt3(w, __ldg(r4 + 8 + 4u * c1 + c2));
+    return 16u * c1 + 4u * c2 + c3;
 }
 
 __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
@@ -80,6 +85,7 @@ struct TileSmem {
     uint32_t *sSeqOff;  // [2T] offset of the sequence line inside the stream image
     uint32_t *sEnc;     // [2T]
     uint32_t *sSlow;    // [2T]
+    uint32_t *sFlag;    // [2T] read already queued for the sequential indel replay
     uint32_t *sErr;     // [err_cap]
     uint32_t *sErrThr;  // [64]
     uint32_t *sCtl;     // [8]: 0 nErr, 1 nSlow, 2 tileBytes
@@ -103,6 +109,7 @@ __device__ __forceinline__ TileSmem carve(uint8_t *base, const GenParams &p) {
     s.sSeqOff = (uint32_t *)q; q += 8u * T;
     s.sEnc = (uint32_t *)q; q += 8u * T;
     s.sSlow = (uint32_t *)q; q += 8u * T;
+    s.sFlag = (uint32_t *)q; q += 8u * T;
     s.sErr = (uint32_t *)q; q += 4u * p.err_cap;
     s.sErrThr = (uint32_t *)q; q += 4u * ISS_QROW;
     s.sCtl = (uint32_t *)q;
@@ -203,13 +210,15 @@ __device__ void replay_indels(const GenParams &p, const TileSmem &s, uint32_t rd
 
 extern __shared__ __align__(16) uint8_t iss_smem[];
 
-__global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant__ GenParams p) {
+__global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const TileSmem s = carve(iss_smem, p);
     if (tid < ISS_QROW) s.sErrThr[tid] = p.err_thr[tid];
     const uint64_t ntiles = (p.total_pairs + T - 1) / T;
     bool store_pending = false;
-    const uint32_t o = tid >= T ? 1u : 0u, pair = tid - o * T;
+    // roles: q4 = 0..3 -> orientation o = q4 >> 1, position half = q4 & 1; rd = index of the read in the tile
+    const uint32_t q4 = tid >> p.tile_shift, pair = tid & (T - 1u);
+    const uint32_t o = q4 >> 1, half = q4 & 1u, rd = o * T + pair;
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t gp0 = tile * T;
@@ -221,6 +230,7 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
             if (store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             s.sCtl[0] = 0; s.sCtl[1] = 0;
         }
+        if (tid < 2u * T) s.sFlag[tid] = 0;
         __syncthreads();
 
         // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97)
@@ -291,8 +301,8 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
                 if (binr == 4) binr = 3;
                 if (!p.bin_valid[0][binf] || !p.bin_valid[1][binr]) atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_QUALBIN);
             }
-            s.sQrow[tid] = (binf * L) * ISS_QROW;
-            s.sQrow[T + tid] = ((4u + binr) * L) * ISS_QROW;
+            s.sQrow[tid] = (binf * L) * ISS_QBT_STRIDE;
+            s.sQrow[T + tid] = ((4u + binr) * L) * ISS_QBT_STRIDE;
             s.sP[tid] = P;
             s.sKey[tid] = key;
             s.sSeg[tid] = lo;
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
         const uint32_t tile_bytes = (uint32_t)(s.sOff[npairs - 1] - g0) + s.sCtl[3];
 
         // ---- phase 2a: record skeleton, one thread per read:  "@{name}_{i}_{cpu}/{1|2}\n" ... "\n+\n" ... "\n"
-        if (valid) {
+        if (valid && half == 0) {
             const DevSegment *sg = p.segs + s.sSeg[pair];
             uint8_t *img = s.img[o] + a0 + (uint32_t)(s.sOff[pair] - g0);
             const uint64_t i = s.sP[pair] - sg->item_base;
@@ -340,7 +350,7 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
             img[w++] = '/';
             img[w++] = (uint8_t)('1' + o);
             img[w++] = '\n';
-            s.sSeqOff[tid] = (uint32_t)(img - s.img[o]) + w;
+            s.sSeqOff[rd] = (uint32_t)(img - s.img[o]) + w;
             img[w + L] = '\n';
             img[w + L + 1] = '+';
             img[w + L + 2] = '\n';
@@ -383,35 +393,43 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
         }
         __syncthreads();
 
-        // ---- phase 3: indel scan in the no-event world (error_models/__init__.py:187-224)
+        // ---- phase 3: indel scan in the no-event world (error_models/__init__.py:187-224).  The pair's combined list
+        //      of non-zero positions (forward then reverse) is cut in four equal parts, one per thread of the pair.
         const uint64_t P = valid ? s.sP[pair] : 0, key = valid ? s.sKey[pair] : 0;
         const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
         const uint32_t att8 = valid ? (s.sAtt[pair] << 8) : 0;
-        uint8_t *seq = s.img[o] + (valid ? s.sSeqOff[tid] : 0);
-        const uint32_t nnz = p.n_nz[o];
-        if (valid && nnz) {
-            const uint32_t sIns = iss_read_stream(o, ISS_K_INS) | att8, sDel = iss_read_stream(o, ISS_K_DEL) | att8;
-            bool fired = false;
+        uint8_t *seq = s.img[o] + (valid ? s.sSeqOff[rd] : 0);
+        const uint32_t nnz_all = p.n_nz[0] + p.n_nz[1];
+        if (valid && nnz_all) {
+            const uint32_t n_begin = (q4 * nnz_all) >> 2, n_end = ((q4 + 1u) * nnz_all) >> 2;
+            uint32_t fired = 0;  // bit so set when read orientation so has an event
             uint32_t cached = 0xFFFFFFFFu;
             Philox4 dblk = {0, 0, 0, 0};
-            for (uint32_t n = 0; n < nnz && !fired; ++n) {
-                const uint32_t pos = p.m.nzpos[o * L + n];
-                const uint32_t c = seq[pos];
+            for (uint32_t n = n_begin; n < n_end; ++n) {
+                const uint32_t so = n >= p.n_nz[0] ? 1u : 0u;
+                if ((fired >> so) & 1u) continue;
+                const uint32_t pos = p.m.nzpos[so * L + (n - so * p.n_nz[0])];
+                const uint32_t c = (s.img[so] + s.sSeqOff[so * T + pair])[pos];
                 if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
-                const uint32_t tb = o * L + pos;
+                const uint32_t tb = so * L + pos;
                 const uint32_t m = p.m.ins_nz[tb];
+                bool hit = false;
                 if (m) {
-                    const Philox4 w = philox4x32_10(pos, sIns, Plo, Phi, k0, k1);
+                    const Philox4 w = philox4x32_10(pos, iss_read_stream(so, ISS_K_INS) | att8, Plo, Phi, k0, k1);
                     const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.ins_thr) + tb);
-                    fired |= ((m & 1u) && w.x <= t.x) | ((m & 2u) && w.y <= t.y) | ((m & 4u) && w.z <= t.z) | ((m & 8u) && w.w <= t.w);
+                    hit = ((m & 1u) && w.x <= t.x) | ((m & 2u) && w.y <= t.y) | ((m & 4u) && w.z <= t.z) | ((m & 8u) && w.w <= t.w);
                 }
                 const uint32_t code = base_code(c);
                 if ((p.m.del_nz[tb] >> code) & 1u) {
-                    if ((pos >> 2) != cached) { cached = pos >> 2; dblk = philox4x32_10(cached, sDel, Plo, Phi, k0, k1); }
-                    fired |= pick(dblk, pos & 3u) <= __ldg(p.m.del_thr + tb * 4 + code);
+                    const uint32_t ck = (so << 30) | (pos >> 2);
+                    if (ck != cached) { cached = ck; dblk = philox4x32_10(pos >> 2, iss_read_stream(so, ISS_K_DEL) | att8, Plo, Phi, k0, k1); }
+                    hit |= pick(dblk, pos & 3u) <= __ldg(p.m.del_thr + tb * 4 + code);
                 }
+                if (hit) fired |= 1u << so;
             }
-            if (fired) s.sSlow[atomicAdd(&s.sCtl[1], 1u)] = tid;
+            for (uint32_t so = 0; so < 2; ++so)
+                if (((fired >> so) & 1u) && atomicExch(&s.sFlag[so * T + pair], 1u) == 0u)
+                    s.sSlow[atomicAdd(&s.sCtl[1], 1u)] = so * T + pair;
         }
         __syncthreads();
         {
@@ -427,33 +445,48 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
             }
         }
 
-        // ---- phase 4: phred scores + substitution tests, one thread per read, lanes in lockstep on the position
+        // ---- phase 4: phred scores + substitution tests.  Thread (o, half) walks half of the read's Philox QUAL
+        //      blocks; the 32 lanes of a warp are 32 pairs at the same position, so they share <= 3 quality rows.
         if (valid) {
             uint8_t *qual = seq + L + 3;
             const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
-            const uint32_t nblk = (L + 1u) >> 1;
+            const uint32_t nblk = (L + 1u) >> 1, hb = (nblk + 1u) >> 1;
+            const uint32_t b_begin = half ? hb : 0u, b_end = half ? nblk : hb;
             if (p.qual_mode == ISS_QUAL_KDE_MODE) {
-                const uint32_t *rows = p.m.qual_thr + s.sQrow[tid];
-                for (uint32_t b = 0; b < nblk; ++b) {
-                    const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
+                const uint32_t *rows = p.m.qual_thr + s.sQrow[rd];
+                uint4 l1a = {0, 0, 0, 0}, l1b = {0, 0, 0, 0};
+                if (b_begin < b_end) {
+                    const uint32_t pa = 2u * b_begin, pb = (pa + 1u < L) ? pa + 1u : pa;
+                    l1a = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pa * ISS_QBT_STRIDE));
+                    l1b = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pb * ISS_QBT_STRIDE));
+                }
+                for (uint32_t b = b_begin; b < b_end; ++b) {
                     const uint32_t pos = 2u * b;
-                    const uint32_t q0 = qrow_search(rows + (size_t)pos * ISS_QROW, w.x);
+                    uint4 n1a = l1a, n1b = l1b;
+                    if (b + 1u < b_end) {  // level 1 of the next two rows is fetched before this step's dependent loads
+                        const uint32_t pa = pos + 2u, pb = (pa + 1u < L) ? pa + 1u : pa;
+                        n1a = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pa * ISS_QBT_STRIDE));
+                        n1b = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pb * ISS_QBT_STRIDE));
+                    }
+                    const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
+                    const uint32_t q0 = qbt_finish(rows + (size_t)pos * ISS_QBT_STRIDE, l1a, w.x);
                     qual[pos] = (uint8_t)(q0 + 33u);
                     if (w.y > s.sErrThr[q0]) {
                         const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
-                        if (slot < p.err_cap) s.sErr[slot] = (tid << 16) | pos; else apply_substitution(p, s, tid, pos);
+                        if (slot < p.err_cap) s.sErr[slot] = (rd << 16) | pos; else apply_substitution(p, s, rd, pos);
                     }
                     if (pos + 1u < L) {
-                        const uint32_t q1 = qrow_search(rows + (size_t)(pos + 1u) * ISS_QROW, w.z);
+                        const uint32_t q1 = qbt_finish(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, l1b, w.z);
                         qual[pos + 1u] = (uint8_t)(q1 + 33u);
                         if (w.w > s.sErrThr[q1]) {
                             const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
-                            if (slot < p.err_cap) s.sErr[slot] = (tid << 16) | (pos + 1u); else apply_substitution(p, s, tid, pos + 1u);
+                            if (slot < p.err_cap) s.sErr[slot] = (rd << 16) | (pos + 1u); else apply_substitution(p, s, rd, pos + 1u);
                         }
                     }
+                    l1a = n1a; l1b = n1b;
                 }
             } else {
-                for (uint32_t b = 0; b < nblk; ++b) {
+                for (uint32_t b = b_begin; b < b_end; ++b) {
                     const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
 #pragma unroll
                     for (uint32_t h = 0; h < 2; ++h) {
@@ -470,7 +503,7 @@ __global__ void __launch_bounds__(256) iss_generate_kernel(const __grid_constant
                         qual[pos] = (uint8_t)(q + 33u);
                         if (wt > s.sErrThr[q]) {
                             const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
-                            if (slot < p.err_cap) s.sErr[slot] = (tid << 16) | pos; else apply_substitution(p, s, tid, pos);
+                            if (slot < p.err_cap) s.sErr[slot] = (rd << 16) | pos; else apply_substitution(p, s, rd, pos);
                         }
                     }
                 }
@@ -538,7 +571,7 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 
 // ---- host-visible launch helpers --------------------------------------------------------------------
 size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) {
-    return 2ull * img_cap + 8ull * T * 4 + 16ull * T * 2 + 4ull * T * 2 + 8ull * T * 4 + 4ull * err_cap + 4ull * ISS_QROW + 32;
+    return 2ull * img_cap + 8ull * T * 4 + 16ull * T * 2 + 4ull * T * 2 + 8ull * T * 5 + 4ull * err_cap + 4ull * ISS_QROW + 32;
 }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
@@ -546,12 +579,12 @@ cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
 }
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
-    iss_generate_kernel<<<grid, 2 * p.tile_pairs, smem, stream>>>(p);
+    iss_generate_kernel<<<grid, 4 * p.tile_pairs, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t iss_occupancy(uint32_t T, size_t smem, int *blocks_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel, (int)(2 * T), smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel, (int)(4 * T), smem);
 }
 
 cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {
