@@ -127,7 +127,7 @@ struct DevSegment {
     uint64_t n;           // pairs in the segment
     uint64_t i0;          // pair index i of the first pair
     uint64_t item_base;   // P = item_base + i
-    uint64_t key;         // Philox key
+    uint64_t key;         // Philox key (uniform per launch: the planner cuts batches at key changes)
     uint64_t out_base;    // byte offset of pair i in the batch stream = out_base + cf(i)  (mod 2^64)
     uint32_t rec;
     uint32_t cpu;
@@ -177,6 +177,7 @@ struct GenParams {
     uint32_t tile_pairs;      // T: pairs per tile (32 or 64); blockDim.x == 4T
     uint32_t tile_shift;      // log2(T)
     uint64_t total_pairs;
+    uint64_t key;             // Philox key of every pair of this launch (a batch never spans two workers)
     uint8_t *out1;
     uint8_t *out2;
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)

@@ -24,6 +24,8 @@
 #include "iss_device.cuh"
 #include "iss_kernels.h"
 
+extern __shared__ __align__(16) uint8_t iss_smem[];
+
 namespace {
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,63 +73,66 @@ __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t en
     return __ldg(g.ascii + abs_pos);
 }
 
-struct TileSmem {
-    uint8_t *img[2];
-    uint64_t *sP;       // [T] pair ordinal
-    uint64_t *sKey;     // [T]
-    uint64_t *sOff;     // [T] byte offset of the pair's record in the batch stream
-    uint64_t *sWabs;    // [2T] absolute index (base or byte) of the window start in the genome array
-    uint64_t *sRecLen;  // [T] record length
-    uint64_t *sWin;     // [2T] window start inside the record (fs / rs)
-    uint32_t *sSeg;     // [T]
-    uint32_t *sAtt;     // [T]
-    uint32_t *sQrow;    // [2T] element offset of the read's quality rows
-    uint32_t *sSeqOff;  // [2T] offset of the sequence line inside the stream image
-    uint32_t *sEnc;     // [2T]
-    uint32_t *sSlow;    // [2T]
-    uint32_t *sFlag;    // [2T] read already queued for the sequential indel replay
-    uint32_t *sErr;     // [err_cap]
-    uint32_t *sErrThr;  // [64]
-    uint32_t *sCtl;     // [8]: 0 nErr, 1 nSlow, 2 tileBytes
+// Shared-memory layout of one tile, as byte offsets from iss_smem.  Offsets (not pointers) keep every access
+// provably in the shared window, so the compiler emits LDS/STS instead of generic LD/ST.
+struct Lay {
+    uint32_t img[2];   // FASTQ stream images (R1, R2)
+    uint32_t sP;       // u64[T]  pair ordinal
+    uint32_t sOff;     // u64[T]  byte offset of the pair's record in the batch stream
+    uint32_t sRecLen;  // u64[T]  record length
+    uint32_t sWabs;    // u64[2T] absolute index (base or byte) of the window start in the genome array
+    uint32_t sWin;     // u64[2T] window start inside the record (fs / rs)
+    uint32_t sSeg;     // u32[T]
+    uint32_t sAtt;     // u32[T]
+    uint32_t sQrow;    // u32[2T] element offset of the read's quality rows
+    uint32_t sSeqOff;  // u32[2T] offset of the sequence line inside the stream image
+    uint32_t sEnc;     // u32[2T]
+    uint32_t sSlow;    // u32[2T]
+    uint32_t sFlag;    // u32[2T] read already queued for the sequential indel replay
+    uint32_t sErr;     // u32[err_cap]
+    uint32_t sErrThr;  // u32[64]
+    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 3 bytes of the tile's last record
 };
 
-__device__ __forceinline__ TileSmem carve(uint8_t *base, const GenParams &p) {
-    TileSmem s;
+__device__ __forceinline__ Lay carve(const GenParams &p) {
+    Lay l;
     const uint32_t T = p.tile_pairs;
-    uint8_t *q = base;
-    s.img[0] = q; q += p.img_cap;
-    s.img[1] = q; q += p.img_cap;
-    s.sP = (uint64_t *)q; q += 8u * T;
-    s.sKey = (uint64_t *)q; q += 8u * T;
-    s.sOff = (uint64_t *)q; q += 8u * T;
-    s.sRecLen = (uint64_t *)q; q += 8u * T;
-    s.sWabs = (uint64_t *)q; q += 16u * T;
-    s.sWin = (uint64_t *)q; q += 16u * T;
-    s.sSeg = (uint32_t *)q; q += 4u * T;
-    s.sAtt = (uint32_t *)q; q += 4u * T;
-    s.sQrow = (uint32_t *)q; q += 8u * T;
-    s.sSeqOff = (uint32_t *)q; q += 8u * T;
-    s.sEnc = (uint32_t *)q; q += 8u * T;
-    s.sSlow = (uint32_t *)q; q += 8u * T;
-    s.sFlag = (uint32_t *)q; q += 8u * T;
-    s.sErr = (uint32_t *)q; q += 4u * p.err_cap;
-    s.sErrThr = (uint32_t *)q; q += 4u * ISS_QROW;
-    s.sCtl = (uint32_t *)q;
-    return s;
+    uint32_t q = 0;
+    l.img[0] = q; q += p.img_cap;
+    l.img[1] = q; q += p.img_cap;
+    l.sP = q; q += 8u * T;
+    l.sOff = q; q += 8u * T;
+    l.sRecLen = q; q += 8u * T;
+    l.sWabs = q; q += 16u * T;
+    l.sWin = q; q += 16u * T;
+    l.sSeg = q; q += 4u * T;
+    l.sAtt = q; q += 4u * T;
+    l.sQrow = q; q += 8u * T;
+    l.sSeqOff = q; q += 8u * T;
+    l.sEnc = q; q += 8u * T;
+    l.sSlow = q; q += 8u * T;
+    l.sFlag = q; q += 8u * T;
+    l.sErr = q; q += 4u * p.err_cap;
+    l.sErrThr = q; q += 4u * ISS_QROW;
+    l.sCtl = q;
+    return l;
 }
+__device__ __forceinline__ uint64_t *u64p(uint32_t off) { return reinterpret_cast<uint64_t *>(iss_smem + off); }
+__device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cast<uint32_t *>(iss_smem + off); }
+__device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
 
 // bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
 
 // ---- substitution of one (read, position) ---------------------------------------------------------
-__device__ __forceinline__ void apply_substitution(const GenParams &p, const TileSmem &s, uint32_t rd, uint32_t pos) {
+__device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay &l, uint32_t rd, uint32_t pos) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
-    uint8_t *seq = s.img[o] + s.sSeqOff[rd];
+    uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
     const uint32_t c = seq[pos];
     if (!is_acgt(c)) return;  // "RYWSMKHBVDN" are never substituted (__init__.py:94)
     const uint32_t code = base_code(c);
-    const uint64_t P = s.sP[pair], key = s.sKey[pair];
-    const Philox4 w = philox4x32_10(pos >> 2, iss_read_stream(o, ISS_K_SUBC) | (s.sAtt[pair] << 8), (uint32_t)P,
+    const uint64_t P = u64p(l.sP)[pair], key = p.key;
+    const Philox4 w = philox4x32_10(pos >> 2, iss_read_stream(o, ISS_K_SUBC) | (u32p(l.sAtt)[pair] << 8), (uint32_t)P,
                                     (uint32_t)(P >> 32), (uint32_t)key, (uint32_t)(key >> 32));
     const uint64_t r = pick(w, pos & 3u);
     const uint32_t e = ((o * L + pos) << 2) + code;
@@ -145,15 +150,15 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Til
 //   insertion at index nucl+1  == push on the LIFO (a later lane lands in front of an earlier one)
 //   pop(nucl)                  == drop cur; the next element takes index nucl WITHOUT being examined
 //   IndexError at seq[nucl]    == the stream is exhausted: nothing further is drawn
-__device__ void replay_indels(const GenParams &p, const TileSmem &s, uint32_t rd, uint8_t *scratch) {
+__device__ void replay_indels(const GenParams &p, const Lay &l, uint32_t rd, uint8_t *scratch) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
-    uint8_t *seq = s.img[o] + s.sSeqOff[rd];
+    uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
     uint8_t *orig = scratch;
     uint8_t *stk = scratch + L;
     for (uint32_t k = 0; k < L; ++k) orig[k] = seq[k];
-    const uint64_t P = s.sP[pair], key = s.sKey[pair];
-    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), att8 = s.sAtt[pair] << 8;
+    const uint64_t P = u64p(l.sP)[pair], key = p.key;
+    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), att8 = u32p(l.sAtt)[pair] << 8;
     const uint32_t sIns = iss_read_stream(o, ISS_K_INS) | att8, sDel = iss_read_stream(o, ISS_K_DEL) | att8;
     uint32_t sp = 0, k = 0, outlen = 0;
     for (uint32_t nucl = 0; nucl + 1 < L; ++nucl) {
@@ -187,9 +192,9 @@ __device__ void replay_indels(const GenParams &p, const TileSmem &s, uint32_t rd
         seq[outlen++] = (uint8_t)x;
     }
     if (outlen < L) {  // extension from the reference sequence (:141-155)
-        const uint32_t enc = s.sEnc[rd];
-        const uint64_t win = s.sWin[rd], reclen = s.sRecLen[pair];
-        const uint64_t rec_abs = s.sWabs[rd] - win;  // absolute index of the record's first base
+        const uint32_t enc = u32p(l.sEnc)[rd];
+        const uint64_t win = u64p(l.sWin)[rd], reclen = u64p(l.sRecLen)[pair];
+        const uint64_t rec_abs = u64p(l.sWabs)[rd] - win;  // absolute index of the record's first base
         uint32_t e = 0;
         while (outlen < L) {
             uint32_t ch;
@@ -208,12 +213,10 @@ __device__ void replay_indels(const GenParams &p, const TileSmem &s, uint32_t rd
 
 }  // namespace
 
-extern __shared__ __align__(16) uint8_t iss_smem[];
-
 __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
-    const TileSmem s = carve(iss_smem, p);
-    if (tid < ISS_QROW) s.sErrThr[tid] = p.err_thr[tid];
+    const Lay l = carve(p);
+    if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
     const uint64_t ntiles = (p.total_pairs + T - 1) / T;
     bool store_pending = false;
     // roles: q4 = 0..3 -> orientation o = q4 >> 1, position half = q4 & 1; rd = index of the read in the tile
@@ -228,9 +231,9 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
         // ---- phase 0: the previous tile's bulk stores must have finished READING shared memory
         if (tid == 0) {
             if (store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            s.sCtl[0] = 0; s.sCtl[1] = 0;
+            u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0;
         }
-        if (tid < 2u * T) s.sFlag[tid] = 0;
+        if (tid < 2u * T) u32p(l.sFlag)[tid] = 0;
         __syncthreads();
 
         // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97)
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             }
             const DevSegment *sg = p.segs + lo;
             const uint64_t i = sg->i0 + (gp - sg->pair_start);
-            const uint64_t P = sg->item_base + i, key = sg->key;
+            const uint64_t P = sg->item_base + i, key = p.key;
             const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
             const DevRecord *rec = p.g.recs + sg->rec;
             const int64_t len = (int64_t)rec->len;
@@ -301,33 +304,32 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 if (binr == 4) binr = 3;
                 if (!p.bin_valid[0][binf] || !p.bin_valid[1][binr]) atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_QUALBIN);
             }
-            s.sQrow[tid] = (binf * L) * ISS_QBT_STRIDE;
-            s.sQrow[T + tid] = ((4u + binr) * L) * ISS_QBT_STRIDE;
-            s.sP[tid] = P;
-            s.sKey[tid] = key;
-            s.sSeg[tid] = lo;
-            s.sAtt[tid] = att;
-            s.sRecLen[tid] = (uint64_t)len;
-            s.sWin[tid] = (uint64_t)fs;
-            s.sWin[T + tid] = (uint64_t)rs;
-            s.sWabs[tid] = rec->data_off + (uint64_t)fs;
-            s.sWabs[T + tid] = rec->data_off + (uint64_t)rs;
-            s.sEnc[tid] = rec->enc;
-            s.sEnc[T + tid] = rec->enc;
+            u32p(l.sQrow)[tid] = (binf * L) * ISS_QBT_STRIDE;
+            u32p(l.sQrow)[T + tid] = ((4u + binr) * L) * ISS_QBT_STRIDE;
+            u64p(l.sP)[tid] = P;
+            u32p(l.sSeg)[tid] = lo;
+            u32p(l.sAtt)[tid] = att;
+            u64p(l.sRecLen)[tid] = (uint64_t)len;
+            u64p(l.sWin)[tid] = (uint64_t)fs;
+            u64p(l.sWin)[T + tid] = (uint64_t)rs;
+            u64p(l.sWabs)[tid] = rec->data_off + (uint64_t)fs;
+            u64p(l.sWabs)[T + tid] = rec->data_off + (uint64_t)rs;
+            u32p(l.sEnc)[tid] = rec->enc;
+            u32p(l.sEnc)[T + tid] = rec->enc;
             const uint64_t off = sg->out_base + iss_cf(i, sg->fixed_len);
-            s.sOff[tid] = off;
-            if (tid == npairs - 1) s.sCtl[3] = sg->fixed_len + iss_digits(i);  // bytes of the last record
+            u64p(l.sOff)[tid] = off;
+            if (tid == npairs - 1) u32p(l.sCtl)[3] = sg->fixed_len + iss_digits(i);  // bytes of the last record
         }
         __syncthreads();
-        const uint64_t g0 = s.sOff[0];
+        const uint64_t g0 = u64p(l.sOff)[0];
         const uint32_t a0 = (uint32_t)(g0 & 15u);
-        const uint32_t tile_bytes = (uint32_t)(s.sOff[npairs - 1] - g0) + s.sCtl[3];
+        const uint32_t tile_bytes = (uint32_t)(u64p(l.sOff)[npairs - 1] - g0) + u32p(l.sCtl)[3];
 
         // ---- phase 2a: record skeleton, one thread per read:  "@{name}_{i}_{cpu}/{1|2}\n" ... "\n+\n" ... "\n"
         if (valid && half == 0) {
-            const DevSegment *sg = p.segs + s.sSeg[pair];
-            uint8_t *img = s.img[o] + a0 + (uint32_t)(s.sOff[pair] - g0);
-            const uint64_t i = s.sP[pair] - sg->item_base;
+            const DevSegment *sg = p.segs + u32p(l.sSeg)[pair];
+            uint8_t *img = imgp(l, o) + a0 + (uint32_t)(u64p(l.sOff)[pair] - g0);
+            const uint64_t i = u64p(l.sP)[pair] - sg->item_base;
             const DevRecord *rec = p.g.recs + sg->rec;
             uint32_t w = 0;
             img[w++] = '@';
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             img[w++] = '/';
             img[w++] = (uint8_t)('1' + o);
             img[w++] = '\n';
-            s.sSeqOff[rd] = (uint32_t)(img - s.img[o]) + w;
+            u32p(l.sSeqOff)[rd] = (uint32_t)(img - imgp(l, o)) + w;
             img[w + L] = '\n';
             img[w + L + 1] = '+';
             img[w + L + 2] = '\n';
@@ -366,9 +368,9 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 const uint32_t j = idx - rd * p.nchunk;
                 const uint32_t ro = rd >= T ? 1u : 0u, rp = rd - ro * T;
                 if (rp >= npairs) continue;
-                uint8_t *seq = s.img[ro] + s.sSeqOff[rd];
-                const uint64_t wabs = s.sWabs[rd];
-                if (s.sEnc[rd] == ISS_ENC_2BIT) {
+                uint8_t *seq = imgp(l, ro) + u32p(l.sSeqOff)[rd];
+                const uint64_t wabs = u64p(l.sWabs)[rd];
+                if (u32p(l.sEnc)[rd] == ISS_ENC_2BIT) {
                     const uint64_t q = ro ? (wabs + L - 16u * j - 16u) : (wabs + 16u * j);
                     const uint32_t wi = (uint32_t)(q >> 4), sh = ((uint32_t)q & 15u) * 2u;
                     const uint32_t w0 = __ldg(p.g.packed + wi), w1 = __ldg(p.g.packed + wi + 1);
@@ -395,10 +397,10 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
 
         // ---- phase 3: indel scan in the no-event world (error_models/__init__.py:187-224).  The pair's combined list
         //      of non-zero positions (forward then reverse) is cut in four equal parts, one per thread of the pair.
-        const uint64_t P = valid ? s.sP[pair] : 0, key = valid ? s.sKey[pair] : 0;
+        const uint64_t P = valid ? u64p(l.sP)[pair] : 0, key = p.key;
         const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
-        const uint32_t att8 = valid ? (s.sAtt[pair] << 8) : 0;
-        uint8_t *seq = s.img[o] + (valid ? s.sSeqOff[rd] : 0);
+        const uint32_t att8 = valid ? (u32p(l.sAtt)[pair] << 8) : 0;
+        uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
         const uint32_t nnz_all = p.n_nz[0] + p.n_nz[1];
         if (valid && nnz_all) {
             const uint32_t n_begin = (q4 * nnz_all) >> 2, n_end = ((q4 + 1u) * nnz_all) >> 2;
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 const uint32_t so = n >= p.n_nz[0] ? 1u : 0u;
                 if ((fired >> so) & 1u) continue;
                 const uint32_t pos = p.m.nzpos[so * L + (n - so * p.n_nz[0])];
-                const uint32_t c = (s.img[so] + s.sSeqOff[so * T + pair])[pos];
+                const uint32_t c = (imgp(l, so) + u32p(l.sSeqOff)[so * T + pair])[pos];
                 if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
                 const uint32_t tb = so * L + pos;
                 const uint32_t m = p.m.ins_nz[tb];
@@ -428,16 +430,16 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 if (hit) fired |= 1u << so;
             }
             for (uint32_t so = 0; so < 2; ++so)
-                if (((fired >> so) & 1u) && atomicExch(&s.sFlag[so * T + pair], 1u) == 0u)
-                    s.sSlow[atomicAdd(&s.sCtl[1], 1u)] = so * T + pair;
+                if (((fired >> so) & 1u) && atomicExch(&u32p(l.sFlag)[so * T + pair], 1u) == 0u)
+                    u32p(l.sSlow)[atomicAdd(&u32p(l.sCtl)[1], 1u)] = so * T + pair;
         }
         __syncthreads();
         {
-            const uint32_t nslow = s.sCtl[1];
+            const uint32_t nslow = u32p(l.sCtl)[1];
             if (nslow) {  // warp-uniform; rare for real models
                 for (uint32_t base = 0; base < nslow; base += ISS_SLOW_SLOTS) {
                     if (tid < ISS_SLOW_SLOTS && base + tid < nslow)
-                        replay_indels(p, s, s.sSlow[base + tid],
+                        replay_indels(p, l, u32p(l.sSlow)[base + tid],
                                       p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride);
                 }
                 __syncthreads();
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             const uint32_t nblk = (L + 1u) >> 1, hb = (nblk + 1u) >> 1;
             const uint32_t b_begin = half ? hb : 0u, b_end = half ? nblk : hb;
             if (p.qual_mode == ISS_QUAL_KDE_MODE) {
-                const uint32_t *rows = p.m.qual_thr + s.sQrow[rd];
+                const uint32_t *rows = p.m.qual_thr + u32p(l.sQrow)[rd];
                 uint4 l1a = {0, 0, 0, 0}, l1b = {0, 0, 0, 0};
                 if (b_begin < b_end) {
                     const uint32_t pa = 2u * b_begin, pb = (pa + 1u < L) ? pa + 1u : pa;
@@ -471,16 +473,16 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                     const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
                     const uint32_t q0 = qbt_finish(rows + (size_t)pos * ISS_QBT_STRIDE, l1a, w.x);
                     qual[pos] = (uint8_t)(q0 + 33u);
-                    if (w.y > s.sErrThr[q0]) {
-                        const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
-                        if (slot < p.err_cap) s.sErr[slot] = (rd << 16) | pos; else apply_substitution(p, s, rd, pos);
+                    if (w.y > u32p(l.sErrThr)[q0]) {
+                        const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                        if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, rd, pos);
                     }
                     if (pos + 1u < L) {
                         const uint32_t q1 = qbt_finish(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, l1b, w.z);
                         qual[pos + 1u] = (uint8_t)(q1 + 33u);
-                        if (w.w > s.sErrThr[q1]) {
-                            const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
-                            if (slot < p.err_cap) s.sErr[slot] = (rd << 16) | (pos + 1u); else apply_substitution(p, s, rd, pos + 1u);
+                        if (w.w > u32p(l.sErrThr)[q1]) {
+                            const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution(p, l, rd, pos + 1u);
                         }
                     }
                     l1a = n1a; l1b = n1b;
@@ -501,9 +503,9 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                             q = p.m.basic_val[a];
                         }
                         qual[pos] = (uint8_t)(q + 33u);
-                        if (wt > s.sErrThr[q]) {
-                            const uint32_t slot = atomicAdd(&s.sCtl[0], 1u);
-                            if (slot < p.err_cap) s.sErr[slot] = (rd << 16) | pos; else apply_substitution(p, s, rd, pos);
+                        if (wt > u32p(l.sErrThr)[q]) {
+                            const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, rd, pos);
                         }
                     }
                 }
@@ -513,11 +515,11 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
 
         // ---- phase 5: substitutions, compacted over the whole tile (error_models/__init__.py:95-109)
         {
-            const uint32_t nerr_all = s.sCtl[0];
+            const uint32_t nerr_all = u32p(l.sCtl)[0];
             const uint32_t nerr = nerr_all < p.err_cap ? nerr_all : p.err_cap;
             for (uint32_t e = tid; e < nerr; e += blockDim.x) {
-                const uint32_t v = s.sErr[e];
-                apply_substitution(p, s, v >> 16, v & 0xFFFFu);
+                const uint32_t v = u32p(l.sErr)[e];
+                apply_substitution(p, l, v >> 16, v & 0xFFFFu);
             }
             if (tid == 0 && nerr_all) atomicAdd(p.counters + 1, (unsigned long long)nerr_all);
         }
@@ -537,15 +539,15 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 const uint32_t st = idx >= edge ? 1u : 0u;
                 const uint32_t e = idx - st * edge;
                 const uint32_t byte = e < head ? e : (head + mid + (e - head));
-                (st ? p.out2 : p.out1)[g0 + byte] = s.img[st][a0 + byte];
+                (st ? p.out2 : p.out1)[g0 + byte] = imgp(l, st)[a0 + byte];
             }
 #ifndef ISS_NO_BULK_STORE
             if (tid == 0 && mid) {
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out1 + g0 + head),
-                             "r"(smem_addr(s.img[0] + a0 + head)), "r"(mid)
+                             "r"(smem_addr(imgp(l, 0) + a0 + head)), "r"(mid)
                              : "memory");
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out2 + g0 + head),
-                             "r"(smem_addr(s.img[1] + a0 + head)), "r"(mid)
+                             "r"(smem_addr(imgp(l, 1) + a0 + head)), "r"(mid)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 store_pending = true;
@@ -554,7 +556,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             for (uint32_t idx = tid; idx < 2u * (mid >> 4); idx += blockDim.x) {
                 const uint32_t st = idx >= (mid >> 4) ? 1u : 0u;
                 const uint32_t e = idx - st * (mid >> 4);
-                const uint4 v = *reinterpret_cast<const uint4 *>(s.img[st] + a0 + head + 16u * e);
+                const uint4 v = *reinterpret_cast<const uint4 *>(imgp(l, st) + a0 + head + 16u * e);
                 *reinterpret_cast<uint4 *>((st ? p.out2 : p.out1) + g0 + head + 16u * e) = v;
             }
 #endif
@@ -571,7 +573,7 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 
 // ---- host-visible launch helpers --------------------------------------------------------------------
 size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) {
-    return 2ull * img_cap + 8ull * T * 4 + 16ull * T * 2 + 4ull * T * 2 + 8ull * T * 5 + 4ull * err_cap + 4ull * ISS_QROW + 32;
+    return 2ull * img_cap + 8ull * T * 3 + 16ull * T * 2 + 4ull * T * 2 + 8ull * T * 5 + 4ull * err_cap + 4ull * ISS_QROW + 32;
 }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device

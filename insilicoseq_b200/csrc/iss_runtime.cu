@@ -189,10 +189,13 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     uint64_t pairs = 0, bytes = 0;
     uint32_t nseg = 0;
     const uint64_t first_item = c->cur_item;
+    uint64_t batch_key = 0;
     while (c->cur_item < c->items.size() && pairs < c->batch_pairs && nseg < c->max_segs) {
         const iss_work_item &it = c->items[c->cur_item];
         const uint64_t left = it.n_pairs - c->cur_off;
         if (left == 0) { c->cur_item++; c->cur_off = 0; continue; }
+        if (nseg == 0) batch_key = it.key;
+        else if (it.key != batch_key) break;  // one Philox key per launch: the key is a kernel parameter
         const uint64_t take = std::min(left, c->batch_pairs - pairs);
         const HostRecord &hr = c->recs[it.record];
         DevSegment &sg = s.h_segs[nseg];
@@ -232,6 +235,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.tile_pairs = c->tile_pairs;
     p.tile_shift = c->tile_pairs == 64 ? 6u : 5u;
     p.total_pairs = pairs;
+    p.key = batch_key;
     p.out1 = s.d_out[0];
     p.out2 = s.d_out[1];
     p.img_cap = c->img_cap;
