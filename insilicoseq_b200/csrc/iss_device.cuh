@@ -190,9 +190,15 @@ struct GenParams {
     uint32_t scratch_stride;  // >= 5L + 8
     uint32_t gc_thr;          // accept iff w < gc_thr  (ceil(0.90 * 2^32))
     unsigned long long *counters;  // [0] slow reads [1] substitution events [2] error flags
+    uint32_t store_mutations;
+    uint32_t pad0;
+    uint4 *events;                 // mutation records of this batch (--store_mutations)
+    unsigned long long *event_count;
+    unsigned long long event_cap;
 };
 
 #define ISS_SLOW_SLOTS 16
 #define ISS_DEVERR_RANGE 1u
 #define ISS_DEVERR_QUALBIN 2u
 #define ISS_DEVERR_CHAR 4u
+#define ISS_DEVERR_EVENTS 8u

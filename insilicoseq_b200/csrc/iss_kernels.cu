@@ -123,8 +123,25 @@ __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_
 
 // bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
 
+// ---- mutation events (--store_mutations, error_models/__init__.py:98-108,197-207,211-221) -------------------
+// One 16-byte record per VCF line, appended in arbitrary order; the host sorts by key and formats the text.
+//   key = pair (batch-local) << 20 | orientation << 19 | phase << 18 (0 indel loop, 1 substitutions) | position << 4 | order
+//   order: insertion lane 0..3, deletion 4 (the order the reference appends them inside one loop iteration)
+__device__ __forceinline__ void emit_event(const GenParams &p, uint64_t gpair, uint32_t o, uint32_t phase, uint32_t pos,
+                                           uint32_t order, uint32_t ref, uint32_t alt0, uint32_t alt1, uint32_t qual) {
+    const unsigned long long slot = atomicAdd(p.event_count, 1ull);
+    if (slot >= p.event_cap) { atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_EVENTS); return; }
+    const uint64_t key = (gpair << 20) | ((uint64_t)o << 19) | ((uint64_t)phase << 18) | ((uint64_t)pos << 4) | order;
+    uint4 e;
+    e.x = (uint32_t)key;
+    e.y = (uint32_t)(key >> 32);
+    e.z = ref | (alt0 << 8) | (alt1 << 16) | (qual << 24);
+    e.w = 0;
+    p.events[slot] = e;
+}
+
 // ---- substitution of one (read, position) ---------------------------------------------------------
-__device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay &l, uint32_t rd, uint32_t pos) {
+__device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rd, uint32_t pos) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
     uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
@@ -141,7 +158,15 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
     uint32_t idx = 0;
     for (uint32_t j = 0; j < na; ++j) idx += (r >= __ldg(thr + j)) ? 1u : 0u;
     if (idx >= na) idx = na - 1u;
-    seq[pos] = p.m.subst_alt[(size_t)e * ISS_MAX_ALT + idx];
+    const uint32_t alt = p.m.subst_alt[(size_t)e * ISS_MAX_ALT + idx];
+    if (p.store_mutations) {
+        // recorded only when the new base differs from the read BEFORE indels ("original", generator.py:155,186)
+        const uint64_t wabs = u64p(l.sWabs)[rd];
+        const uint32_t enc = u32p(l.sEnc)[rd];
+        const uint32_t orig = o ? complement_ascii(genome_ascii(p.g, enc, wabs + (L - 1u - pos))) : genome_ascii(p.g, enc, wabs + pos);
+        if (alt != orig) emit_event(p, gp0 + pair, o, 1u, pos, 0u, c, alt, 0u, (uint32_t)seq[L + 3u + pos] - 33u);
+    }
+    seq[pos] = (uint8_t)alt;
 }
 
 // ---- sequential replay of introduce_indels + adjust_seq_length for one read ---------------------------
@@ -150,7 +175,7 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
 //   insertion at index nucl+1  == push on the LIFO (a later lane lands in front of an earlier one)
 //   pop(nucl)                  == drop cur; the next element takes index nucl WITHOUT being examined
 //   IndexError at seq[nucl]    == the stream is exhausted: nothing further is drawn
-__device__ void replay_indels(const GenParams &p, const Lay &l, uint32_t rd, uint8_t *scratch) {
+__device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rd, uint8_t *scratch) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
     uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
@@ -170,7 +195,11 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint32_t rd, uin
         if (m) {
             const Philox4 w = philox4x32_10(nucl, sIns, (uint32_t)P, (uint32_t)(P >> 32), k0, k1);
             for (uint32_t lane = 0; lane < 4; ++lane)
-                if (((m >> lane) & 1u) && pick(w, lane) <= p.m.ins_thr[tb * 4 + lane]) stk[sp++] = p.m.ins_base[tb * 4 + lane];
+                if (((m >> lane) & 1u) && pick(w, lane) <= p.m.ins_thr[tb * 4 + lane]) {
+                    const uint32_t ib = p.m.ins_base[tb * 4 + lane];
+                    stk[sp++] = (uint8_t)ib;
+                    if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, lane, cur, cur, ib, 255u);
+                }
         }
         const uint32_t code = base_code(cur);
         bool del = false;
@@ -180,7 +209,8 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint32_t rd, uin
         }
         if (del) {
             uint32_t x;
-            if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;
+            if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;  // "ref" is read after the pop: IndexError -> no record
+            if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, 4u, x, (uint32_t)'.', 0u, 255u);
             seq[outlen++] = (uint8_t)x;
         } else {
             seq[outlen++] = (uint8_t)cur;
@@ -439,7 +469,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             if (nslow) {  // warp-uniform; rare for real models
                 for (uint32_t base = 0; base < nslow; base += ISS_SLOW_SLOTS) {
                     if (tid < ISS_SLOW_SLOTS && base + tid < nslow)
-                        replay_indels(p, l, u32p(l.sSlow)[base + tid],
+                        replay_indels(p, l, gp0, u32p(l.sSlow)[base + tid],
                                       p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride);
                 }
                 __syncthreads();
@@ -475,14 +505,14 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                     qual[pos] = (uint8_t)(q0 + 33u);
                     if (w.y > u32p(l.sErrThr)[q0]) {
                         const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                        if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, rd, pos);
+                        if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, gp0, rd, pos);
                     }
                     if (pos + 1u < L) {
                         const uint32_t q1 = qbt_finish(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, l1b, w.z);
                         qual[pos + 1u] = (uint8_t)(q1 + 33u);
                         if (w.w > u32p(l.sErrThr)[q1]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution(p, l, rd, pos + 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution(p, l, gp0, rd, pos + 1u);
                         }
                     }
                     l1a = n1a; l1b = n1b;
@@ -505,7 +535,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                         qual[pos] = (uint8_t)(q + 33u);
                         if (wt > u32p(l.sErrThr)[q]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, rd, pos);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, gp0, rd, pos);
                         }
                     }
                 }
@@ -519,7 +549,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             const uint32_t nerr = nerr_all < p.err_cap ? nerr_all : p.err_cap;
             for (uint32_t e = tid; e < nerr; e += blockDim.x) {
                 const uint32_t v = u32p(l.sErr)[e];
-                apply_substitution(p, l, v >> 16, v & 0xFFFFu);
+                apply_substitution(p, l, gp0, v >> 16, v & 0xFFFFu);
             }
             if (tid == 0 && nerr_all) atomicAdd(p.counters + 1, (unsigned long long)nerr_all);
         }

@@ -57,6 +57,16 @@ struct Slot {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     int state = 0;  // 0 free, 1 in flight, 2 handed to the consumer
     uint64_t nbytes = 0, n_pairs = 0, first_item = 0, batch_index = 0;
+    // --store_mutations: device event list -> host text
+    uint4 *d_events = nullptr;
+    unsigned long long *d_evcount = nullptr;
+    unsigned long long *h_evcount = nullptr;
+    uint64_t event_cap = 0;
+    uint32_t nseg = 0;
+    uint8_t *d_scratch = nullptr;  // slow-path scratch of the kernel running in this slot (kernels of different slots overlap)
+    uint64_t scratch_bytes = 0;
+    std::vector<uint4> h_events;
+    std::string vcf;
 };
 
 struct HostRecord {
@@ -79,6 +89,7 @@ struct iss_ctx {
     DevGenome gview{};
     DevModel mview{};
     std::vector<HostRecord> recs;
+    std::vector<std::string> rec_names;
     bool have_genome = false, have_model = false;
     // generation state
     std::vector<iss_work_item> items;
@@ -91,8 +102,6 @@ struct iss_ctx {
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
     bool active = false, exhausted = false;
-    uint8_t *d_scratch = nullptr;
-    uint64_t scratch_bytes = 0;
     unsigned long long *d_counters = nullptr;
     // benchmarking marks
     cudaStream_t tstream = nullptr;
@@ -118,6 +127,10 @@ void free_slots(iss_ctx *c) {
         if (s.h_out[1]) cudaFreeHost(s.h_out[1]);
         if (s.d_segs) cudaFree(s.d_segs);
         if (s.h_segs) cudaFreeHost(s.h_segs);
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        if (s.d_events) cudaFree(s.d_events);
+        if (s.d_evcount) cudaFree(s.d_evcount);
+        if (s.h_evcount) cudaFreeHost(s.h_evcount);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
@@ -139,7 +152,14 @@ int rebuild_views(iss_ctx *c) {
         if (c->gh.n_records)
             CU(cudaMemcpy(dr.data(), c->d_genome + c->gh.recs_off, sizeof(DevRecord) * dr.size(), cudaMemcpyDeviceToHost));
         c->recs.resize(dr.size());
-        for (size_t i = 0; i < dr.size(); ++i) c->recs[i] = HostRecord{dr[i].len, dr[i].name_len};
+        std::vector<char> names(c->gh.names_bytes + 1);
+        if (c->gh.names_bytes)
+            CU(cudaMemcpy(names.data(), c->d_genome + c->gh.names_off, c->gh.names_bytes, cudaMemcpyDeviceToHost));
+        c->rec_names.resize(dr.size());
+        for (size_t i = 0; i < dr.size(); ++i) {
+            c->recs[i] = HostRecord{dr[i].len, dr[i].name_len};
+            c->rec_names[i].assign(names.data() + dr[i].name_off, dr[i].name_len);
+        }
         c->have_genome = true;
         c->stats.genome_bytes_device = c->genome_bytes;
     }
@@ -244,15 +264,23 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.gc_bias = c->opts.gc_bias;
     p.nchunk = (L + 15u) / 16u;
     p.chunk_magic = (uint32_t)((0x100000000ull + p.nchunk - 1) / p.nchunk);
-    p.scratch = c->d_scratch;
+    p.scratch = s.d_scratch;
     p.scratch_stride = (uint32_t)align_up(5ull * L + 8, 16);
     p.gc_thr = 3865470567u;  // ceil(0.90 * 2^32): u < 0.90  <=>  w < gc_thr   (generator.py:88)
     p.counters = c->d_counters;
+    p.store_mutations = c->mh.store_mutations;
+    p.events = s.d_events;
+    p.event_count = s.d_evcount;
+    p.event_cap = s.event_cap;
+    s.nseg = nseg;
+    if (p.store_mutations) CU(cudaMemsetAsync(s.d_evcount, 0, sizeof(unsigned long long), s.stream));
     const uint64_t ntiles = (pairs + c->tile_pairs - 1) / c->tile_pairs;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, c->grid);
     CU(cudaEventRecord(s.ev_k0, s.stream));
     CU(iss_launch_generate(p, grid, c->smem, s.stream));
     CU(cudaEventRecord(s.ev_k1, s.stream));
+    if (c->mh.store_mutations)
+        CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     if (!c->opts.device_only) {
         CU(cudaMemcpyAsync(s.h_out[0], s.d_out[0], bytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -268,6 +296,51 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     c->stats.kernel_launches += 1;
     c->stats.pairs += pairs;
     c->stats.fastq_bytes += 2 * bytes;
+    return ISS_OK;
+}
+
+
+// write_mutations (iss/generator.py:598-620): "{id}\t{position+1}\t.\t{ref}\t{alt}\t{quality}\t\t\n", in the order the
+// reference appends them: forward indels, forward substitutions, reverse indels, reverse substitutions, pair by pair.
+int format_vcf(iss_ctx *c, Slot &s) {
+    const unsigned long long n = *s.h_evcount;
+    s.vcf.clear();
+    if (n == 0) return ISS_OK;
+    if (n > s.event_cap) return fail(ISS_E_DEVICE, "mutation event buffer overflow");
+    s.h_events.resize(n);
+    CU(cudaMemcpy(s.h_events.data(), s.d_events, sizeof(uint4) * n, cudaMemcpyDeviceToHost));
+    c->stats.d2h_bytes += sizeof(uint4) * n;
+    std::sort(s.h_events.begin(), s.h_events.end(), [](const uint4 &a, const uint4 &b) {
+        return (((uint64_t)a.y << 32) | a.x) < (((uint64_t)b.y << 32) | b.x);
+    });
+    s.vcf.reserve(n * 48);
+    uint32_t seg = 0;
+    char num[24];
+    for (const uint4 &e : s.h_events) {
+        const uint64_t key = ((uint64_t)e.y << 32) | e.x;
+        const uint64_t gp = key >> 20;
+        const uint32_t o = (key >> 19) & 1u, pos = (key >> 4) & 0x3FFFu;
+        while (seg + 1 < s.nseg && s.h_segs[seg + 1].pair_start <= gp) ++seg;
+        const DevSegment &sg = s.h_segs[seg];
+        const uint64_t i = sg.i0 + (gp - sg.pair_start);
+        s.vcf += c->rec_names[sg.rec];
+        s.vcf += '_';
+        s.vcf.append(num, snprintf(num, sizeof num, "%llu", (unsigned long long)i));
+        s.vcf += '_';
+        s.vcf.append(num, snprintf(num, sizeof num, "%u", sg.cpu));
+        s.vcf += o ? "/2\t" : "/1\t";
+        s.vcf.append(num, snprintf(num, sizeof num, "%u", pos + 1));
+        s.vcf += "\t.\t";
+        s.vcf += (char)(e.z & 0xFF);
+        s.vcf += '\t';
+        s.vcf += (char)((e.z >> 8) & 0xFF);
+        if ((e.z >> 16) & 0xFF) s.vcf += (char)((e.z >> 16) & 0xFF);
+        s.vcf += '\t';
+        const uint32_t q = e.z >> 24;
+        if (q == 255u) s.vcf += '.';
+        else s.vcf.append(num, snprintf(num, sizeof num, "%u", q));
+        s.vcf += "\t\t\n";
+    }
     return ISS_OK;
 }
 
@@ -310,7 +383,6 @@ void iss_ctx_destroy(iss_ctx *c) {
     free_slots(c);
     if (c->d_genome) cudaFree(c->d_genome);
     if (c->d_model) cudaFree(c->d_model);
-    if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->comm) ncclCommDestroy(c->comm);
     for (auto &m : c->marks) if (m) cudaEventDestroy(m);
@@ -617,7 +689,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     const uint32_t grid = (uint32_t)(c->sm_count * bps);
     const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
     const uint32_t max_segs = 1u << 16;
-    const bool realloc = c->slots.size() != o.n_slots || c->slot_cap < slot_cap || c->max_segs != max_segs ||
+    const bool realloc = c->slots.size() != o.n_slots || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
                          (bool)c->opts.device_only != (c->slots.size() && c->slots[0].h_out[0] == nullptr);
     if (realloc) {
         free_slots(c);
@@ -628,6 +700,12 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             if (!o.device_only) {
                 CU(cudaMallocHost(&s.h_out[0], slot_cap));
                 CU(cudaMallocHost(&s.h_out[1], slot_cap));
+            }
+            if (c->mh.store_mutations) {
+                s.event_cap = 32ull * batch_pairs + 1024;
+                CU(cudaMalloc(&s.d_events, sizeof(uint4) * s.event_cap));
+                CU(cudaMalloc(&s.d_evcount, sizeof(unsigned long long)));
+                CU(cudaMallocHost(&s.h_evcount, sizeof(unsigned long long)));
             }
             CU(cudaMalloc(&s.d_segs, sizeof(DevSegment) * max_segs));
             CU(cudaMallocHost(&s.h_segs, sizeof(DevSegment) * max_segs));
@@ -641,10 +719,12 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     }
     for (auto &s : c->slots) s.state = 0;
     const uint64_t scratch = (uint64_t)grid * ISS_SLOW_SLOTS * align_up(5ull * L + 8, 16);
-    if (scratch > c->scratch_bytes) {
-        if (c->d_scratch) cudaFree(c->d_scratch);
-        CU(cudaMalloc(&c->d_scratch, scratch));
-        c->scratch_bytes = scratch;
+    for (auto &s : c->slots) {
+        if (scratch > s.scratch_bytes) {
+            if (s.d_scratch) cudaFree(s.d_scratch);
+            CU(cudaMalloc(&s.d_scratch, scratch));
+            s.scratch_bytes = scratch;
+        }
     }
     c->batch_pairs = batch_pairs;
     c->max_rec = max_rec;
@@ -675,7 +755,7 @@ int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
             if (cnt[2]) {
                 CU(cudaMemset(c->d_counters + 2, 0, sizeof(unsigned long long)));
                 char buf[128];
-                snprintf(buf, sizeof buf, "device error flags 0x%llx (1 window out of range, 2 empty quality bin, 4 bad character)", cnt[2]);
+                snprintf(buf, sizeof buf, "device error flags 0x%llx (1 window out of range, 2 empty quality bin, 4 bad character, 8 mutation buffer overflow)", cnt[2]);
                 return fail(ISS_E_DEVICE, buf);
             }
             return ISS_OK;
@@ -695,6 +775,11 @@ int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
     b->nbytes = s.nbytes;
     b->vcf = nullptr;
     b->vcf_bytes = 0;
+    if (c->mh.store_mutations) {
+        if (int rc = format_vcf(c, s)) return rc;
+        b->vcf = reinterpret_cast<const uint8_t *>(s.vcf.data());
+        b->vcf_bytes = s.vcf.size();
+    }
     b->n_pairs = s.n_pairs;
     b->first_item = s.first_item;
     b->batch_index = s.batch_index;

@@ -19,12 +19,16 @@ def run_product(case, device=0, batch_pairs=0, engine=None, model=None):
         m = model or product_model(case)
         e.set_model(m)
         items = eng_mod.worker_items(case["work"], case["cpu"], case["seed"], e.record_lengths, e.read_length)
-        r1, r2 = [], []
+        r1, r2, vcf = [], [], []
         for b in e.generate(items, sequence_type=case.get("sequence_type", "metagenomics"),
                             gc_bias=bool(case.get("gc_bias")), batch_pairs=batch_pairs):
             r1.append(b.r1.tobytes())
             r2.append(b.r2.tobytes())
-        return b"".join(r1), b"".join(r2), e.stats()
+            if b.vcf is not None:
+                vcf.append(b.vcf.tobytes())
+        st = e.stats()
+        st["vcf"] = b"".join(vcf)
+        return b"".join(r1), b"".join(r2), st
     finally:
         if own:
             e.close()

@@ -33,11 +33,34 @@ def test_golden_fixture(name):
         assert first_diff(r2, exp["R2"]) is None
     assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
     assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
+    if case.get("store_mutations"):
+        assert first_diff(stats["vcf"], exp["vcf"]) is None
+        assert hashlib.sha256(stats["vcf"]).hexdigest() == case["sha256"]["vcf"]
+
+
+@pytest.mark.parametrize("spec,npairs,bp", [("profile:MiSeq", 4000, 0), ("models/stress20.npz", 20000, 257),
+                                           ("models/stress20_sparse.npz", 20000, 0), ("models/miseq_150.npz", 8000, 1000)])
+def test_store_mutations_vcf_against_oracle(spec, npairs, bp):
+    """--store_mutations: the VCF lines (iss/generator.py:598-620) in the reference's order, incl. indel records."""
+    recs_spec = [dict(id="vcf_a", synth_seed=17, length=60000), dict(id="vcf_b", synth_seed=18, length=900)]
+    if "sparse" in spec:
+        recs_spec[0]["sprinkle"] = dict(frac_lower=0.2, n_runs=20, iupac="RYKMSWBDHVN")
+    case = dict(model=spec, seed=99, cpu=2, store_mutations=True, records=recs_spec, work=[[0, npairs], [1, 200]])
+    r1, r2, stats = run_product(case, batch_pairs=bp)
+    om = oracle.OracleModel(fixtures.model_path(spec), store_mutations=True)
+    recs = fixtures.materialise_records(case)
+    work = [(recs[ri][0], recs[ri][1].encode(), n) for ri, n in case["work"]]
+    o1, o2, ov = oracle.run_worker(om, work, case["cpu"], case["seed"], vcf=True)
+    assert first_diff(r1, o1) is None and first_diff(r2, o2) is None
+    assert first_diff(stats["vcf"], ov) is None
+    assert len(ov) > 1000
 
 
 @pytest.mark.parametrize("batch_pairs", [1, 7, 64, 100])
-def test_batch_size_invariance(batch_pairs):
-    case, exp = fixtures.load_case("hiseq_multi_short")
+@pytest.mark.parametrize("name", ["hiseq_multi_short", "stress_indels_dense"])
+def test_batch_size_invariance(name, batch_pairs):
+    """Small batches run concurrently on the ring's streams: results must not depend on the batch size."""
+    case, exp = fixtures.load_case(name)
     r1, r2, _ = run_product(case, batch_pairs=batch_pairs)
     assert r1 == exp["R1"] and r2 == exp["R2"]
 

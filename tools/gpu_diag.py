@@ -24,7 +24,7 @@ for name in only:
     ok1 = hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
     ok2 = hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
     print("%-30s R1 %s R2 %s  (%d B, slow=%d, subst=%d, %.2fs)" % (name, ok1, ok2, len(r1), st["slow_reads"], st["subst_errors"], time.time() - t))
-    for tag, got, want in (("R1", r1, exp["R1"]), ("R2", r2, exp["R2"])):
+    for tag, got, want in (("R1", r1, exp["R1"]), ("R2", r2, exp["R2"]), ("VCF", st["vcf"], exp["vcf"])):
         if want is not None and got != want:
             d = first_diff(got, want)
             print("   %s first diff at byte %d (len got %d want %d)\n     got : %r\n     want: %r" % (tag, d[0], len(got), len(want), d[1], d[2]))
