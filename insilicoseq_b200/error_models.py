@@ -291,32 +291,31 @@ class KDErrorModel(ErrorModel):
 
 
 def basic_phred_table(mean_quality, sd=0.01, cap=0.9999):
-    """Distribution of prob_to_phred(min(N(phred_to_prob(mean_quality), sd), cap)) (basic.py:52-53, util.py:32-45)
-    as an inversion table on a 32-bit word: phred = val[#{k : w >= thr[k]}].
+    """BasicErrorModel.gen_phred_scores (basic.py:52-53) as an integer inversion table.
 
-    phred(p) = int(round(-10 log10(1 - p))) is non-decreasing in p, so P(phred >= v) = P(X >= 1 - 10**(-(v - .5)/10))."""
+    The reference draws x ~ N(phred_to_prob(mean_quality), sd) per position and maps it through
+    phred(x) = prob_to_phred(min(x, cap)) = int(round(-10 log10(1 - min(x, cap)))) (util.py:32-45), which is
+    non-decreasing in x.  RNG contract v1 defines the normal draw by inversion on the phred integer:
+        phred = val[#{k : w >= thr[k]}],   thr[k] = ceil(P(phred < val[k+1]) * 2**32)
+    with P(phred >= v) = P(x >= 1 - 10**(-(v - 0.5)/10)).  Returns (thr uint32[n] ascending, val int64[n+1])."""
     from scipy.stats import norm
 
     mu = float(1 - 10 ** (-mean_quality / 10))
     vmax = int(round(-10 * np.log10(1 - cap)))
-    thr, val = [], []
+    ts = {}
     v = vmax
-    lows = []
-    while v > -200:
-        x_v = 1.0 - 10.0 ** (-(v - 0.5) / 10.0)  # smallest p with phred(p) >= v
-        t = norm.cdf(x_v, loc=mu, scale=sd)       # u >= t  =>  phred >= v
-        lows.append((v, t))
+    while v > -1000:
+        x_v = 1.0 - 10.0 ** (-(v - 0.5) / 10.0)   # smallest probability whose phred is >= v
+        t = float(norm.cdf(x_v, loc=mu, scale=sd))  # u >= t  <=>  phred >= v
         if t * TWO32 < 1.0:
             break
+        ts[v] = t
         v -= 1
-    lows.reverse()  # ascending v
-    vmin = lows[0][0]
-    vals = [vmin]
-    for v, t in lows[1:]:
-        thr.append(int(min(math.ceil(t * TWO32), 2 ** 32 - 1)))
-        vals.append(v)
-    del val
-    return np.array(thr, dtype=np.uint32), np.array(vals, dtype=np.int64)
+    vmin = v
+    order = sorted(ts)
+    thr = np.array([min(math.ceil(ts[k] * TWO32), 2 ** 32 - 1) for k in order], dtype=np.uint32)
+    val = np.array([vmin] + order, dtype=np.int64)
+    return thr, val
 
 
 class BasicErrorModel(ErrorModel):

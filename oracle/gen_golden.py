@@ -117,13 +117,22 @@ def build_cases():
                       fragment_length=420, fragment_sd=35,
                       records=[rec("fragrec", 9000, 121), rec("shortfrag", 430, 122)], work=[[0, 60], [1, 30]],
                       inline=True))
+    cases.append(dict(name="basic_mode", model="basic", seed=42, cpu=0, store_mutations=True,
+                      records=[rec("ecoli_like", 1330, 131), rec("b2", 700, 132)], work=[[0, 150], [1, 40]], inline=True))
+    cases.append(dict(name="basic_mode_fragment", model="basic", seed=3, cpu=1, fragment_length=450, fragment_sd=0,
+                      records=[rec("my_genome", 1000, 133)], work=[[0, 60]], inline=True))
+    cases.append(dict(name="perfect_mode", model="perfect", seed=9, cpu=0,
+                      records=[rec("pg", 2500, 134)], work=[[0, 400]], inline=True))
     return cases
 
 
 def run_reference(case, tmp):
     recs = materialise_records(case)
     fl, fsd = case.get("fragment_length"), case.get("fragment_sd")
-    em = pr.load_kde_model(model_path(case["model"]), fl, fsd, bool(case.get("store_mutations")))
+    if case["model"] in ("basic", "perfect"):
+        em = pr.load_simple_model(case["model"], fl, fsd, bool(case.get("store_mutations")))
+    else:
+        em = pr.load_kde_model(model_path(case["model"]), fl, fsd, bool(case.get("store_mutations")))
     work = [(pr.make_record(recs[ri][1], recs[ri][0]), n, "default") for ri, n in case["work"]]
     prefix = os.path.join(tmp, "w")
     pr.run_worker(work, em, case["cpu"], prefix, case["seed"], case.get("sequence_type", "metagenomics"),
@@ -138,7 +147,11 @@ def run_c_oracle(case):
     recs = materialise_records(case)
     fl, fsd = case.get("fragment_length"), case.get("fragment_sd")
     ft = pr.fragment_table(fl, fsd) if fl is not None else None
-    om = oracle.OracleModel(model_path(case["model"]), fl, fsd, bool(case.get("store_mutations")), frag_table=ft)
+    if case["model"] in ("basic", "perfect"):
+        om = oracle.OracleModel(case["model"], fl, fsd, bool(case.get("store_mutations")), frag_table=ft,
+                                basic_table=pr.basic_phred_table(30))
+    else:
+        om = oracle.OracleModel(model_path(case["model"]), fl, fsd, bool(case.get("store_mutations")), frag_table=ft)
     work = [(recs[ri][0], recs[ri][1].encode(), n) for ri, n in case["work"]]
     return oracle.run_worker(om, work, case["cpu"], case["seed"],
                              amplicon=case.get("sequence_type") == "amplicon", gc_bias=bool(case.get("gc_bias")),

@@ -135,9 +135,14 @@ def truncate_profile(npz_in, npz_out, read_length):
 
 
 class OracleModel:
-    """Flat f64 view of a KDE profile for the C oracle."""
+    """Flat f64 view of an error model for the C oracle: a KDE profile (.npz), or the reference's
+    BasicErrorModel / PerfectErrorModel attribute sets (npz_path = "basic" / "perfect")."""
 
-    def __init__(self, npz_path, fragment_length=None, fragment_sd=None, store_mutations=False, frag_table=None):
+    def __init__(self, npz_path, fragment_length=None, fragment_sd=None, store_mutations=False, frag_table=None,
+                 basic_table=None):
+        if npz_path in ("basic", "perfect"):
+            self._init_simple(npz_path, fragment_length, fragment_sd, store_mutations, frag_table, basic_table)
+            return
         prof = np.load(npz_path, allow_pickle=True)
         assert str(prof["model"]) == "kde", prof["model"]
         L = int(prof["read_length"])
@@ -210,6 +215,55 @@ class OracleModel:
         self.c = _CModel()
         self._fill()
 
+    def _init_simple(self, kind, fragment_length, fragment_sd, store_mutations, frag_table, basic_table):
+        """iss/error_models/basic.py:18-39 and perfect.py:16-33: L=125, insert 200, no indels; basic substitutes
+        uniformly among the 3 other bases, perfect 'substitutes' a base by itself."""
+        L = 125
+        self.read_length = L
+        self.npz_path = kind
+        self.store_mutations = bool(store_mutations) and kind == "basic"
+        self.nq = 41
+        self.kind = kind
+        if kind == "basic":
+            choices = {"A": ("TCG", [1 / 3] * 3), "T": ("ACG", [1 / 3] * 3), "C": ("ATG", [1 / 3] * 3), "G": ("ATC", [1 / 3] * 3)}
+        else:
+            choices = {"A": ("ATCG", [1, 0, 0, 0]), "T": ("ATCG", [0, 1, 0, 0]), "C": ("ATCG", [0, 0, 1, 0]), "G": ("ATCG", [0, 0, 0, 1])}
+        subst_n = np.zeros((2, L, 4), dtype=np.int32)
+        subst_cdf = np.ones((2, L, 4, MAX_ALT), dtype=np.float64)
+        subst_alt = np.full((2, L, 4, MAX_ALT), ord("N"), dtype=np.uint8)
+        for c, base in enumerate(BASES):
+            alts, probs = choices[base]
+            subst_n[:, :, c] = len(alts)
+            subst_cdf[:, :, c, :len(alts)] = _choice_cdf(probs)
+            subst_alt[:, :, c, :len(alts)] = [ord(a) for a in alts]
+        ins_base = np.zeros((2, L, 4), dtype=np.uint8)
+        ins_base[:] = [ord(b) for b in "ATCG"]
+        # phred_to_prob on the python ints prob_to_phred returns (identical values to the np.int64 form)
+        self._arrays = dict(insert_cdf=np.zeros(1), bin_cdf=np.ones((2, 4)), bin_rows=np.zeros((2, 4), dtype=np.int32),
+                            qual_cdf=np.zeros(1), phred_prob=np.array([1 - 10 ** (-q / 10) for q in range(self.nq + 1)]),
+                            subst_n=subst_n, subst_cdf=subst_cdf, subst_alt=subst_alt, ins_p=np.zeros((2, L, 4)),
+                            ins_base=ins_base, del_p=np.zeros((2, L, 4)))
+        self.frag_lo, self.frag_mode, self.n_frag = 0, 0, 0
+        frag_thr = np.zeros(1, dtype=np.uint64)
+        if fragment_length is not None and fragment_sd is not None:
+            self.frag_mode = 1
+            self.frag_lo = int(frag_table[0])
+            t = np.ascontiguousarray(frag_table[1], dtype=np.uint64)
+            self.n_frag = len(t)
+            frag_thr = t if len(t) else frag_thr
+        self._arrays["frag_thr"] = frag_thr
+        if kind == "basic":
+            thr, val = basic_table
+            self._arrays["basic_thr"] = np.ascontiguousarray(thr, dtype=np.uint32) if len(thr) else np.zeros(1, dtype=np.uint32)
+            self._arrays["basic_val"] = np.ascontiguousarray(val, dtype=np.uint8)
+            self._n_basic = len(thr)
+        else:
+            self._arrays["basic_thr"] = np.zeros(1, dtype=np.uint32)
+            self._arrays["basic_val"] = np.zeros(1, dtype=np.uint8)
+            self._n_basic = 0
+        self.c = _CModel()
+        self._fill()
+
     def _fill(self):
         c = self.c
         c.read_length = self.read_length
@@ -219,10 +273,11 @@ class OracleModel:
         c.frag_lo = self.frag_lo
         c.n_frag = self.n_frag
         c.store_mutations = int(self.store_mutations)
-        c.fixed_insert = -1
-        c.qual_mode = 0
-        c.const_phred = 0
-        c.n_basic = 0
+        kind = getattr(self, "kind", "kde")
+        c.fixed_insert = -1 if kind == "kde" else 200
+        c.qual_mode = {"kde": 0, "perfect": 1, "basic": 2}[kind]
+        c.const_phred = 40 if kind == "perfect" else 0
+        c.n_basic = getattr(self, "_n_basic", 0)
         for name, arr in self._arrays.items():
             arr = np.ascontiguousarray(arr)
             self._arrays[name] = arr

@@ -95,6 +95,29 @@ def fragment_table(mu, sd):
     return lo, thr
 
 
+def basic_phred_table(mean_quality, sd=0.01, cap=0.9999):
+    """Oracle-side twin of insilicoseq_b200.error_models.basic_phred_table (same definition, separate code):
+    BasicErrorModel's per-position normal draw (iss/error_models/basic.py:52) by inversion on the phred integer."""
+    import math
+
+    from scipy.stats import norm
+
+    mu = float(1 - 10 ** (-mean_quality / 10))
+    vmax = int(round(-10 * np.log10(1 - cap)))
+    rows = []
+    v = vmax
+    while v > -1000:
+        t = float(norm.cdf(1.0 - 10.0 ** (-(v - 0.5) / 10.0), loc=mu, scale=sd))
+        if t * 2.0 ** 32 < 1.0:
+            break
+        rows.append((v, t))
+        v -= 1
+    rows.sort()
+    thr = np.array([min(math.ceil(t * 2.0 ** 32), 2 ** 32 - 1) for _, t in rows], dtype=np.uint32)
+    val = np.array([v] + [k for k, _ in rows], dtype=np.int64)
+    return thr, val
+
+
 class PhiloxDriver:
     """Context manager: while active, the five RNG entry points return slot-addressed Philox draws."""
 
@@ -213,6 +236,20 @@ class PhiloxDriver:
 
     def _normal(self, loc=0.0, scale=1.0, size=None):
         f = sys._getframe(1)
+        if f.f_code.co_name == "gen_phred_scores" and size is not None:
+            # BasicErrorModel (basic.py:52): position p takes the QUAL phred word of p; the value returned is the
+            # probability whose phred is exactly the tabulated integer (prob_to_phred(min(x, .9999)) maps it back)
+            o = self._orient(f)
+            mq = f.f_locals["mean_quality"]
+            if ("basic", mq, scale) not in self._frag_cache:
+                self._frag_cache[("basic", mq, scale)] = basic_phred_table(mq, scale)
+            thr, val = self._frag_cache[("basic", mq, scale)]
+            out = np.empty(int(size), dtype=np.float64)
+            for pos in range(int(size)):
+                w = self._word(philox.read_stream(o, philox.K_QUAL), pos >> 1, 2 * (pos & 1))
+                v = int(val[int(np.searchsorted(thr, np.uint32(w), side="right"))])
+                out[pos] = 1.0 - 10.0 ** (-v / 10.0)
+            return out
         if size is not None or f.f_code.co_name != "simulate_read":
             raise RuntimeError("np.random.normal form not on the hot path")
         keyt = (float(loc), float(scale))
@@ -291,6 +328,21 @@ def make_record(seq, rec_id):
     from Bio.SeqRecord import SeqRecord
 
     return SeqRecord(Seq(seq), id=rec_id, description="")
+
+
+def load_simple_model(kind, fragment_length=None, fragment_sd=None, store_mutations=False):
+    """BasicErrorModel / PerfectErrorModel of the reference.  The reference's PerfectErrorModel never sets
+    `store_mutations` (perfect.py:16-33) although mut_sequence reads it (error_models/__init__.py:98) -- it raises
+    AttributeError on the first Q40 'error' (~1e-4 per base).  The attribute is injected on the INSTANCE here so the
+    evident intent (identity substitution) can be pinned; no reference code is changed."""
+    import_reference()
+    from iss.error_models import basic, perfect
+
+    if kind == "basic":
+        return basic.BasicErrorModel(fragment_length, fragment_sd, store_mutations)
+    m = perfect.PerfectErrorModel(fragment_length, fragment_sd)
+    m.store_mutations = False
+    return m
 
 
 def load_kde_model(npz_path, fragment_length=None, fragment_sd=None, store_mutations=False):

@@ -5,6 +5,11 @@ from insilicoseq_b200 import error_models
 
 
 def product_model(case):
+    fl, fsd = case.get("fragment_length"), case.get("fragment_sd")
+    if case["model"] == "basic":
+        return error_models.BasicErrorModel(fl, fsd, bool(case.get("store_mutations")))
+    if case["model"] == "perfect":
+        return error_models.PerfectErrorModel(fl, fsd)
     return error_models.KDErrorModel(fixtures.model_path(case["model"]), case.get("fragment_length"),
                                      case.get("fragment_sd"), bool(case.get("store_mutations")))
 

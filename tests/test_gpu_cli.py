@@ -99,3 +99,40 @@ def test_gpu_count_invariance(tmp_path):
     assert outs[0] == outs[1]
     e1, e2 = _expected(recs, ab, "profile:miSeq_0.npz", 6000, 4, 5)
     assert outs[1] == (e1, e2)
+
+
+def test_cli_baseline_config0_basic_mode(tmp_path):
+    """BASELINE.json configs[0]: `iss generate --genomes ecoli.fasta --mode basic -n 1000 --seed 42 --cpus 1`
+    (1 record of 1330 bp, like the reference's data/ecoli.fasta) -- 500 pairs, L=125, insert 200."""
+    import patched_reference as pr
+
+    seq = fixtures.synth_genome(4242, 1330)
+    fa = tmp_path / "ecoli.fasta"
+    fa.write_text(">NC_fake.1 Escherichia coli fragment\n" + "\n".join(seq[i:i + 70] for i in range(0, 1330, 70)) + "\n")
+    out = str(tmp_path / "c0")
+    app.main(["generate", "--genomes", str(fa), "--mode", "basic", "-n", "1000", "--seed", "42", "--cpus", "1",
+              "--gpus", "1", "-o", out, "-q"])
+    om = oracle.OracleModel("basic", basic_table=pr.basic_phred_table(30))
+    e1, e2 = oracle.run_worker(om, [("NC_fake.1", seq.encode(), 500)], 0, 42)
+    assert open(out + "_R1.fastq", "rb").read() == e1
+    assert open(out + "_R2.fastq", "rb").read() == e2
+    assert e1.count(b"\n") == 2000
+
+
+def test_cli_store_mutations_vcf(tmp_path):
+    fa, abf, recs, ab = _write_inputs(tmp_path)
+    out = str(tmp_path / "vcfrun")
+    app.main(["generate", "-g", fa, "-b", abf, "--model", "miseq", "-n", "3000", "--seed", "21", "--cpus", "2", "--gpus", "1",
+              "-o", out, "-q", "--store_mutations"])
+    vcf = open(out + ".vcf", "rb").read()
+    assert vcf.startswith(b"##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+
+    class M:
+        read_length = 301
+
+    records = [fasta.Record(seq.encode(), id=name) for name, seq in recs]
+    chunks = list(generator.generate_work_divider(records, None, ab, 3000, None, None, M(), "x", -((1500) // -2)))
+    om = oracle.OracleModel(fixtures.model_path("profile:miSeq_0.npz"), store_mutations=True)
+    body = b"".join(oracle.run_worker(om, [(r.id, r.seq, n) for r, n, _ in work], cpu, 21, vcf=True)[2]
+                    for cpu, work in enumerate(chunks))
+    assert vcf.split(b"\n", 2)[2] == body and len(body) > 500

@@ -94,6 +94,26 @@ def test_fragment_table_matches_oracle_side():
         assert lo_a == lo_b and np.array_equal(t_a, t_b)
 
 
+def test_basic_and_perfect_lowering():
+    import patched_reference as pr
+
+    thr_a, val_a = error_models.basic_phred_table(30)
+    thr_b, val_b = pr.basic_phred_table(30)
+    assert np.array_equal(thr_a, thr_b) and np.array_equal(val_a, val_b)
+    assert val_a[-1] == 40 and (np.diff(val_a) == 1).all() and (np.diff(thr_a.astype(np.int64)) >= 0).all()
+    b = error_models.BasicErrorModel().device_tables()
+    assert b.scalars["qual_mode"] == 2 and b.scalars["fixed_insert"] == 200 and b.scalars["read_length"] == 125
+    assert not b.arrays["ins_nz"].any() and not b.arrays["del_nz"].any()
+    pm = error_models.PerfectErrorModel().device_tables()
+    assert pm.scalars["qual_mode"] == 1 and pm.scalars["const_phred"] == 40
+    # identity 'substitution': choice over [1,0,0,0] etc. always returns the original base
+    for c, base in enumerate(error_models.BASES):
+        thr = pm.arrays["subst_thr"][0, 5, c]
+        alts = pm.arrays["subst_alt"][0, 5, c]
+        for w in (0, 1, 2 ** 31, 2 ** 32 - 1):
+            assert chr(alts[int((np.uint64(w) >= thr).sum())]) == base
+
+
 def test_worker_items_bookkeeping():
     items = eng_mod.worker_items([(0, 5), (1, 3), (2, 0), (0, 4)], cpu_number=3, seed=7,
                                  record_lengths=[1000, 100, 1000], read_length=126)

@@ -22,8 +22,14 @@ def _run_oracle(case):
         import patched_reference as pr
 
         ft = pr.fragment_table(fl, fsd)
-    om = oracle.OracleModel(fixtures.model_path(case["model"]), fl, fsd, bool(case.get("store_mutations")),
-                            frag_table=ft)
+    if case["model"] in ("basic", "perfect"):
+        import patched_reference as pr
+
+        om = oracle.OracleModel(case["model"], fl, fsd, bool(case.get("store_mutations")), frag_table=ft,
+                                basic_table=pr.basic_phred_table(30))
+    else:
+        om = oracle.OracleModel(fixtures.model_path(case["model"]), fl, fsd, bool(case.get("store_mutations")),
+                                frag_table=ft)
     work = [(recs[ri][0], recs[ri][1].encode(), n) for ri, n in case["work"]]
     return oracle.run_worker(om, work, case["cpu"], case["seed"], amplicon=case.get("sequence_type") == "amplicon",
                              gc_bias=bool(case.get("gc_bias")), vcf=True)
