@@ -29,6 +29,7 @@ def is_stale():
 def build_native(force=False, extra_flags=(), verbose=False):
     if not force and not is_stale():
         return LIB
+    extra_flags = list(extra_flags) + os.environ.get("ISS_NVCC_EXTRA", "").split()
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + SOURCES + ["-lnccl"]
     if verbose:
         print(" ".join(cmd))

@@ -43,6 +43,31 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return o;
 }
 
+// Same function with the ten round keys precomputed (rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1).  With rk in the
+// kernel's constant bank a round is 2 IMAD.WIDE + 2 LOP3.
+__host__ __device__ __forceinline__ Philox4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                             const uint32_t *__restrict__ rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi0 = __umulhi(PHILOX_M0, c0), lo0 = PHILOX_M0 * c0;
+        const uint32_t hi1 = __umulhi(PHILOX_M1, c2), lo1 = PHILOX_M1 * c2;
+#else
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        const uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+__host__ __device__ inline void philox_round_keys(uint64_t key, uint32_t rk[20]) {
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+}
+
 // stream ids of RNG contract v1
 #define ISS_S_PAIR 0u
 #define ISS_K_QUAL 0u
@@ -157,6 +182,52 @@ __host__ __device__ __forceinline__ uint64_t iss_cf(uint64_t i, uint32_t fixed_l
     return s;
 }
 
+// Shared-memory layout of one tile, as byte offsets from the dynamic shared memory base (computed on the host so
+// that they sit in the constant bank).  Offsets, not pointers: every access stays provably in the shared window.
+struct Lay {
+    uint32_t img[2];   // FASTQ stream images (R1, R2)
+    uint32_t sP;       // u64[T]  pair ordinal
+    uint32_t sOff;     // u64[T]  byte offset of the pair's record in the batch stream
+    uint32_t sRecLen;  // u64[T]  record length
+    uint32_t sWabs;    // u64[2T] absolute index (base or byte) of the window start in the genome array
+    uint32_t sWin;     // u64[2T] window start inside the record (fs / rs)
+    uint32_t sSeg;     // u32[T]
+    uint32_t sAtt;     // u32[T]
+    uint32_t sQrow;    // u32[2T] element offset of the read's quality rows
+    uint32_t sSeqOff;  // u32[2T] offset of the sequence line inside the stream image
+    uint32_t sEnc;     // u32[2T]
+    uint32_t sSlow;    // u32[2T]
+    uint32_t sFlag;    // u32[2T] read already queued for the sequential indel replay
+    uint32_t sErr;     // u32[err_cap]
+    uint32_t sErrThr;  // u32[64]
+    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 3 bytes of the tile's last record
+    uint32_t total;    // bytes of dynamic shared memory
+};
+
+__host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uint32_t err_cap) {
+    Lay l;
+    uint32_t q = 0;
+    l.img[0] = q; q += img_cap;
+    l.img[1] = q; q += img_cap;
+    l.sP = q; q += 8u * T;
+    l.sOff = q; q += 8u * T;
+    l.sRecLen = q; q += 8u * T;
+    l.sWabs = q; q += 16u * T;
+    l.sWin = q; q += 16u * T;
+    l.sSeg = q; q += 4u * T;
+    l.sAtt = q; q += 4u * T;
+    l.sQrow = q; q += 8u * T;
+    l.sSeqOff = q; q += 8u * T;
+    l.sEnc = q; q += 8u * T;
+    l.sSlow = q; q += 8u * T;
+    l.sFlag = q; q += 8u * T;
+    l.sErr = q; q += 4u * err_cap;
+    l.sErrThr = q; q += 4u * ISS_QROW;
+    l.sCtl = q; q += 32u;
+    l.total = q;
+    return l;
+}
+
 #define ISS_QUAL_KDE_MODE 0u
 #define ISS_QUAL_CONST_MODE 1u
 #define ISS_QUAL_TABLE_MODE 2u
@@ -178,6 +249,8 @@ struct GenParams {
     uint32_t tile_shift;      // log2(T)
     uint64_t total_pairs;
     uint64_t key;             // Philox key of every pair of this launch (a batch never spans two workers)
+    uint32_t rk[20];          // the ten Philox round keys (k0 + r*W0, k1 + r*W1): constant-bank operands of the LOP3s
+    Lay lay;
     uint8_t *out1;
     uint8_t *out2;
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)

@@ -55,7 +55,11 @@ __device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (ui
 //   words 32..95  the 64 leaves (0xFFFFFFFF padded)
 // #{j < 64 : w > row[j]} = 16*c1 + 4*c2 + c3 on a nondecreasing row: three dependent 16-byte loads.
 __device__ __forceinline__ uint32_t cnt3(uint32_t w, const uint4 &t) {
-    return (w > t.x ? 1u : 0u) + (w > t.y ? 1u : 0u) + (w > t.z ? 1u : 0u);
+    uint32_t c = 0;  // t.x <= t.y <= t.z: the last true test wins
+    if (w > t.x) c = 1;
+    if (w > t.y) c = 2;
+    if (w > t.z) c = 3;
+    return c;
 }
 __device__ __forceinline__ uint32_t qbt_finish(const uint32_t *__restrict__ row, const uint4 &lvl1, uint32_t w) {
     const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
@@ -73,50 +77,6 @@ __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t en
     return __ldg(g.ascii + abs_pos);
 }
 
-// Shared-memory layout of one tile, as byte offsets from iss_smem.  Offsets (not pointers) keep every access
-// provably in the shared window, so the compiler emits LDS/STS instead of generic LD/ST.
-struct Lay {
-    uint32_t img[2];   // FASTQ stream images (R1, R2)
-    uint32_t sP;       // u64[T]  pair ordinal
-    uint32_t sOff;     // u64[T]  byte offset of the pair's record in the batch stream
-    uint32_t sRecLen;  // u64[T]  record length
-    uint32_t sWabs;    // u64[2T] absolute index (base or byte) of the window start in the genome array
-    uint32_t sWin;     // u64[2T] window start inside the record (fs / rs)
-    uint32_t sSeg;     // u32[T]
-    uint32_t sAtt;     // u32[T]
-    uint32_t sQrow;    // u32[2T] element offset of the read's quality rows
-    uint32_t sSeqOff;  // u32[2T] offset of the sequence line inside the stream image
-    uint32_t sEnc;     // u32[2T]
-    uint32_t sSlow;    // u32[2T]
-    uint32_t sFlag;    // u32[2T] read already queued for the sequential indel replay
-    uint32_t sErr;     // u32[err_cap]
-    uint32_t sErrThr;  // u32[64]
-    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 3 bytes of the tile's last record
-};
-
-__device__ __forceinline__ Lay carve(const GenParams &p) {
-    Lay l;
-    const uint32_t T = p.tile_pairs;
-    uint32_t q = 0;
-    l.img[0] = q; q += p.img_cap;
-    l.img[1] = q; q += p.img_cap;
-    l.sP = q; q += 8u * T;
-    l.sOff = q; q += 8u * T;
-    l.sRecLen = q; q += 8u * T;
-    l.sWabs = q; q += 16u * T;
-    l.sWin = q; q += 16u * T;
-    l.sSeg = q; q += 4u * T;
-    l.sAtt = q; q += 4u * T;
-    l.sQrow = q; q += 8u * T;
-    l.sSeqOff = q; q += 8u * T;
-    l.sEnc = q; q += 8u * T;
-    l.sSlow = q; q += 8u * T;
-    l.sFlag = q; q += 8u * T;
-    l.sErr = q; q += 4u * p.err_cap;
-    l.sErrThr = q; q += 4u * ISS_QROW;
-    l.sCtl = q;
-    return l;
-}
 __device__ __forceinline__ uint64_t *u64p(uint32_t off) { return reinterpret_cast<uint64_t *>(iss_smem + off); }
 __device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cast<uint32_t *>(iss_smem + off); }
 __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
@@ -148,9 +108,9 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
     const uint32_t c = seq[pos];
     if (!is_acgt(c)) return;  // "RYWSMKHBVDN" are never substituted (__init__.py:94)
     const uint32_t code = base_code(c);
-    const uint64_t P = u64p(l.sP)[pair], key = p.key;
-    const Philox4 w = philox4x32_10(pos >> 2, iss_read_stream(o, ISS_K_SUBC) | (u32p(l.sAtt)[pair] << 8), (uint32_t)P,
-                                    (uint32_t)(P >> 32), (uint32_t)key, (uint32_t)(key >> 32));
+    const uint64_t P = u64p(l.sP)[pair];
+    const Philox4 w = philox4x32_10_rk(pos >> 2, iss_read_stream(o, ISS_K_SUBC) | (u32p(l.sAtt)[pair] << 8), (uint32_t)P,
+                                       (uint32_t)(P >> 32), p.rk);
     const uint64_t r = pick(w, pos & 3u);
     const uint32_t e = ((o * L + pos) << 2) + code;
     const uint32_t na = p.m.subst_n[e];
@@ -169,6 +129,10 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
     seq[pos] = (uint8_t)alt;
 }
 
+__device__ __noinline__ void apply_substitution_overflow(const GenParams &p, uint64_t gp0, uint32_t rd, uint32_t pos) {
+    apply_substitution(p, p.lay, gp0, rd, pos);  // substitution list full: rare, kept out of the hot loop's code
+}
+
 // ---- sequential replay of introduce_indels + adjust_seq_length for one read ---------------------------
 // Reference list semantics (error_models/__init__.py:187-226) restated as a stream:
 //   seq = out[0..nucl) ++ [cur] ++ future,   future = LIFO of inserted bases on top of the unread original.
@@ -182,8 +146,8 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
     uint8_t *orig = scratch;
     uint8_t *stk = scratch + L;
     for (uint32_t k = 0; k < L; ++k) orig[k] = seq[k];
-    const uint64_t P = u64p(l.sP)[pair], key = p.key;
-    const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), att8 = u32p(l.sAtt)[pair] << 8;
+    const uint64_t P = u64p(l.sP)[pair];
+    const uint32_t att8 = u32p(l.sAtt)[pair] << 8;
     const uint32_t sIns = iss_read_stream(o, ISS_K_INS) | att8, sDel = iss_read_stream(o, ISS_K_DEL) | att8;
     uint32_t sp = 0, k = 0, outlen = 0;
     for (uint32_t nucl = 0; nucl + 1 < L; ++nucl) {
@@ -193,7 +157,7 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
         const uint32_t tb = o * L + nucl;
         const uint32_t m = p.m.ins_nz[tb];
         if (m) {
-            const Philox4 w = philox4x32_10(nucl, sIns, (uint32_t)P, (uint32_t)(P >> 32), k0, k1);
+            const Philox4 w = philox4x32_10_rk(nucl, sIns, (uint32_t)P, (uint32_t)(P >> 32), p.rk);
             for (uint32_t lane = 0; lane < 4; ++lane)
                 if (((m >> lane) & 1u) && pick(w, lane) <= p.m.ins_thr[tb * 4 + lane]) {
                     const uint32_t ib = p.m.ins_base[tb * 4 + lane];
@@ -204,7 +168,7 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
         const uint32_t code = base_code(cur);
         bool del = false;
         if ((p.m.del_nz[tb] >> code) & 1u) {
-            const Philox4 w = philox4x32_10(nucl >> 2, sDel, (uint32_t)P, (uint32_t)(P >> 32), k0, k1);
+            const Philox4 w = philox4x32_10_rk(nucl >> 2, sDel, (uint32_t)P, (uint32_t)(P >> 32), p.rk);
             del = pick(w, nucl & 3u) <= p.m.del_thr[tb * 4 + code];
         }
         if (del) {
@@ -243,9 +207,12 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
 
 }  // namespace
 
-__global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_constant__ GenParams p) {
+#ifndef ISS_MIN_BLOCKS
+#define ISS_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
-    const Lay l = carve(p);
+    const Lay &l = p.lay;
     if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
     const uint64_t ntiles = (p.total_pairs + T - 1) / T;
     bool store_pending = false;
@@ -276,14 +243,14 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             }
             const DevSegment *sg = p.segs + lo;
             const uint64_t i = sg->i0 + (gp - sg->pair_start);
-            const uint64_t P = sg->item_base + i, key = p.key;
-            const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
+            const uint64_t P = sg->item_base + i;
+            const uint32_t Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
             const DevRecord *rec = p.g.recs + sg->rec;
             const int64_t len = (int64_t)rec->len;
             uint32_t att = 0;
             Philox4 b0;
             for (;;) {  // --gc_bias: re-simulate the pair until the accept draw passes (generator.py:82-92)
-                b0 = philox4x32_10(0, ISS_S_PAIR | (att << 8), Plo, Phi, k0, k1);
+                b0 = philox4x32_10_rk(0, ISS_S_PAIR | (att << 8), Plo, Phi, p.rk);
                 if (!p.gc_bias || b0.w < p.gc_thr) break;
                 ++att;
             }
@@ -292,7 +259,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             bool have_b2 = false;
             int64_t insert;
             if (p.frag_mode) {  // int(np.random.normal(mu, sd)) by inversion on the integer table
-                b2 = philox4x32_10(2, ISS_S_PAIR | a8, Plo, Phi, k0, k1);
+                b2 = philox4x32_10_rk(2, ISS_S_PAIR | a8, Plo, Phi, p.rk);
                 have_b2 = true;
                 const uint64_t r64 = u64of(b2.z, b2.w);
                 uint32_t a = 0, b = p.n_frag;
@@ -306,7 +273,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 insert = (int64_t)a;
             }
             const int64_t frag = insert + 2 * (int64_t)L;
-            const Philox4 b1 = philox4x32_10(1, ISS_S_PAIR | a8, Plo, Phi, k0, k1);
+            const Philox4 b1 = philox4x32_10_rk(1, ISS_S_PAIR | a8, Plo, Phi, p.rk);
             int64_t fs;
             if (p.amplicon) fs = 0;
             else {
@@ -319,7 +286,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
             if (p.amplicon) { rs = len - (int64_t)L; re = len; }
             else { rs = fe + insert; re = rs + (int64_t)L; }
             if (re > len) {  // generator.py:172-176
-                if (!have_b2) b2 = philox4x32_10(2, ISS_S_PAIR | a8, Plo, Phi, k0, k1);
+                if (!have_b2) b2 = philox4x32_10_rk(2, ISS_S_PAIR | a8, Plo, Phi, p.rk);
                 re = (int64_t)L + (int64_t)__umul64hi(u64of(b2.x, b2.y), (uint64_t)(len - (int64_t)L));
                 rs = re - (int64_t)L;
             }
@@ -427,8 +394,8 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
 
         // ---- phase 3: indel scan in the no-event world (error_models/__init__.py:187-224).  The pair's combined list
         //      of non-zero positions (forward then reverse) is cut in four equal parts, one per thread of the pair.
-        const uint64_t P = valid ? u64p(l.sP)[pair] : 0, key = p.key;
-        const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32), Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
+        const uint64_t P = valid ? u64p(l.sP)[pair] : 0;
+        const uint32_t Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
         const uint32_t att8 = valid ? (u32p(l.sAtt)[pair] << 8) : 0;
         uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
         const uint32_t nnz_all = p.n_nz[0] + p.n_nz[1];
@@ -447,14 +414,14 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                 const uint32_t m = p.m.ins_nz[tb];
                 bool hit = false;
                 if (m) {
-                    const Philox4 w = philox4x32_10(pos, iss_read_stream(so, ISS_K_INS) | att8, Plo, Phi, k0, k1);
+                    const Philox4 w = philox4x32_10_rk(pos, iss_read_stream(so, ISS_K_INS) | att8, Plo, Phi, p.rk);
                     const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.ins_thr) + tb);
                     hit = ((m & 1u) && w.x <= t.x) | ((m & 2u) && w.y <= t.y) | ((m & 4u) && w.z <= t.z) | ((m & 8u) && w.w <= t.w);
                 }
                 const uint32_t code = base_code(c);
                 if ((p.m.del_nz[tb] >> code) & 1u) {
                     const uint32_t ck = (so << 30) | (pos >> 2);
-                    if (ck != cached) { cached = ck; dblk = philox4x32_10(pos >> 2, iss_read_stream(so, ISS_K_DEL) | att8, Plo, Phi, k0, k1); }
+                    if (ck != cached) { cached = ck; dblk = philox4x32_10_rk(pos >> 2, iss_read_stream(so, ISS_K_DEL) | att8, Plo, Phi, p.rk); }
                     hit |= pick(dblk, pos & 3u) <= __ldg(p.m.del_thr + tb * 4 + code);
                 }
                 if (hit) fired |= 1u << so;
@@ -500,26 +467,26 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                         n1a = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pa * ISS_QBT_STRIDE));
                         n1b = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pb * ISS_QBT_STRIDE));
                     }
-                    const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
+                    const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
                     const uint32_t q0 = qbt_finish(rows + (size_t)pos * ISS_QBT_STRIDE, l1a, w.x);
                     qual[pos] = (uint8_t)(q0 + 33u);
                     if (w.y > u32p(l.sErrThr)[q0]) {
                         const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                        if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, gp0, rd, pos);
+                        if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, gp0, rd, pos);
                     }
                     if (pos + 1u < L) {
                         const uint32_t q1 = qbt_finish(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, l1b, w.z);
                         qual[pos + 1u] = (uint8_t)(q1 + 33u);
                         if (w.w > u32p(l.sErrThr)[q1]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution(p, l, gp0, rd, pos + 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution_overflow(p, gp0, rd, pos + 1u);
                         }
                     }
                     l1a = n1a; l1b = n1b;
                 }
             } else {
                 for (uint32_t b = b_begin; b < b_end; ++b) {
-                    const Philox4 w = philox4x32_10(b, sQ, Plo, Phi, k0, k1);
+                    const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
 #pragma unroll
                     for (uint32_t h = 0; h < 2; ++h) {
                         const uint32_t pos = 2u * b + h;
@@ -535,7 +502,7 @@ __global__ void __launch_bounds__(256, 4) iss_generate_kernel(const __grid_const
                         qual[pos] = (uint8_t)(q + 33u);
                         if (wt > u32p(l.sErrThr)[q]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution(p, l, gp0, rd, pos);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, gp0, rd, pos);
                         }
                     }
                 }
@@ -602,9 +569,7 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 }
 
 // ---- host-visible launch helpers --------------------------------------------------------------------
-size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) {
-    return 2ull * img_cap + 8ull * T * 3 + 16ull * T * 2 + 4ull * T * 2 + 8ull * T * 5 + 4ull * err_cap + 4ull * ISS_QROW + 32;
-}
+size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) { return iss_make_layout(T, img_cap, err_cap).total; }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
     return cudaFuncSetAttribute(iss_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);

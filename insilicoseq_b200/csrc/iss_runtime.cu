@@ -256,6 +256,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.tile_shift = c->tile_pairs == 64 ? 6u : 5u;
     p.total_pairs = pairs;
     p.key = batch_key;
+    philox_round_keys(batch_key, p.rk);
+    p.lay = iss_make_layout(c->tile_pairs, c->img_cap, c->err_cap);
     p.out1 = s.d_out[0];
     p.out2 = s.d_out[1];
     p.img_cap = c->img_cap;
