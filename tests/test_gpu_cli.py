@@ -91,14 +91,14 @@ def test_gpu_count_invariance(tmp_path):
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     fa, abf, recs, ab = _write_inputs(tmp_path)
     outs = []
-    for g in (1, 2):
+    for g in sorted({1, 2, min(_ndev(), 8)}):
         out = str(tmp_path / ("g%d" % g))
-        app.main(["generate", "-g", fa, "-b", abf, "--model", "miseq", "-n", "6000", "--seed", "5", "--cpus", "4",
+        app.main(["generate", "-g", fa, "-b", abf, "--model", "miseq", "-n", "6000", "--seed", "5", "--cpus", "8",
                   "--gpus", str(g), "-o", out, "-q"])
         outs.append((open(out + "_R1.fastq", "rb").read(), open(out + "_R2.fastq", "rb").read()))
-    assert outs[0] == outs[1]
-    e1, e2 = _expected(recs, ab, "profile:miSeq_0.npz", 6000, 4, 5)
-    assert outs[1] == (e1, e2)
+    assert all(o == outs[0] for o in outs)
+    e1, e2 = _expected(recs, ab, "profile:miSeq_0.npz", 6000, 8, 5)
+    assert outs[-1] == (e1, e2)
 
 
 def test_cli_baseline_config0_basic_mode(tmp_path):
