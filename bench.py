@@ -194,6 +194,7 @@ def main():
     from insilicoseq_b200 import engine as eng_mod
     from insilicoseq_b200 import error_models
 
+    numa_node = parallel.bind_to_device_numa(local)  # before the pinned ring is allocated
     eng = eng_mod.Engine(local)
     if rank == 0:
         model = error_models.KDErrorModel(os.path.join(error_models.PROFILE_DIR, MODEL_FILE)).truncate(READ_LEN)
@@ -294,6 +295,7 @@ def main():
                          "avg_launch_ms": k_ms / max(launches, 1),
                          "note": "the kernel is integer-issue bound, not HBM bound (SURVEY.md 8d); see DESIGN.md section 6"},
             "clocks": clk,
+            "host": {"numa_node_rank0": numa_node, "cpus": os.cpu_count()},
         }
         if world == 1 and not args.no_cpu_baseline:
             per_core = 60_000

@@ -48,6 +48,8 @@ typedef struct iss_ctx iss_ctx;
 int iss_abi_version(void);
 const char *iss_last_error(void);
 int iss_device_count(int *count);
+/* PCI bus id ("0000:3b:00.0") of a device, for NUMA-aware placement of the host thread that owns its pinned ring. */
+int iss_device_pci_bus_id(int device, char *buf, int len);
 int iss_ctx_create(int device, iss_ctx **out);
 void iss_ctx_destroy(iss_ctx *ctx);
 

@@ -61,6 +61,7 @@ EXPORTS = {
     "iss_abi_version": (ctypes.c_int, []),
     "iss_last_error": (ctypes.c_char_p, []),
     "iss_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "iss_device_pci_bus_id": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "iss_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "iss_ctx_destroy": (None, [ctypes.c_void_p]),
     "iss_ctx_set_genome": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssRecord), ctypes.c_uint32]),

@@ -67,6 +67,7 @@ def generate_reads(args):
 
         def run_device(d):
             try:
+                parallel.bind_to_device_numa(d)
                 for cpu_number, (work, prefix) in jobs:
                     if parallel.chunk_owner(cpu_number, n_gpus) == d:
                         worker_iterator(work, error_model, cpu_number, prefix, seed, args.sequence_type, args.gc_bias,

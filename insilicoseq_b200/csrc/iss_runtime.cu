@@ -359,6 +359,12 @@ int iss_device_count(int *count) {
     return ISS_OK;
 }
 
+int iss_device_pci_bus_id(int device, char *buf, int len) {
+    if (!buf || len < 16) return fail(ISS_E_ARG, "buffer too small");
+    CU(cudaDeviceGetPCIBusId(buf, len, device));
+    return ISS_OK;
+}
+
 int iss_ctx_create(int device, iss_ctx **out) {
     if (!out) return fail(ISS_E_ARG, "out is null");
     int n = 0;
