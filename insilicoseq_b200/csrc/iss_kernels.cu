@@ -49,25 +49,30 @@ __device__ __forceinline__ uint32_t pick(const Philox4 &w, uint32_t j) {
 }
 __device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
-// Quality rows are stored as a 3-level 4-ary search tree (ISS_QBT_STRIDE words per row, built by the runtime):
-//   words  0..3   level 1: row[15], row[31], row[47], pad
-//   words  4..19  level 2: for each 16-entry group g: row[16g+3], row[16g+7], row[16g+11], pad
-//   words 32..95  the 64 leaves (0xFFFFFFFF padded)
-// #{j < 64 : w > row[j]} = 16*c1 + 4*c2 + c3 on a nondecreasing row: three dependent 16-byte loads.
-__device__ __forceinline__ uint32_t cnt3(uint32_t w, const uint4 &t) {
-    uint32_t c = 0;  // t.x <= t.y <= t.z: the last true test wins
-    if (w > t.x) c = 1;
-    if (w > t.y) c = 2;
-    if (w > t.z) c = 3;
+// Quality rows are stored as a 2-level 8-ary search tree (ISS_QBT_STRIDE = 96 words per row, 128 B aligned, built by
+// the runtime from the sorted 64-entry row r[]):
+//   words 0..7    splitters s_k = r[8k+7], k = 0..6, pad
+//   words 8..71   the eight 8-entry leaf groups, group g stored at physical slot (5 - g) & 7, so that the first
+//                 128-byte line holds the splitters and groups 5,4,3 (= phred 24..47): one line per draw for q >= 24
+// #{j < 64 : w > r[j]} = 8*cA + cB with cA = #{k : w > s_k}, cB = #{j < 7 : w > r[8cA + j]}; both counts are 3-step
+// binary searches in registers.  One dependent load stage.
+__device__ __forceinline__ uint32_t cnt7(uint32_t w, const uint4 &lo, const uint4 &hi) {
+    // sorted t0..t6 = lo.x lo.y lo.z lo.w hi.x hi.y hi.z
+    uint32_t c = (w > lo.w) ? 4u : 0u;
+    const uint32_t m1 = c ? hi.y : lo.y;
+    c += (w > m1) ? 2u : 0u;
+    const uint32_t m2 = (c & 4u) ? ((c & 2u) ? hi.z : hi.x) : ((c & 2u) ? lo.z : lo.x);
+    c += (w > m2) ? 1u : 0u;
     return c;
 }
-__device__ __forceinline__ uint32_t qbt_finish(const uint32_t *__restrict__ row, const uint4 &lvl1, uint32_t w) {
+__device__ __forceinline__ uint32_t qbt_search(const uint32_t *__restrict__ row, uint32_t w) {
     const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
-    const uint32_t c1 = cnt3(w, lvl1);
-    const uint32_t c2 = cnt3(w, __ldg(r4 + 1 + c1));
-    const uint32_t c3 = cnt3(w, __ldg(r4 + 8 + 4u * c1 + c2));
-    return 16u * c1 + 4u * c2 + c3;
+    const uint32_t cA = cnt7(w, __ldg(r4), __ldg(r4 + 1));
+    const uint32_t slot = (5u - cA) & 7u;
+    const uint32_t cB = cnt7(w, __ldg(r4 + 2 + 2u * slot), __ldg(r4 + 3 + 2u * slot));
+    return 8u * cA + cB;
 }
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
     if (enc == ISS_ENC_2BIT) {
@@ -453,36 +458,31 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
             const uint32_t b_begin = half ? hb : 0u, b_end = half ? nblk : hb;
             if (p.qual_mode == ISS_QUAL_KDE_MODE) {
                 const uint32_t *rows = p.m.qual_thr + u32p(l.sQrow)[rd];
-                uint4 l1a = {0, 0, 0, 0}, l1b = {0, 0, 0, 0};
                 if (b_begin < b_end) {
-                    const uint32_t pa = 2u * b_begin, pb = (pa + 1u < L) ? pa + 1u : pa;
-                    l1a = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pa * ISS_QBT_STRIDE));
-                    l1b = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pb * ISS_QBT_STRIDE));
+                    prefetch_l1(rows + (size_t)(2u * b_begin) * ISS_QBT_STRIDE);
+                    prefetch_l1(rows + (size_t)(2u * b_begin + 1u) * ISS_QBT_STRIDE);  // one pad row follows the table
                 }
                 for (uint32_t b = b_begin; b < b_end; ++b) {
                     const uint32_t pos = 2u * b;
-                    uint4 n1a = l1a, n1b = l1b;
-                    if (b + 1u < b_end) {  // level 1 of the next two rows is fetched before this step's dependent loads
-                        const uint32_t pa = pos + 2u, pb = (pa + 1u < L) ? pa + 1u : pa;
-                        n1a = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pa * ISS_QBT_STRIDE));
-                        n1b = __ldg(reinterpret_cast<const uint4 *>(rows + (size_t)pb * ISS_QBT_STRIDE));
+                    if (b + 1u < b_end) {  // the hot line of the next two rows travels to L1 while this step computes
+                        prefetch_l1(rows + (size_t)(pos + 2u) * ISS_QBT_STRIDE);
+                        prefetch_l1(rows + (size_t)(pos + 3u) * ISS_QBT_STRIDE);
                     }
                     const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
-                    const uint32_t q0 = qbt_finish(rows + (size_t)pos * ISS_QBT_STRIDE, l1a, w.x);
+                    const uint32_t q0 = qbt_search(rows + (size_t)pos * ISS_QBT_STRIDE, w.x);
                     qual[pos] = (uint8_t)(q0 + 33u);
                     if (w.y > u32p(l.sErrThr)[q0]) {
                         const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
                         if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, gp0, rd, pos);
                     }
                     if (pos + 1u < L) {
-                        const uint32_t q1 = qbt_finish(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, l1b, w.z);
+                        const uint32_t q1 = qbt_search(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, w.z);
                         qual[pos + 1u] = (uint8_t)(q1 + 33u);
                         if (w.w > u32p(l.sErrThr)[q1]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
                             if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution_overflow(p, gp0, rd, pos + 1u);
                         }
                     }
-                    l1a = n1a; l1b = n1b;
                 }
             } else {
                 for (uint32_t b = b_begin; b < b_end; ++b) {

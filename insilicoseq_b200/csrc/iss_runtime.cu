@@ -503,7 +503,7 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     }
     uint64_t off = align_up(sizeof(ModelHeader), 16);
     auto place = [&](uint64_t bytes) { uint64_t at = off; off = align_up(off + std::max<uint64_t>(bytes, 16), 16); return at; };
-    const uint64_t qual_bytes = m->qual_mode == ISS_QUAL_KDE ? 2ull * 4 * L * ISS_QBT_STRIDE * 4 : 0;
+    const uint64_t qual_bytes = m->qual_mode == ISS_QUAL_KDE ? (2ull * 4 * L + 1) * ISS_QBT_STRIDE * 4 : 0;
     h.frag_thr_off = place(8ull * m->n_frag);
     h.insert_thr_off = place(4ull * m->n_insert);
     h.qual_thr_off = place(qual_bytes);
@@ -524,20 +524,15 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     auto put = [&](uint64_t at, const void *src, uint64_t bytes) { if (src && bytes) memcpy(blob.data() + at, src, bytes); };
     put(h.frag_thr_off, m->frag_thr, 8ull * m->n_frag);
     put(h.insert_thr_off, m->insert_thr, 4ull * m->n_insert);
-    if (qual_bytes) {  // [2][4][L][64] sorted rows -> 3-level 4-ary search-tree rows (layout: iss_kernels.cu)
+    if (qual_bytes) {  // [2][4][L][64] sorted rows -> 2-level 8-ary search-tree rows (layout: iss_kernels.cu)
         uint32_t *dst = reinterpret_cast<uint32_t *>(blob.data() + h.qual_thr_off);
-        for (uint64_t row = 0; row < 8ull * L; ++row) {
-            const uint32_t *src = m->qual_thr + row * ISS_QROW;
+        for (uint64_t row = 0; row < 8ull * L + 1; ++row) {  // +1: an all-pad row so that row L of the last table may be prefetched
             uint32_t *t = dst + row * ISS_QBT_STRIDE;
-            t[0] = src[15]; t[1] = src[31]; t[2] = src[47]; t[3] = 0xFFFFFFFFu;
-            for (int g = 0; g < 4; ++g) {
-                t[4 + 4 * g + 0] = src[16 * g + 3];
-                t[4 + 4 * g + 1] = src[16 * g + 7];
-                t[4 + 4 * g + 2] = src[16 * g + 11];
-                t[4 + 4 * g + 3] = 0xFFFFFFFFu;
-            }
-            for (int j = 20; j < 32; ++j) t[j] = 0xFFFFFFFFu;
-            memcpy(t + 32, src, ISS_QROW * 4);
+            for (int j = 0; j < ISS_QBT_STRIDE; ++j) t[j] = 0xFFFFFFFFu;
+            if (row == 8ull * L) break;
+            const uint32_t *src = m->qual_thr + row * ISS_QROW;
+            for (int k = 0; k < 7; ++k) t[k] = src[8 * k + 7];
+            for (int g = 0; g < 8; ++g) memcpy(t + 8 + 8 * ((5 - g) & 7), src + 8 * g, 32);
         }
     }
     put(h.subst_n_off, m->subst_n, 2ull * L * 4);
