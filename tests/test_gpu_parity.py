@@ -81,3 +81,77 @@ def test_against_oracle_at_scale(spec, npairs):
     assert first_diff(r2, o2) is None
     if spec in ("profile:MiSeq", "models/stress20.npz"):
         assert stats["slow_reads"] > 0  # the sequential indel replay really ran
+
+
+def test_error_conventions_at_the_c_abi():
+    """ISS_E_CHAR for characters outside util.rev_comp's dictionary (the reference raises KeyError mid-run),
+    ISS_E_SHORT for a record not longer than the read length (reference: AssertionError, generator.py:130),
+    ISS_E_STATE for calls out of order."""
+    from insilicoseq_b200 import _lib, error_models
+    from insilicoseq_b200.engine import Engine, philox_key
+
+    with Engine(0) as e:
+        with pytest.raises(_lib.NativeError) as err:
+            e.set_genome([("bad", b"ACGTACGTXACGT" * 20)])
+        assert err.value.code == _lib.ISS_E_CHAR and "0x58" in str(err.value)
+        with pytest.raises(_lib.NativeError) as err:
+            e.submit([(0, 0, 10, 0, 0, 1)])
+        assert err.value.code == _lib.ISS_E_STATE
+        e.set_genome([("ok", fixtures.synth_genome(1, 500)), ("short", fixtures.synth_genome(2, 126)), ("u", b"ACGU" * 100)][:2])
+        e.set_model(error_models.KDErrorModel(fixtures.model_path("profile:HiSeq")))
+        with pytest.raises(_lib.NativeError) as err:
+            e.submit([(1, 0, 10, 0, 0, philox_key(1, 0))])  # len == L: `assert read_length < len(record.seq)` fails
+        assert err.value.code == _lib.ISS_E_SHORT
+        with pytest.raises(RuntimeError):
+            e.submit([(0, 0, 10, 0, 0, 1)], sequence_type="nanopore")
+        # the engine is still usable after the rejected calls
+        out = b"".join(b.r1.tobytes() for b in e.generate([(0, 0, 5, 0, 0, philox_key(1, 0))]))
+        assert out.count(b"\n") == 20
+
+
+def test_uracil_is_rejected_like_the_reference_keyerror():
+    from insilicoseq_b200 import _lib
+    from insilicoseq_b200.engine import Engine
+
+    with Engine(0) as e:
+        with pytest.raises(_lib.NativeError) as err:
+            e.set_genome([("rna", b"ACGU" * 100)])
+        assert err.value.code == _lib.ISS_E_CHAR
+
+
+def test_forced_indels_like_the_reference_tests():
+    """iss/test/test_error_model.py:59-105 force events with probability 1.0 in the model's dicts (ins at position 1,
+    del at positions 0/1) and check the list semantics of introduce_indels / adjust_seq_length.  Same forcing here,
+    through the plugin surface (dict attributes of the model), against the oracle; every read takes the replay path."""
+    from insilicoseq_b200 import error_models
+    from insilicoseq_b200 import engine as eng_mod
+
+    m = error_models.KDErrorModel(fixtures.model_path("models/ecoli.npz"))
+    m.ins_for[1]["G"] = 1.0
+    m.del_for[0]["A"] = 1.0
+    m.del_rev[0]["C"] = 1.0
+    m.del_rev[1]["G"] = 1.0
+    om = oracle.OracleModel(fixtures.model_path("models/ecoli.npz"))
+    ins_p, del_p = om.table("ins_p").copy(), om.table("del_p").copy()
+    ins_p[0, 1, list(m.ins_for[1].keys()).index("G")] = 1.0
+    del_p[0, 0, "ACGT".index("A")] = 1.0
+    del_p[1, 0, "ACGT".index("C")] = 1.0
+    del_p[1, 1, "ACGT".index("G")] = 1.0
+    om.set_table("ins_p", ins_p)
+    om.set_table("del_p", del_p)
+    genome = ("GG" + "GTACC" * 100 + "GG" + "ATATA" * 100).encode()
+    with eng_mod.Engine(0) as e:
+        e.set_genome([("ref_genome", genome)])
+        e.set_model(m)
+        items = eng_mod.worker_items([(0, 3000)], 0, 87, e.record_lengths, e.read_length)
+        r1, r2 = b"", b""
+        for b in e.generate(items):
+            r1 += b.r1.tobytes()
+            r2 += b.r2.tobytes()
+        st = e.stats()
+    o1, o2 = oracle.run_worker(om, [("ref_genome", genome, 3000)], 0, 87)
+    assert first_diff(r1, o1) is None and first_diff(r2, o2) is None
+    assert st["slow_reads"] >= 3000  # every forward read has the forced insertion
+    seqs = r1.split(b"\n")[1::4]
+    assert all(len(s) == 20 for s in seqs)
+    assert sum(s[1:2] == b"G" or s[0:1] != b"A" for s in seqs) == len(seqs)

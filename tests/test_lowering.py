@@ -145,3 +145,31 @@ def test_product_fails_loudly_without_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(_lib.NativeError):
         eng_mod.Engine(0)
+
+
+def test_bad_model_files_exit_like_the_reference(tmp_path):
+    """iss/test/test_error_model.py:108-110 (test_bad_err_mod): an unreadable profile logs and exits."""
+    empty = tmp_path / "empty_file"
+    empty.write_bytes(b"")
+    with pytest.raises(SystemExit):
+        error_models.KDErrorModel(str(empty))
+    from insilicoseq_b200 import generator
+
+    with pytest.raises(SystemExit):
+        generator.load_error_model("kde", None, None, None, None, False)  # --model is required in --mode kde
+    with pytest.raises(SystemExit):
+        generator.load_error_model("kde", None, "hiseq", 400, None, False)  # fragment length without sd
+
+
+def test_lowering_rejects_what_the_reference_could_not_sample():
+    m = error_models.KDErrorModel(fixtures.model_path("models/ecoli.npz"))
+    m.subst_choices_for[3]["A"] = (["T", "C", "G"], [0.5, 0.6, 0.2])  # np.random.choice: probabilities do not sum to 1
+    with pytest.raises(ValueError):
+        m.device_tables()
+    m = error_models.KDErrorModel(fixtures.model_path("models/ecoli.npz"))
+    m.ins_for[2]["G"] = 1.0       # forced events as in iss/test/test_error_model.py:64-65
+    m.del_for[0]["A"] = float("nan")  # `u < nan` is False: never fires
+    t = m.device_tables().arrays
+    lane = list(m.ins_for[2].keys()).index("G")
+    assert (t["ins_nz"][0, 2] >> lane) & 1 and t["ins_thr"][0, 2, lane] == 0xFFFFFFFF
+    assert not (t["del_nz"][0, 0] >> error_models.BASES.index("A")) & 1
