@@ -142,6 +142,10 @@ typedef struct {
     uint64_t batch_pairs;     /* pairs per ring slot; 0 = default */
     uint32_t n_slots;         /* ring depth (>= 2); 0 = default */
     uint32_t device_only;     /* 1: keep FASTQ in HBM (no D2H) -- kernel-throughput measurements */
+    uint32_t tma_gather;      /* 1: stage each read's packed genome window into shared memory with cp.async.bulk + mbarrier
+                                 instead of LDG (needs L >= 96).  Measured 1-2 % slower on B200 for both an L2-resident and
+                                 an HBM-random genome, hence off by default. */
+    uint32_t reserved;
 } iss_gen_opts;
 
 /* Starts asynchronous generation of all items (order preserved).  Records with len <= L are the

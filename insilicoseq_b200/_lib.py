@@ -40,7 +40,8 @@ class IssWorkItem(ctypes.Structure):
 
 class IssGenOpts(ctypes.Structure):
     _fields_ = [("sequence_type", ctypes.c_uint32), ("gc_bias", ctypes.c_uint32), ("batch_pairs", ctypes.c_uint64),
-                ("n_slots", ctypes.c_uint32), ("device_only", ctypes.c_uint32)]
+                ("n_slots", ctypes.c_uint32), ("device_only", ctypes.c_uint32), ("tma_gather", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
 
 
 class IssBatch(ctypes.Structure):

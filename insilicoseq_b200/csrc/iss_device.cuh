@@ -264,6 +264,8 @@ struct GenParams {
     uint32_t gc_thr;          // accept iff w < gc_thr  (ceil(0.90 * 2^32))
     unsigned long long *counters;  // [0] slow reads [1] substitution events [2] error flags
     uint32_t store_mutations;
+    uint32_t tma_gather;           // 1: genome windows are staged into shared memory with cp.async.bulk (needs 15 + stage_bytes <= L)
+    uint32_t stage_bytes;          // 16 * ceil((L + 125) / 64)
     uint32_t pad0;
     uint4 *events;                 // mutation records of this batch (--store_mutations)
     unsigned long long *event_count;

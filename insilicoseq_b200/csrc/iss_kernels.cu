@@ -88,6 +88,38 @@ __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_
 
 // bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
 
+// ---- mbarrier / TMA bulk-copy helpers (genome windows: global -> shared, completion counted on an mbarrier) -------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+// Staged span of a read's window: the 16-byte aligned run of packed genome bytes that covers every word the gather
+// touches ([wabs - 15, wabs + L + 46) in bases), placed 16-byte aligned inside the record's (not yet written) quality line.
+__device__ __forceinline__ uint64_t stage_src_byte(uint64_t wabs) { return ((wabs - 16u) >> 2) & ~(uint64_t)15u; }
+__device__ __forceinline__ uint32_t stage_dst_off(uint32_t img_off, uint32_t seq_off, uint32_t L) {
+    return ((img_off + seq_off + L + 3u + 15u) & ~15u);  // absolute offset from iss_smem
+}
+
 // ---- mutation events (--store_mutations, error_models/__init__.py:98-108,197-207,211-221) -------------------
 // One 16-byte record per VCF line, appended in arbitrary order; the host sorts by key and formats the text.
 //   key = pair (batch-local) << 20 | orientation << 19 | phase << 18 (0 indel loop, 1 substitutions) | position << 4 | order
@@ -219,6 +251,9 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const Lay &l = p.lay;
     if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
+    const uint32_t mbar = smem_addr(iss_smem + l.sCtl + 16u);  // 8-byte mbarrier behind the control words
+    if (tid == 0 && p.tma_gather) mbar_init(mbar, 2u * T);      // every (pair, orientation) thread arrives once per tile
+    uint32_t tile_parity = 0;
     const uint64_t ntiles = (p.total_pairs + T - 1) / T;
     bool store_pending = false;
     // roles: q4 = 0..3 -> orientation o = q4 >> 1, position half = q4 & 1; rd = index of the read in the tile
@@ -354,13 +389,27 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
             img[w++] = '/';
             img[w++] = (uint8_t)('1' + o);
             img[w++] = '\n';
-            u32p(l.sSeqOff)[rd] = (uint32_t)(img - imgp(l, o)) + w;
+            const uint32_t seq_off = (uint32_t)(img - imgp(l, o)) + w;
+            u32p(l.sSeqOff)[rd] = seq_off;
             img[w + L] = '\n';
             img[w + L + 1] = '+';
             img[w + L + 2] = '\n';
             img[w + 2 * L + 3] = '\n';
+            if (p.tma_gather) {
+                if (rec->enc == ISS_ENC_2BIT) {  // TMA: packed window -> the record's quality line (overwritten in phase 4)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_expect_tx(mbar, p.stage_bytes);
+                    bulk_load(smem_addr(iss_smem + stage_dst_off(l.img[o], seq_off, L)),
+                              reinterpret_cast<const uint8_t *>(p.g.packed) + stage_src_byte(u64p(l.sWabs)[rd]), p.stage_bytes, mbar);
+                } else {
+                    mbar_arrive(mbar);
+                }
+            }
+        } else if (p.tma_gather && half == 0) {
+            mbar_arrive(mbar);  // lanes of a partial tile keep the arrival count constant
         }
         __syncthreads();
+        if (p.tma_gather) { mbar_wait(mbar, tile_parity); tile_parity ^= 1u; }
 
         // ---- phase 2b: gather the windows, flattened over (read, 16-base chunk)
         {
@@ -374,8 +423,18 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
                 const uint64_t wabs = u64p(l.sWabs)[rd];
                 if (u32p(l.sEnc)[rd] == ISS_ENC_2BIT) {
                     const uint64_t q = ro ? (wabs + L - 16u * j - 16u) : (wabs + 16u * j);
-                    const uint32_t wi = (uint32_t)(q >> 4), sh = ((uint32_t)q & 15u) * 2u;
-                    const uint32_t w0 = __ldg(p.g.packed + wi), w1 = __ldg(p.g.packed + wi + 1);
+                    const uint32_t sh = ((uint32_t)q & 15u) * 2u;
+                    uint32_t w0, w1;
+                    if (p.tma_gather) {  // words of the span staged by TMA in the record's quality line
+                        const uint32_t *st = u32p(stage_dst_off(l.img[ro], u32p(l.sSeqOff)[rd], L));
+                        const uint32_t wi = (uint32_t)((q >> 4) - (stage_src_byte(wabs) >> 2));
+                        w0 = st[wi];
+                        w1 = st[wi + 1];
+                    } else {
+                        const uint32_t wi = (uint32_t)(q >> 4);
+                        w0 = __ldg(p.g.packed + wi);
+                        w1 = __ldg(p.g.packed + wi + 1);
+                    }
                     uint32_t w = __funnelshift_r(w0, w1, sh);
                     if (ro) w ^= 0xAAAAAAAAu;  // complement every base: code ^ 2
 #pragma unroll

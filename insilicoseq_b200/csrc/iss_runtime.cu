@@ -11,6 +11,7 @@
 #include <nccl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -271,6 +272,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.gc_thr = 3865470567u;  // ceil(0.90 * 2^32): u < 0.90  <=>  w < gc_thr   (generator.py:88)
     p.counters = c->d_counters;
     p.store_mutations = c->mh.store_mutations;
+    p.stage_bytes = 16u * ((L + 125u + 63u) / 64u);
+    p.tma_gather = (15u + p.stage_bytes <= L) && c->opts.tma_gather;
     p.events = s.d_events;
     p.event_count = s.d_evcount;
     p.event_cap = s.event_cap;
@@ -658,6 +661,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     if (o.n_slots == 0) o.n_slots = 3;
     if (o.n_slots < 2 && !o.device_only) o.n_slots = 2;
     if (o.n_slots > 16) o.n_slots = 16;
+    if (const char *e = getenv("ISS_TMA_GATHER")) o.tma_gather = (e[0] == '1');  // A/B switch for benchmarks
     uint64_t max_rec = 0, total = 0;
     for (uint64_t k = 0; k < n_items; ++k) {
         const iss_work_item &it = items[k];

@@ -139,7 +139,8 @@ class Engine(object):
             e.record_lengths = list(src.record_lengths)
 
     # -- generation -------------------------------------------------------------------------------------
-    def submit(self, items, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0, device_only=False):
+    def submit(self, items, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0, device_only=False,
+               tma_gather=False):
         """items: iterable of dicts/tuples (record, cpu_number, n_pairs, i0, item_base, key)."""
         items = list(items)
         arr = (_lib.IssWorkItem * max(len(items), 1))()
@@ -155,7 +156,8 @@ class Engine(object):
         if sequence_type not in st:
             # generator.py:139 raises RuntimeError for the forward read of an unknown sequence type
             raise RuntimeError("sequence type '%s' is not supported" % sequence_type)
-        opts = _lib.IssGenOpts(st[sequence_type], int(bool(gc_bias)), int(batch_pairs), int(n_slots), int(bool(device_only)))
+        opts = _lib.IssGenOpts(st[sequence_type], int(bool(gc_bias)), int(batch_pairs), int(n_slots), int(bool(device_only)),
+                               int(bool(tma_gather)), 0)
         self._device_only = bool(device_only)
         _lib.check(self._lib.iss_ctx_submit(self._h, arr, len(items), ctypes.byref(opts)))
 

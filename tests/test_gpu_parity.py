@@ -56,6 +56,16 @@ def test_store_mutations_vcf_against_oracle(spec, npairs, bp):
     assert len(ov) > 1000
 
 
+@pytest.mark.parametrize("name", ["novaseq_single", "hiseq_multi_short", "miseq_legacy_indels", "miseq150_bench_model",
+                                  "amplicon_miseq", "nextseq_large_digest", "basic_mode"])
+def test_tma_staged_gather_path(name):
+    """opts.tma_gather: genome windows staged into shared memory by cp.async.bulk + mbarrier (2-bit records, L >= 96)."""
+    case, exp = fixtures.load_case(name)
+    r1, r2, _ = run_product(case, tma_gather=True, batch_pairs=97)
+    assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
+    assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
+
+
 @pytest.mark.parametrize("batch_pairs", [1, 7, 64, 100])
 @pytest.mark.parametrize("name", ["hiseq_multi_short", "stress_indels_dense"])
 def test_batch_size_invariance(name, batch_pairs):
