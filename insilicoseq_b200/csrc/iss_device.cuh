@@ -262,6 +262,7 @@ struct GenParams {
     uint8_t *scratch;         // slow-path scratch: gridDim.x * ISS_SLOW_SLOTS * scratch_stride bytes
     uint32_t scratch_stride;  // >= 5L + 8
     uint32_t gc_thr;          // accept iff w < gc_thr  (ceil(0.90 * 2^32))
+    uint32_t slow_slots;      // reads replayed per round: min(ISS_SLOW_SLOTS, 4 * err_cap / L) (their draw masks alias the substitution list)
     unsigned long long *counters;  // [0] slow reads [1] substitution events [2] error flags
     uint32_t store_mutations;
     uint32_t tma_gather;           // 1: genome windows are staged into shared memory with cp.async.bulk (needs 15 + stage_bytes <= L)

@@ -176,7 +176,8 @@ __device__ __noinline__ void apply_substitution_overflow(const GenParams &p, uin
 //   insertion at index nucl+1  == push on the LIFO (a later lane lands in front of an earlier one)
 //   pop(nucl)                  == drop cur; the next element takes index nucl WITHOUT being examined
 //   IndexError at seq[nucl]    == the stream is exhausted: nothing further is drawn
-__device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rd, uint8_t *scratch) {
+__device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rd, uint8_t *scratch,
+                              const uint8_t *mask /* shared: per position, bits 0-3 insertion lanes that fire, 4-7 deletion fires for base b */) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
     uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
@@ -184,30 +185,22 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
     uint8_t *stk = scratch + L;
     for (uint32_t k = 0; k < L; ++k) orig[k] = seq[k];
     const uint64_t P = u64p(l.sP)[pair];
-    const uint32_t att8 = u32p(l.sAtt)[pair] << 8;
-    const uint32_t sIns = iss_read_stream(o, ISS_K_INS) | att8, sDel = iss_read_stream(o, ISS_K_DEL) | att8;
     uint32_t sp = 0, k = 0, outlen = 0;
     for (uint32_t nucl = 0; nucl + 1 < L; ++nucl) {
         uint32_t cur;
         if (sp) cur = stk[--sp]; else if (k < L) cur = orig[k++]; else break;
         if (!is_acgt(cur)) { seq[outlen++] = (uint8_t)cur; continue; }
         const uint32_t tb = o * L + nucl;
-        const uint32_t m = p.m.ins_nz[tb];
-        if (m) {
-            const Philox4 w = philox4x32_10_rk(nucl, sIns, (uint32_t)P, (uint32_t)(P >> 32), p.rk);
+        const uint32_t mk = mask[nucl];  // every draw of this read was made in parallel (phase 3b)
+        if (mk & 15u) {
             for (uint32_t lane = 0; lane < 4; ++lane)
-                if (((m >> lane) & 1u) && pick(w, lane) <= p.m.ins_thr[tb * 4 + lane]) {
+                if ((mk >> lane) & 1u) {
                     const uint32_t ib = p.m.ins_base[tb * 4 + lane];
                     stk[sp++] = (uint8_t)ib;
                     if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, lane, cur, cur, ib, 255u);
                 }
         }
-        const uint32_t code = base_code(cur);
-        bool del = false;
-        if ((p.m.del_nz[tb] >> code) & 1u) {
-            const Philox4 w = philox4x32_10_rk(nucl >> 2, sDel, (uint32_t)P, (uint32_t)(P >> 32), p.rk);
-            del = pick(w, nucl & 3u) <= p.m.del_thr[tb * 4 + code];
-        }
+        const bool del = (mk >> (4u + base_code(cur))) & 1u;
         if (del) {
             uint32_t x;
             if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;  // "ref" is read after the pop: IndexError -> no record
@@ -497,13 +490,52 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
         __syncthreads();
         {
             const uint32_t nslow = u32p(l.sCtl)[1];
-            if (nslow) {  // warp-uniform; rare for real models
-                for (uint32_t base = 0; base < nslow; base += ISS_SLOW_SLOTS) {
-                    if (tid < ISS_SLOW_SLOTS && base + tid < nslow)
+            if (nslow) {  // block-uniform; rare for the bundled models, 15 % of the pairs for a dense fitted model
+                // phase 3b: all indel draws of the queued reads, in parallel.  A draw is addressed by (read, position, lane)
+                // and does not depend on the evolving sequence -- only WHICH deletion threshold applies depends on the
+                // current base -- so the mask holds the insertion lanes that fire and, per base, whether a deletion
+                // fires.  The masks live in the (still unused) substitution list.
+                uint8_t *masks = reinterpret_cast<uint8_t *>(u32p(l.sErr));
+                const uint32_t ngrp = (L + 2u) >> 2;  // groups of 4 loop positions 0..L-2
+                for (uint32_t base = 0; base < nslow; base += p.slow_slots) {
+                    const uint32_t nround = (nslow - base < p.slow_slots) ? (nslow - base) : p.slow_slots;
+                    for (uint32_t idx = tid; idx < nround * ngrp; idx += blockDim.x) {
+                        const uint32_t sidx = idx / ngrp, g = idx - sidx * ngrp;
+                        const uint32_t srd = u32p(l.sSlow)[base + sidx];
+                        const uint32_t so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
+                        const uint64_t sP = u64p(l.sP)[sp_];
+                        const uint32_t sa8 = u32p(l.sAtt)[sp_] << 8;
+                        Philox4 dblk = {0, 0, 0, 0};
+                        bool have_d = false;
+                        for (uint32_t j = 0; j < 4; ++j) {
+                            const uint32_t nucl = 4u * g + j;
+                            if (nucl + 1u >= L) break;
+                            const uint32_t tb = so * L + nucl;
+                            uint32_t mk = 0;
+                            const uint32_t m = p.m.ins_nz[tb];
+                            if (m) {
+                                const Philox4 w = philox4x32_10_rk(nucl, iss_read_stream(so, ISS_K_INS) | sa8, (uint32_t)sP, (uint32_t)(sP >> 32), p.rk);
+                                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.ins_thr) + tb);
+                                mk = (((m & 1u) && w.x <= t.x) ? 1u : 0u) | (((m & 2u) && w.y <= t.y) ? 2u : 0u) |
+                                     (((m & 4u) && w.z <= t.z) ? 4u : 0u) | (((m & 8u) && w.w <= t.w) ? 8u : 0u);
+                            }
+                            const uint32_t dz = p.m.del_nz[tb];
+                            if (dz) {
+                                if (!have_d) { dblk = philox4x32_10_rk(g, iss_read_stream(so, ISS_K_DEL) | sa8, (uint32_t)sP, (uint32_t)(sP >> 32), p.rk); have_d = true; }
+                                const uint32_t word = pick(dblk, j);
+                                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.del_thr) + tb);
+                                mk |= (((dz & 1u) && word <= t.x) ? 16u : 0u) | (((dz & 2u) && word <= t.y) ? 32u : 0u) |
+                                      (((dz & 4u) && word <= t.z) ? 64u : 0u) | (((dz & 8u) && word <= t.w) ? 128u : 0u);
+                            }
+                            masks[sidx * L + nucl] = (uint8_t)mk;
+                        }
+                    }
+                    __syncthreads();
+                    if (tid < nround)
                         replay_indels(p, l, gp0, u32p(l.sSlow)[base + tid],
-                                      p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride);
+                                      p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride, masks + tid * L);
+                    __syncthreads();
                 }
-                __syncthreads();
                 if (tid == 0) atomicAdd(p.counters + 0, (unsigned long long)nslow);
             }
         }

@@ -269,6 +269,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.chunk_magic = (uint32_t)((0x100000000ull + p.nchunk - 1) / p.nchunk);
     p.scratch = s.d_scratch;
     p.scratch_stride = (uint32_t)align_up(5ull * L + 8, 16);
+    p.slow_slots = std::max<uint32_t>(1u, std::min<uint32_t>(ISS_SLOW_SLOTS, 4u * c->err_cap / L));
     p.gc_thr = 3865470567u;  // ceil(0.90 * 2^32): u < 0.90  <=>  w < gc_thr   (generator.py:88)
     p.counters = c->d_counters;
     p.store_mutations = c->mh.store_mutations;
