@@ -245,8 +245,9 @@ struct GenParams {
     uint32_t err_thr[ISS_QROW];
     const DevSegment *segs;
     uint32_t nseg;
-    uint32_t tile_pairs;      // T: pairs per tile (32 or 64); blockDim.x == 4T
+    uint32_t tile_pairs;      // T: pairs per tile (32 or 64); blockDim.x == 2 * S * T
     uint32_t tile_shift;      // log2(T)
+    uint32_t split_shift;     // log2(S), S = threads per read (2, or 4 for long reads)
     uint64_t total_pairs;
     uint64_t key;             // Philox key of every pair of this launch (a batch never spans two workers)
     uint32_t rk[20];          // the ten Philox round keys (k0 + r*W0, k1 + r*W1): constant-bank operands of the LOP3s

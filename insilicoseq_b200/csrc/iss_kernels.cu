@@ -2,7 +2,8 @@
 //
 // One persistent kernel (iss_generate_kernel) produces finished FASTQ text for a batch of read pairs:
 //
-//   tile = T pairs (2T reads), blockDim = 4T: thread <-> (pair, orientation, position half); a warp holds 32
+//   tile = T pairs (2T reads), blockDim = 2*S*T: thread <-> (pair, orientation, one of S position parts; S = 2, or 4
+//   for long reads whose images leave room for only 2 CTAs/SM); a warp holds 32
 //   different pairs in the same role, so its lanes walk the model tables in lockstep
 //   phase 1  pair setup        insert size, window positions, quality bins        generator.py:121-177, kde.py:72-97
 //   phase 2  headers + gather  2-bit (or byte) genome windows -> ASCII in smem     generator.py:146-153,179-183, util.py:48-92
@@ -237,10 +238,8 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
 
 }  // namespace
 
-#ifndef ISS_MIN_BLOCKS
-#define ISS_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const __grid_constant__ GenParams p) {
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const Lay &l = p.lay;
     if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
@@ -249,9 +248,10 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
     uint32_t tile_parity = 0;
     const uint64_t ntiles = (p.total_pairs + T - 1) / T;
     bool store_pending = false;
-    // roles: q4 = 0..3 -> orientation o = q4 >> 1, position half = q4 & 1; rd = index of the read in the tile
+    // roles: q4 = 0..2S-1 -> orientation o = q4 / S, position part = q4 % S; rd = index of the read in the tile
     const uint32_t q4 = tid >> p.tile_shift, pair = tid & (T - 1u);
-    const uint32_t o = q4 >> 1, half = q4 & 1u, rd = o * T + pair;
+    const uint32_t S = 1u << p.split_shift, nroles = 2u * S;
+    const uint32_t o = q4 >> p.split_shift, half = q4 & (S - 1u), rd = o * T + pair;
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t gp0 = tile * T;
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
         uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
         const uint32_t nnz_all = p.n_nz[0] + p.n_nz[1];
         if (valid && nnz_all) {
-            const uint32_t n_begin = (q4 * nnz_all) >> 2, n_end = ((q4 + 1u) * nnz_all) >> 2;
+            const uint32_t n_begin = (q4 * nnz_all) / nroles, n_end = ((q4 + 1u) * nnz_all) / nroles;
             uint32_t fired = 0;  // bit so set when read orientation so has an event
             uint32_t cached = 0xFFFFFFFFu;
             Philox4 dblk = {0, 0, 0, 0};
@@ -540,13 +540,13 @@ __global__ void __launch_bounds__(256, ISS_MIN_BLOCKS) iss_generate_kernel(const
             }
         }
 
-        // ---- phase 4: phred scores + substitution tests.  Thread (o, half) walks half of the read's Philox QUAL
+        // ---- phase 4: phred scores + substitution tests.  Thread (o, part) walks its part of the read's Philox QUAL
         //      blocks; the 32 lanes of a warp are 32 pairs at the same position, so they share <= 3 quality rows.
         if (valid) {
             uint8_t *qual = seq + L + 3;
             const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
-            const uint32_t nblk = (L + 1u) >> 1, hb = (nblk + 1u) >> 1;
-            const uint32_t b_begin = half ? hb : 0u, b_end = half ? nblk : hb;
+            const uint32_t nblk = (L + 1u) >> 1;
+            const uint32_t b_begin = (half * nblk) >> p.split_shift, b_end = ((half + 1u) * nblk) >> p.split_shift;
             if (p.qual_mode == ISS_QUAL_KDE_MODE) {
                 const uint32_t *rows = p.m.qual_thr + u32p(l.sQrow)[rd];
                 if (b_begin < b_end) {
@@ -663,16 +663,22 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) { return iss_make_layout(T, img_cap, err_cap).total; }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
-    return cudaFuncSetAttribute(iss_generate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
 }
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
-    iss_generate_kernel<<<grid, 4 * p.tile_pairs, smem, stream>>>(p);
+    const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
+    if (threads > 256) iss_generate_kernel<512, 2><<<grid, threads, smem, stream>>>(p);
+    else iss_generate_kernel<256, 4><<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t iss_occupancy(uint32_t T, size_t smem, int *blocks_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel, (int)(4 * T), smem);
+cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, size_t smem, int *blocks_per_sm) {
+    const int threads = (int)((2u << split_shift) * T);
+    if (threads > 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4>, threads, smem);
 }
 
 cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {

@@ -98,7 +98,7 @@ struct iss_ctx {
     uint64_t cur_item = 0, cur_off = 0;  // planner cursor
     uint64_t batch_pairs = 0, slot_cap = 0, max_rec = 0;
     uint32_t n_slots = 0, max_segs = 0;
-    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 1024, grid = 0;
+    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 1024, grid = 0, split_shift = 1;
     size_t smem = 0;
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
@@ -255,6 +255,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.nseg = nseg;
     p.tile_pairs = c->tile_pairs;
     p.tile_shift = c->tile_pairs == 64 ? 6u : 5u;
+    p.split_shift = c->split_shift;
     p.total_pairs = pairs;
     p.key = batch_key;
     philox_round_keys(batch_key, p.rk);
@@ -692,8 +693,15 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
     }
     int bps = 0;
-    CU(iss_occupancy(T, smem, &bps));
+    uint32_t split_shift = 1;
+    CU(iss_occupancy(T, split_shift, smem, &bps));
     if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
+    if (bps <= 2 && T == 64) {  // long reads: the images leave room for <= 2 CTAs/SM -> 4 threads per read keep 32 warps/SM
+        int bps4 = 0;
+        CU(iss_occupancy(T, 2, smem, &bps4));
+        if (bps4 >= bps) { split_shift = 2; bps = bps4; }
+    }
+    c->split_shift = split_shift;
     const uint32_t grid = (uint32_t)(c->sm_count * bps);
     const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
     const uint32_t max_segs = 1u << 16;

@@ -16,7 +16,7 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "insilicoseq_b20
                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cub = [f for f in os.listdir(tmp) if f.startswith("iss_kernels.") and f.endswith(".cubin")][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(sass) if l.startswith(".text._Z19iss_generate_kernel")][0]
+start = [i for i, l in enumerate(sass) if l.startswith(".text._Z19iss_generate_kernelILi%s" % os.environ.get("ISS_KERNEL_THREADS", "256"))][0]
 ins, cur, inl = [], None, None
 for l in sass[start + 1:]:
     if (l.startswith(".text.") or l.startswith("\t.section")) and ins:
