@@ -73,7 +73,6 @@ __device__ __forceinline__ uint32_t qbt_search(const uint32_t *__restrict__ row,
     const uint32_t cB = cnt7(w, __ldg(r4 + 2 + 2u * slot), __ldg(r4 + 3 + 2u * slot));
     return 8u * cA + cB;
 }
-__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
     if (enc == ISS_ENC_2BIT) {
@@ -250,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
     bool store_pending = false;
     // roles: q4 = 0..2S-1 -> orientation o = q4 / S, position part = q4 % S; rd = index of the read in the tile
     const uint32_t q4 = tid >> p.tile_shift, pair = tid & (T - 1u);
-    const uint32_t S = 1u << p.split_shift, nroles = 2u * S;
+    const uint32_t S = 1u << p.split_shift;
     const uint32_t o = q4 >> p.split_shift, half = q4 & (S - 1u), rd = o * T + pair;
 
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -457,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
         const uint32_t nnz_all = p.n_nz[0] + p.n_nz[1];
         if (valid && nnz_all) {
-            const uint32_t n_begin = (q4 * nnz_all) / nroles, n_end = ((q4 + 1u) * nnz_all) / nroles;
+            const uint32_t n_begin = (q4 * nnz_all) >> (p.split_shift + 1u), n_end = ((q4 + 1u) * nnz_all) >> (p.split_shift + 1u);
             uint32_t fired = 0;  // bit so set when read orientation so has an event
             uint32_t cached = 0xFFFFFFFFu;
             Philox4 dblk = {0, 0, 0, 0};
@@ -549,16 +548,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             const uint32_t b_begin = (half * nblk) >> p.split_shift, b_end = ((half + 1u) * nblk) >> p.split_shift;
             if (p.qual_mode == ISS_QUAL_KDE_MODE) {
                 const uint32_t *rows = p.m.qual_thr + u32p(l.sQrow)[rd];
-                if (b_begin < b_end) {
-                    prefetch_l1(rows + (size_t)(2u * b_begin) * ISS_QBT_STRIDE);
-                    prefetch_l1(rows + (size_t)(2u * b_begin + 1u) * ISS_QBT_STRIDE);  // one pad row follows the table
-                }
                 for (uint32_t b = b_begin; b < b_end; ++b) {
                     const uint32_t pos = 2u * b;
-                    if (b + 1u < b_end) {  // the hot line of the next two rows travels to L1 while this step computes
-                        prefetch_l1(rows + (size_t)(pos + 2u) * ISS_QBT_STRIDE);
-                        prefetch_l1(rows + (size_t)(pos + 3u) * ISS_QBT_STRIDE);
-                    }
                     const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
                     const uint32_t q0 = qbt_search(rows + (size_t)pos * ISS_QBT_STRIDE, w.x);
                     qual[pos] = (uint8_t)(q0 + 33u);

@@ -164,3 +164,24 @@ def test_forced_indels_like_the_reference_tests():
     assert st["slow_reads"] >= 3000  # every forward read has the forced insertion
     seqs = r1.split(b"\n")[1::4]
     assert all(len(s) == 20 for s in seqs)
+
+
+def test_work_item_split_across_submits():
+    """An item may be generated in pieces (i0 > 0) -- by another submit or another GPU: draws are counter addressed,
+    so the pieces concatenate to the whole."""
+    from insilicoseq_b200 import error_models
+    from insilicoseq_b200.engine import Engine, philox_key
+
+    genome = fixtures.synth_genome(77, 40000).encode()
+    key = philox_key(9, 4)
+    with Engine(0) as e:
+        e.set_genome([("split_rec", genome)])
+        e.set_model(error_models.KDErrorModel(fixtures.model_path("profile:HiSeq")))
+        whole = b"".join(b.r2.tobytes() for b in e.generate([(0, 4, 5000, 0, 123, key)]))
+        parts = b""
+        for i0, n in ((0, 1), (1, 998), (999, 1), (1000, 3000), (4000, 1000)):
+            parts += b"".join(b.r2.tobytes() for b in e.generate([(0, 4, n, i0, 123, key)], batch_pairs=700))
+    assert parts == whole
+    om = oracle.OracleModel(fixtures.model_path("profile:HiSeq"))
+    _, o2 = oracle.generate(om, genome, "split_rec", key, 123, 4, 0, 5000)
+    assert whole == o2

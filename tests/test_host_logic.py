@@ -149,3 +149,37 @@ def test_world_size_2_sharding_over_gloo(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert "GLOO_OK" in out.stdout
+
+
+@pytest.mark.reference
+def test_draft_and_coverage_paths_match_live_reference(tmp_path):
+    """--draft / --coverage set-up (iss/abundance.py:185-317) against the reference's own functions."""
+    import patched_reference as pr
+
+    if not pr.reference_available():
+        pytest.skip("reference not mounted")
+    pr.import_reference()
+    from iss import abundance as rab
+
+    genomes = tmp_path / "g.fasta"
+    draft1 = tmp_path / "draft1.fasta"
+    with open(genomes, "w") as fh:
+        for k in range(3):
+            fh.write(">full%d\n%s\n" % (k, fixtures.synth_genome(600 + k, 2000 + 500 * k)))
+    with open(draft1, "w") as fh:
+        for k in range(4):
+            fh.write(">contig%d desc\n%s\n" % (k, fixtures.synth_genome(700 + k, 300 + 211 * k)))
+    ab = {"full0": 0.2, "full1": 0.3, "full2": 0.1, str(draft1): 0.4}
+    for mode in ("abundance", "coverage"):
+        assert abundance.expand_draft_abundance(dict(ab), [str(draft1)], mode) == rab.expand_draft_abundance(dict(ab), [str(draft1)], mode)
+    cov = {"full0": 3.0, "full1": 1.5, "full2": 0.25}
+    a = abundance.coverage_scaling(10000, dict(cov), str(genomes), 126)
+    b = rab.coverage_scaling(10000, dict(cov), str(genomes), 126)
+    assert a == b
+    ids = ["full0", "full1", "full2", "contig0", "contig1", "contig2", "contig3"]
+    np.random.seed(5)
+    x = abundance.draft(list(ids), [str(draft1)], abundance.lognormal, str(tmp_path / "o1"))
+    np.random.seed(5)
+    y = rab.draft(list(ids), [str(draft1)], rab.lognormal, str(tmp_path / "o2"))
+    assert set(x) == set(y) and all(abs(x[k] - y[k]) < 1e-15 for k in x)  # set() order inside draft() is not stable
+    assert abundance.to_coverage(1000, 0.5, 126, 5000) == rab.to_coverage(1000, 0.5, 126, 5000)
