@@ -183,6 +183,8 @@ def main():
     from insilicoseq_b200 import parallel
 
     rank, world, local = parallel.env_rank()
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # stdout carries exactly one JSON line (NCCL's version banner goes there)
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
