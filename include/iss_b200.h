@@ -145,7 +145,8 @@ typedef struct {
     uint32_t tma_gather;      /* 1: stage each read's packed genome window into shared memory with cp.async.bulk + mbarrier
                                  instead of LDG (needs L >= 96).  Measured 1-2 % slower on B200 for both an L2-resident and
                                  an HBM-random genome, hence off by default. */
-    uint32_t reserved;
+    uint32_t compress;        /* 1: r1/r2 of every batch are gzip streams (RFC 1952 members of <= 64 KB each, dynamic-Huffman
+                                 DEFLATE, compressed on the GPU) instead of plain FASTQ -- `--compress`, iss/util.py:255-268 */
 } iss_gen_opts;
 
 /* Starts asynchronous generation of all items (order preserved).  Records with len <= L are the
@@ -155,7 +156,8 @@ int iss_ctx_submit(iss_ctx *ctx, const iss_work_item *items, uint64_t n_items, c
 typedef struct {
     const uint8_t *r1;        /* pinned host memory (device memory when device_only) */
     const uint8_t *r2;
-    uint64_t nbytes;          /* bytes in r1 (== bytes in r2: the two records of a pair have equal length) */
+    uint64_t nbytes;          /* bytes in r1 (plain FASTQ: == bytes in r2, the two records of a pair have equal length) */
+    uint64_t nbytes2;         /* bytes in r2 (differs from nbytes only when opts.compress) */
     const uint8_t *vcf;       /* store_mutations: VCF lines of this batch in reference order, else NULL */
     uint64_t vcf_bytes;
     uint64_t n_pairs;
@@ -195,6 +197,10 @@ int iss_ctx_elapsed_ms(iss_ctx *ctx, int idx_from, int idx_to, float *ms);
 
 /* FASTQ bytes of pairs i0..i1-1 of one read file: sum of len("@{name}_{i}_{cpu}/1\n{seq}\n+\n{qual}\n") */
 uint64_t iss_fastq_bytes(uint32_t name_len, uint64_t cpu_number, uint32_t read_length, uint64_t i0, uint64_t i1);
+
+/* gzip `n` host bytes on the GPU (same member format as opts.compress); *out_n receives the compressed size.
+ * ISS_E_ARG when cap is too small (n + n/2048 + 64 always suffices). */
+int iss_ctx_gzip(iss_ctx *ctx, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_n);
 
 /* Philox4x32-10 on the device (one block), for known-answer tests of the device generator. */
 int iss_ctx_philox(iss_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

@@ -41,11 +41,11 @@ class IssWorkItem(ctypes.Structure):
 class IssGenOpts(ctypes.Structure):
     _fields_ = [("sequence_type", ctypes.c_uint32), ("gc_bias", ctypes.c_uint32), ("batch_pairs", ctypes.c_uint64),
                 ("n_slots", ctypes.c_uint32), ("device_only", ctypes.c_uint32), ("tma_gather", ctypes.c_uint32),
-                ("reserved", ctypes.c_uint32)]
+                ("compress", ctypes.c_uint32)]
 
 
 class IssBatch(ctypes.Structure):
-    _fields_ = [("r1", ctypes.c_void_p), ("r2", ctypes.c_void_p), ("nbytes", ctypes.c_uint64),
+    _fields_ = [("r1", ctypes.c_void_p), ("r2", ctypes.c_void_p), ("nbytes", ctypes.c_uint64), ("nbytes2", ctypes.c_uint64),
                 ("vcf", ctypes.c_void_p), ("vcf_bytes", ctypes.c_uint64), ("n_pairs", ctypes.c_uint64),
                 ("first_item", ctypes.c_uint64), ("batch_index", ctypes.c_uint64), ("slot", ctypes.c_uint32),
                 ("kernel_ms", ctypes.c_float)]
@@ -82,6 +82,8 @@ EXPORTS = {
     "iss_ctx_elapsed_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     "iss_fastq_bytes": (ctypes.c_uint64, [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint64,
                                           ctypes.c_uint64]),
+    "iss_ctx_gzip": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                    ctypes.POINTER(ctypes.c_uint64)]),
     "iss_ctx_philox": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 

@@ -21,6 +21,7 @@
 #include "../../include/iss_b200.h"
 #include "iss_device.cuh"
 #include "iss_kernels.h"
+#include "iss_deflate.h"
 
 namespace {
 
@@ -64,6 +65,15 @@ struct Slot {
     unsigned long long *h_evcount = nullptr;
     uint64_t event_cap = 0;
     uint32_t nseg = 0;
+    // opts.compress: staging slots, member sizes/offsets, packed gzip streams, totals read back
+    uint8_t *d_gz_stage[2] = {nullptr, nullptr};
+    uint8_t *d_gz_out[2] = {nullptr, nullptr};
+    uint32_t *d_gz_sizes[2] = {nullptr, nullptr};
+    uint64_t *d_gz_offsets[2] = {nullptr, nullptr};
+    uint64_t *h_gz_total = nullptr;  // pinned [2]
+    uint64_t gz_chunks_cap = 0;
+    uint32_t gz_chunks = 0;
+    uint64_t nbytes2 = 0;
     uint8_t *d_scratch = nullptr;  // slow-path scratch of the kernel running in this slot (kernels of different slots overlap)
     uint64_t scratch_bytes = 0;
     std::vector<uint4> h_events;
@@ -128,6 +138,13 @@ void free_slots(iss_ctx *c) {
         if (s.h_out[1]) cudaFreeHost(s.h_out[1]);
         if (s.d_segs) cudaFree(s.d_segs);
         if (s.h_segs) cudaFreeHost(s.h_segs);
+        for (int k = 0; k < 2; ++k) {
+            if (s.d_gz_stage[k]) cudaFree(s.d_gz_stage[k]);
+            if (s.d_gz_out[k]) cudaFree(s.d_gz_out[k]);
+            if (s.d_gz_sizes[k]) cudaFree(s.d_gz_sizes[k]);
+            if (s.d_gz_offsets[k]) cudaFree(s.d_gz_offsets[k]);
+        }
+        if (s.h_gz_total) cudaFreeHost(s.h_gz_total);
         if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.d_events) cudaFree(s.d_events);
         if (s.d_evcount) cudaFree(s.d_evcount);
@@ -288,7 +305,14 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     CU(cudaEventRecord(s.ev_k1, s.stream));
     if (c->mh.store_mutations)
         CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
-    if (!c->opts.device_only) {
+    if (c->opts.compress) {
+        s.gz_chunks = iss_gz_chunks(bytes);
+        for (int k = 0; k < 2; ++k) {
+            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_stage[k], s.d_gz_sizes[k], s.d_gz_offsets[k], s.d_gz_out[k], c->sm_count, s.stream));
+            CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_offsets[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        }
+        c->stats.kernel_launches += 6;
+    } else if (!c->opts.device_only) {
         CU(cudaMemcpyAsync(s.h_out[0], s.d_out[0], bytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
         c->stats.d2h_bytes += 2 * bytes;
@@ -383,6 +407,7 @@ int iss_ctx_create(int device, iss_ctx **out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     CU(iss_kernel_configure(kMaxSmem));
+    CU(iss_gz_init_device());
     CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
     CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
     *out = c;
@@ -705,7 +730,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     const uint32_t grid = (uint32_t)(c->sm_count * bps);
     const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
     const uint32_t max_segs = 1u << 16;
-    const bool realloc = c->slots.size() != o.n_slots || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
+    const bool realloc = c->slots.size() != o.n_slots || (o.compress && (c->slots.empty() || !c->slots[0].d_gz_stage[0])) || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
                          (bool)c->opts.device_only != (c->slots.size() && c->slots[0].h_out[0] == nullptr);
     if (realloc) {
         free_slots(c);
@@ -722,6 +747,16 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
                 CU(cudaMalloc(&s.d_events, sizeof(uint4) * s.event_cap));
                 CU(cudaMalloc(&s.d_evcount, sizeof(unsigned long long)));
                 CU(cudaMallocHost(&s.h_evcount, sizeof(unsigned long long)));
+            }
+            if (o.compress) {
+                s.gz_chunks_cap = iss_gz_chunks(slot_cap) + 1;
+                for (int k = 0; k < 2; ++k) {
+                    CU(cudaMalloc(&s.d_gz_stage[k], s.gz_chunks_cap * ISS_GZ_STRIDE));
+                    CU(cudaMalloc(&s.d_gz_out[k], s.gz_chunks_cap * ISS_GZ_STRIDE));
+                    CU(cudaMalloc(&s.d_gz_sizes[k], s.gz_chunks_cap * sizeof(uint32_t)));
+                    CU(cudaMalloc(&s.d_gz_offsets[k], (s.gz_chunks_cap + 1) * sizeof(uint64_t)));
+                }
+                CU(cudaMallocHost(&s.h_gz_total, 2 * sizeof(uint64_t)));
             }
             CU(cudaMalloc(&s.d_segs, sizeof(DevSegment) * max_segs));
             CU(cudaMallocHost(&s.h_segs, sizeof(DevSegment) * max_segs));
@@ -789,6 +824,21 @@ int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
     b->r1 = c->opts.device_only ? s.d_out[0] : s.h_out[0];
     b->r2 = c->opts.device_only ? s.d_out[1] : s.h_out[1];
     b->nbytes = s.nbytes;
+    b->nbytes2 = s.nbytes;
+    if (c->opts.compress) {  // sizes are known only now: fetch exactly the compressed bytes
+        b->nbytes = s.h_gz_total[0];
+        b->nbytes2 = s.h_gz_total[1];
+        if (c->opts.device_only) {
+            b->r1 = s.d_gz_out[0];
+            b->r2 = s.d_gz_out[1];
+        } else {
+            if (b->nbytes > c->slot_cap || b->nbytes2 > c->slot_cap) return fail(ISS_E_STATE, "internal: gzip stream larger than the slot");
+            CU(cudaMemcpyAsync(s.h_out[0], s.d_gz_out[0], b->nbytes, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaMemcpyAsync(s.h_out[1], s.d_gz_out[1], b->nbytes2, cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            c->stats.d2h_bytes += b->nbytes + b->nbytes2;
+        }
+    }
     b->vcf = nullptr;
     b->vcf_bytes = 0;
     if (c->mh.store_mutations) {
@@ -856,6 +906,30 @@ int iss_ctx_stats(iss_ctx *c, iss_stats *out) {
 uint64_t iss_fastq_bytes(uint32_t name_len, uint64_t cpu, uint32_t L, uint64_t i0, uint64_t i1) {
     const uint32_t fixed = record_fixed_len(L, name_len, (uint32_t)cpu);
     return iss_cf(i1, fixed) - iss_cf(i0, fixed);
+}
+
+int iss_ctx_gzip(iss_ctx *c, const uint8_t *in, uint64_t n, uint8_t *out, uint64_t cap, uint64_t *out_n) {
+    if (!c || (!in && n) || !out || !out_n) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    const uint32_t nc = iss_gz_chunks(n);
+    uint8_t *d_in = nullptr, *d_stage = nullptr, *d_out = nullptr;
+    uint32_t *d_sizes = nullptr;
+    uint64_t *d_off = nullptr;
+    CU(cudaMalloc(&d_in, n + 16));
+    CU(cudaMalloc(&d_stage, (uint64_t)(nc + 1) * ISS_GZ_STRIDE));
+    CU(cudaMalloc(&d_out, (uint64_t)(nc + 1) * ISS_GZ_STRIDE));
+    CU(cudaMalloc(&d_sizes, (nc + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_off, (nc + 2) * sizeof(uint64_t)));
+    if (n) CU(cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
+    CU(iss_gz_compress(d_in, n, d_stage, d_sizes, d_off, d_out, c->sm_count, 0));
+    uint64_t total = 0;
+    CU(cudaMemcpy(&total, d_off + nc, sizeof total, cudaMemcpyDeviceToHost));
+    int rc = ISS_OK;
+    if (total > cap) rc = fail(ISS_E_ARG, "output buffer too small");
+    else if (total) CU(cudaMemcpy(out, d_out, total, cudaMemcpyDeviceToHost));
+    *out_n = total;
+    cudaFree(d_in); cudaFree(d_stage); cudaFree(d_out); cudaFree(d_sizes); cudaFree(d_off);
+    return rc;
 }
 
 int iss_ctx_philox(iss_ctx *c, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

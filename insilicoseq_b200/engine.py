@@ -22,11 +22,12 @@ def philox_key(seed, cpu_number):
 
 
 class Batch(object):
-    __slots__ = ("r1", "r2", "vcf", "n_pairs", "nbytes", "first_item", "index", "kernel_ms", "_c")
+    __slots__ = ("r1", "r2", "vcf", "n_pairs", "nbytes", "nbytes2", "first_item", "index", "kernel_ms", "_c")
 
     def __init__(self, c, device_only):
         self._c = c
         self.nbytes = int(c.nbytes)
+        self.nbytes2 = int(c.nbytes2)
         self.n_pairs = int(c.n_pairs)
         self.first_item = int(c.first_item)
         self.index = int(c.batch_index)
@@ -36,7 +37,7 @@ class Batch(object):
             self.r1 = self.r2 = None
         else:
             self.r1 = np.ctypeslib.as_array(ctypes.cast(c.r1, _lib.u8p), shape=(self.nbytes,))
-            self.r2 = np.ctypeslib.as_array(ctypes.cast(c.r2, _lib.u8p), shape=(self.nbytes,))
+            self.r2 = np.ctypeslib.as_array(ctypes.cast(c.r2, _lib.u8p), shape=(self.nbytes2,))
         if c.vcf and c.vcf_bytes:
             self.vcf = np.ctypeslib.as_array(ctypes.cast(c.vcf, _lib.u8p), shape=(int(c.vcf_bytes),))
 
@@ -140,7 +141,7 @@ class Engine(object):
 
     # -- generation -------------------------------------------------------------------------------------
     def submit(self, items, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0, device_only=False,
-               tma_gather=False):
+               tma_gather=False, compress=False):
         """items: iterable of dicts/tuples (record, cpu_number, n_pairs, i0, item_base, key)."""
         items = list(items)
         arr = (_lib.IssWorkItem * max(len(items), 1))()
@@ -157,7 +158,7 @@ class Engine(object):
             # generator.py:139 raises RuntimeError for the forward read of an unknown sequence type
             raise RuntimeError("sequence type '%s' is not supported" % sequence_type)
         opts = _lib.IssGenOpts(st[sequence_type], int(bool(gc_bias)), int(batch_pairs), int(n_slots), int(bool(device_only)),
-                               int(bool(tma_gather)), 0)
+                               int(bool(tma_gather)), int(bool(compress)))
         self._device_only = bool(device_only)
         _lib.check(self._lib.iss_ctx_submit(self._h, arr, len(items), ctypes.byref(opts)))
 
@@ -192,6 +193,16 @@ class Engine(object):
         ms = ctypes.c_float(0)
         _lib.check(self._lib.iss_ctx_elapsed_ms(self._h, int(a), int(b), ctypes.byref(ms)))
         return float(ms.value)
+
+    def gzip(self, data):
+        """gzip bytes on the GPU (RFC 1952; the member format of `compress=True` batches)."""
+        data = bytes(data)
+        cap = len(data) + len(data) // 2048 + 256
+        out = np.empty(cap, dtype=np.uint8)
+        n = ctypes.c_uint64(0)
+        src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, dtype=np.uint8)
+        _lib.check(self._lib.iss_ctx_gzip(self._h, src.ctypes.data, len(data), out.ctypes.data, cap, ctypes.byref(n)))
+        return out[: n.value].tobytes()
 
     def philox(self, ctr, key):
         c = (ctypes.c_uint32 * 4)(*ctr)
