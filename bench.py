@@ -274,6 +274,23 @@ def main():
     e1 = eng.stats()
     e2e_value = pairs_step * args.steps / (ms_e * 1e-3)
 
+    # ---- the same with --compress: gzip members produced on the GPU, only compressed bytes cross PCIe ------------
+    def step_gz():
+        n = 0
+        for b in eng.generate(items, batch_pairs=1 << 18, n_slots=3, compress=True):
+            n += b.nbytes + b.nbytes2
+        return n
+
+    step_gz()
+    barrier()
+    eng.mark(0)
+    gz_bytes = 0
+    for _ in range(args.steps):
+        gz_bytes += step_gz()
+    eng.mark(1)
+    ms_z = reduce_max(eng.elapsed_ms(0, 1))
+    barrier()
+
     if rank == 0:
         traffic = None
         try:
@@ -290,6 +307,10 @@ def main():
                     "h2d_bytes_per_step": world * (e1["h2d_bytes"] - e0["h2d_bytes"]) // args.steps,
                     "d2h_bytes_per_step": world * (e1["d2h_bytes"] - e0["d2h_bytes"]) // args.steps,
                     "d2h_GBps_per_gpu": (e1["d2h_bytes"] - e0["d2h_bytes"]) / (ms_e * 1e-3) / 1e9},
+            "e2e_gzip": {"value": pairs_step * args.steps / (ms_z * 1e-3), "unit": "pairs/s", "ms_per_step": ms_z / args.steps,
+                         "d2h_bytes_per_step": world * gz_bytes // args.steps,
+                         "compression_ratio": (e1["d2h_bytes"] - e0["d2h_bytes"]) / max(gz_bytes, 1),
+                         "note": "iss generate --compress: gzip (RFC 1952) members built on the GPU, decompresses to the same FASTQ"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "iss_generate_kernel",

@@ -71,7 +71,7 @@ def generate_reads(args):
                 for cpu_number, (work, prefix) in jobs:
                     if parallel.chunk_owner(cpu_number, n_gpus) == d:
                         worker_iterator(work, error_model, cpu_number, prefix, seed, args.sequence_type, args.gc_bias,
-                                        engine=engines[d])
+                                        engine=engines[d], compress=args.compress)
             except BaseException as e:  # noqa: BLE001 - re-raised in the parent thread
                 errors.append(e)
 
@@ -82,30 +82,29 @@ def generate_reads(args):
             t.join()
         if errors:
             raise errors[0]
+        fq = ".fastq.gz" if args.compress else ".fastq"  # --compress: gzip members come off the GPU, they concatenate
         for cpu_number in range(len(jobs), args.cpus):  # workers that got no chunk still leave (empty) files
-            for suffix in ("_R1.fastq", "_R2.fastq", ".vcf"):
+            for suffix in ("_R1" + fq, "_R2" + fq, ".vcf"):
                 open(temp_file_list[cpu_number] + suffix, "wb").close()
     except KeyboardInterrupt as e:
         logger.error("iss generate interrupted: %s" % e)
-        tmp = [t + s for t in temp_file_list for s in ("_R1.fastq", "_R2.fastq", ".vcf")]
+        tmp = [t + s for t in temp_file_list for s in ("_R1.fastq", "_R2.fastq", "_R1.fastq.gz", "_R2.fastq.gz", ".vcf")]
         tmp.append(genome_file)
         util.cleanup([t for t in tmp if os.path.exists(t)])
         sys.exit(1)
     else:
-        temp_R1 = [t + "_R1.fastq" for t in temp_file_list]
-        temp_R2 = [t + "_R2.fastq" for t in temp_file_list]
+        fq = ".fastq.gz" if args.compress else ".fastq"
+        temp_R1 = [t + "_R1" + fq for t in temp_file_list]
+        temp_R2 = [t + "_R2" + fq for t in temp_file_list]
         temp_mut = [t + ".vcf" for t in temp_file_list]
-        util.concatenate(temp_R1, args.output + "_R1.fastq")
-        util.concatenate(temp_R2, args.output + "_R2.fastq")
+        util.concatenate(temp_R1, args.output + "_R1" + fq)
+        util.concatenate(temp_R2, args.output + "_R2" + fq)
         if args.store_mutations:
             util.concatenate(temp_mut, args.output + ".vcf",
                              "##fileformat=VCFv4.1\n" + "\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO"]))
         util.cleanup(temp_R1 + temp_R2 + temp_mut + [genome_file])
-        if args.compress:
-            util.compress(args.output + "_R1.fastq")
-            util.compress(args.output + "_R2.fastq")
-            if args.store_mutations:
-                util.compress(args.output + ".vcf")
+        if args.compress and args.store_mutations:  # the FASTQ files were compressed on the GPU (util.py:255-268 for the small VCF)
+            util.compress(args.output + ".vcf")
         logger.info("Read generation complete")
     finally:
         for e in engines:

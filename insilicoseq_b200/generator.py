@@ -209,15 +209,17 @@ def register_records(engine, records):
     return records
 
 
-def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence_type, gc_bias, engine=None):
+def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence_type, gc_bias, engine=None, compress=False):
     """Drop-in for iss/generator.py:223-251: writes {worker_prefix}_R1.fastq, _R2.fastq and .vcf for one work chunk.
 
     work: list of (record, n_pairs, mode).  `engine` is an Engine that already holds the genome (records carry
-    .gpu_index) and the model; when omitted a private engine on GPU 0 is created for the call."""
+    .gpu_index) and the model; when omitted a private engine on GPU 0 is created for the call.  `compress=True` writes
+    {worker_prefix}_R1.fastq.gz / _R2.fastq.gz instead: gzip members produced on the GPU (`--compress`)."""
     logger = logging.getLogger(__name__)
     try:
-        forward_handle = open(f"{worker_prefix}_R1.fastq", "wb")
-        reverse_handle = open(f"{worker_prefix}_R2.fastq", "wb")
+        ext = ".fastq.gz" if compress else ".fastq"
+        forward_handle = open(f"{worker_prefix}_R1{ext}", "wb")
+        reverse_handle = open(f"{worker_prefix}_R2{ext}", "wb")
         mutation_handle = open(f"{worker_prefix}.vcf", "wb")
     except PermissionError as e:
         logger.error("Failed to write temporary output file(s): %s" % e)
@@ -243,7 +245,7 @@ def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence
                 logger.debug("Cpu #%s: Generating %s read pairs" % (cpu_number, n_pairs))
             items = worker_items([(rec.gpu_index, n) for rec, n, _ in work], cpu_number, seed, engine.record_lengths,
                                  engine.read_length, logger=logger, record_names=engine.record_names)
-            for batch in engine.generate(items, sequence_type=sequence_type, gc_bias=gc_bias):
+            for batch in engine.generate(items, sequence_type=sequence_type, gc_bias=gc_bias, compress=compress):
                 forward_handle.write(memoryview(batch.r1))
                 reverse_handle.write(memoryview(batch.r2))
                 if batch.vcf is not None:

@@ -136,3 +136,16 @@ def test_cli_store_mutations_vcf(tmp_path):
     body = b"".join(oracle.run_worker(om, [(r.id, r.seq, n) for r, n, _ in work], cpu, 21, vcf=True)[2]
                     for cpu, work in enumerate(chunks))
     assert vcf.split(b"\n", 2)[2] == body and len(body) > 500
+
+
+def test_cli_compress_with_vcf(tmp_path):
+    fa, abf, recs, ab = _write_inputs(tmp_path)
+    out = str(tmp_path / "gz")
+    app.main(["generate", "-g", fa, "-b", abf, "--model", "novaseq", "-n", "20000", "--seed", "3", "--cpus", "3", "--gpus", "1",
+              "-o", out, "-q", "--compress", "--store_mutations"])
+    e1, e2 = _expected(recs, ab, "profile:NovaSeq", 20000, 3, 3)
+    raw1 = open(out + "_R1.fastq.gz", "rb").read()
+    assert gzip.decompress(raw1) == e1 and gzip.open(out + "_R2.fastq.gz", "rb").read() == e2
+    assert len(raw1) * 2.5 < len(e1)
+    assert gzip.open(out + ".vcf.gz", "rb").read().startswith(b"##fileformat=VCFv4.1")
+    assert not os.path.exists(out + "_R1.fastq") and not os.path.exists(out + ".iss.tmp.0_R1.fastq.gz")
