@@ -65,6 +65,7 @@ struct Smem {
     uint32_t misc[32];  // 0 n_sym, 1 total payload bits, 2 overflow flag, 3 crc accumulator, 4 uniform x^(8*(n%256)), 8.. warp sums
     uint16_t parent[516];
     uint16_t codes[260];  // bit-reversed canonical codes
+    uint32_t cl[260];     // code | length << 16: one lookup per literal in the packing loop
     uint8_t lens[260];
 };
 
@@ -134,6 +135,7 @@ __device__ void assign_codes(Smem &s) {  // thread 0: canonical codes, stored bi
     for (uint32_t sym = 0; sym < 257; ++sym) {
         const uint32_t l = s.lens[sym];
         s.codes[sym] = l ? (uint16_t)(__brev(nxt[l]++) >> (32u - l)) : 0;
+        s.cl[sym] = (uint32_t)s.codes[sym] | (l << 16);
     }
 }
 
@@ -198,13 +200,23 @@ __global__ void __launch_bounds__(256) iss_deflate_kernel(const uint8_t *__restr
         __syncthreads();
         // 4. the 258 code lengths, each as the 4-bit code of its value (a flat 4-bit code: code == value, MSB first)
         for (uint32_t sym = tid; sym < 257; sym += 256) put_bits(s.out, 74u + 4u * sym, __brev((uint32_t)s.lens[sym]) >> 28, 4);
-        // 5. my slice: bit count + raw CRC
+        // 5. my slice (256 contiguous bytes, read 16 at a time): bit count + raw CRC
         const uint32_t lo = tid * 256u, hi = (lo + 256u < n) ? lo + 256u : n;
         uint32_t bits = 0, crc = 0;
-        for (uint32_t i = lo; i < hi; ++i) {
-            const uint32_t b = src[i];
-            bits += s.lens[b];
-            crc = s.crcT[(crc ^ b) & 0xFFu] ^ (crc >> 8);
+        {
+            const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);  // chunk base and slices are 16-byte aligned
+            for (uint32_t i = lo; i < hi; i += 16u) {
+                const uint4 v = __ldg(src4 + ((i - lo) >> 4));
+                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) {
+                    if (i + k < hi) {
+                        const uint32_t b = (wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu;
+                        bits += s.cl[b] >> 16;
+                        crc = s.crcT[(crc ^ b) & 0xFFu] ^ (crc >> 8);
+                    }
+                }
+            }
         }
         // block-wide exclusive scan of `bits`
         uint32_t incl = bits;
@@ -228,14 +240,22 @@ __global__ void __launch_bounds__(256) iss_deflate_kernel(const uint8_t *__restr
         if (!too_big) {
             uint64_t acc = 0;
             uint32_t accbits = pos & 31u, wi = pos >> 5;
-            for (uint32_t i = lo; i < hi; ++i) {
-                const uint32_t b = src[i];
-                acc |= (uint64_t)s.codes[b] << accbits;
-                accbits += s.lens[b];
-                if (accbits >= 32u) {
-                    atomicOr(&s.out[wi++], (uint32_t)acc);
-                    acc >>= 32;
-                    accbits -= 32u;
+            const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);
+            for (uint32_t i = lo; i < hi; i += 16u) {
+                const uint4 v = __ldg(src4 + ((i - lo) >> 4));
+                const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) {
+                    if (i + k < hi) {
+                        const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
+                        acc |= (uint64_t)(e & 0xFFFFu) << accbits;
+                        accbits += e >> 16;
+                        if (accbits >= 32u) {
+                            atomicOr(&s.out[wi++], (uint32_t)acc);
+                            acc >>= 32;
+                            accbits -= 32u;
+                        }
+                    }
                 }
             }
             if (accbits) atomicOr(&s.out[wi], (uint32_t)acc);
