@@ -68,7 +68,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -105,6 +105,27 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cores():
+    """CPUs this process may actually use: the affinity mask capped by the cgroup CPU quota (a GPU box can show 128
+    logical CPUs while the container is limited to 16: oversubscribing it makes the CPU arm slower, not faster)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, quota // period))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 # ---- CPU arm: the C oracle port of the reference path (test infrastructure, used here only as the baseline) ------
 def _oracle_chunk(args):
     npz, i0, i1 = args
@@ -126,7 +147,7 @@ def cpu_port_throughput(pairs_per_core, cores=None, repeats=1):
     import oracle
 
     oracle.build()
-    cores = cores or os.cpu_count() or 1
+    cores = cores or usable_cores()
     tmp = tempfile.mkdtemp(prefix="iss_bench_")
     npz = os.path.join(tmp, "miseq_150.npz")
     oracle.truncate_profile(os.path.join(ROOT, "insilicoseq_b200", "profiles", MODEL_FILE), npz, READ_LEN)
@@ -145,8 +166,8 @@ def cpu_port_throughput(pairs_per_core, cores=None, repeats=1):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    per_core = 25_000
-    cores = os.cpu_count() or 1
+    per_core = 100_000
+    cores = usable_cores()
     vals, cores = cpu_port_throughput(per_core, cores, repeats=max(args.warmup, 0) + args.steps)
     vals = vals[-args.steps:]
     v = statistics.mean(vals)
@@ -174,7 +195,7 @@ def workload_config(n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step (default: the BASELINE workload)")
@@ -318,10 +339,10 @@ def main():
                          "avg_launch_ms": k_ms / max(launches, 1),
                          "note": "the kernel is integer-issue bound, not HBM bound (SURVEY.md 8d); see DESIGN.md section 6"},
             "clocks": clk,
-            "host": {"numa_node_rank0": numa_node, "cpus": os.cpu_count()},
+            "host": {"numa_node_rank0": numa_node, "logical_cpus": os.cpu_count(), "usable_cpus": usable_cores()},
         }
         if world == 1 and not args.no_cpu_baseline:
-            per_core = 60_000
+            per_core = 200_000
             vals, cores = cpu_port_throughput(per_core, repeats=1)
             line["cpu_baseline"] = {"value": vals[0], "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": "%d pairs (%d per core) of the same workload, oracle/iss_oracle.c in %d processes"
