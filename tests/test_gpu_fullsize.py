@@ -94,3 +94,26 @@ def test_metagenome_many_records_matches_oracle():
             exp1, _ = oracle.run_worker(om, [(r.id, r.seq, n) for r, n, _ in work], cpu, 7)
             assert hashlib.sha256(got1).digest() == hashlib.sha256(exp1).digest()
             assert len(work) > 50  # many segments per batch
+
+
+def test_thousands_of_tiny_items_with_long_names():
+    """Segment planner stress: 3000 contigs, 1-3 pairs each, record ids of 40-180 characters."""
+    rng = np.random.RandomState(17)
+    recs = []
+    for k in range(3000):
+        name = "NZ_CONTIG%05d.%s" % (k, "x" * int(rng.randint(25, 165)))
+        recs.append(fasta.Record(fixtures.synth_genome(5000 + k, int(rng.randint(200, 700))).encode(), id=name))
+    work = [(k, int(rng.randint(1, 4))) for k in range(3000)]
+    model = error_models.KDErrorModel(os.path.join(error_models.PROFILE_DIR, "HiSeq"))
+    om = oracle.OracleModel(os.path.join(error_models.PROFILE_DIR, "HiSeq"))
+    with eng_mod.Engine(0) as e:
+        generator.register_records(e, recs)
+        e.set_model(model)
+        items = eng_mod.worker_items(work, 12, 99, e.record_lengths, e.read_length)
+        for bp in (0, 500):
+            got1, got2 = b"", b""
+            for b in e.generate(items, batch_pairs=bp):
+                got1 += b.r1.tobytes()
+                got2 += b.r2.tobytes()
+            exp1, exp2 = oracle.run_worker(om, [(recs[k].id, recs[k].seq, n) for k, n in work], 12, 99)
+            assert got1 == exp1 and got2 == exp2
