@@ -253,3 +253,94 @@ def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence
     finally:
         if own:
             engine.close()
+
+
+class Read(object):
+    """What simulate_read hands back per read: the slice of Bio.SeqRecord the reference's callers use."""
+
+    __slots__ = ("id", "seq", "description", "letter_annotations", "annotations")
+
+    def __init__(self, rid, seq, quals):
+        self.id = rid
+        self.seq = seq
+        self.description = ""
+        self.letter_annotations = {"phred_quality": quals}
+        self.annotations = {"mutations": []}
+
+    def format(self, fmt="fastq-sanger"):
+        return "@%s\n%s\n+\n%s\n" % (self.id, self.seq, "".join(chr(q + 33) for q in self.letter_annotations["phred_quality"]))
+
+
+_private_engines = {}
+
+
+def _engine_for(record, error_model, device=0):
+    """One cached engine per (record, model) pair for the single-pair API below."""
+    key = (id(record), id(error_model), device)
+    eng = _private_engines.get(key)
+    if eng is None:
+        if len(_private_engines) >= 4:
+            _private_engines.pop(next(iter(_private_engines))).close()
+        eng = Engine(device)
+        register_records(eng, [record])
+        eng.set_model(error_model)
+        _private_engines[key] = eng
+    return eng
+
+
+def _parse_pair(r1, r2):
+    a = bytes(r1).split(b"\n")
+    b = bytes(r2).split(b"\n")
+    mk = lambda x: Read(x[0][1:].decode(), x[1].decode(), [c - 33 for c in x[3]])  # noqa: E731
+    return mk(a), mk(b)
+
+
+def simulate_read(record, error_model, i, cpu_number, sequence_type, seed=0, item_base=0, engine=None):
+    """iss/generator.py:98-192 for ONE pair, on the GPU: returns (forward, reverse, mutations).
+
+    Same positional arguments as the reference.  The reference draws from the process-global MT19937 state; here the
+    draws are the Philox slots of pair `item_base + i` under key `seed + cpu_number` (RNG contract v1), so the call
+    is a pure function of its arguments.  A record that is not longer than the read length raises AssertionError
+    (generator.py:130), an unknown sequence type RuntimeError (:139)."""
+    from .engine import philox_key
+
+    assert int(error_model.read_length) < len(record.seq)
+    eng = engine or _engine_for(record, error_model)
+    item = (record.gpu_index, int(cpu_number), 1, int(i), int(item_base), philox_key(seed, cpu_number))
+    out = None
+    for batch in eng.generate([item], sequence_type=sequence_type):
+        out = _parse_pair(batch.r1, batch.r2)
+        vcf = bytes(batch.vcf) if batch.vcf is not None else b""
+    mutations = []
+    for line in vcf.decode().splitlines():
+        f = line.split("\t")
+        mutations.append({"id": f[0], "position": int(f[1]) - 1, "ref": f[3], "alt": f[4], "quality": f[5]})
+    return out[0], out[1], mutations
+
+
+def simulate_reads(record, error_model, n_pairs, cpu_number, forward_handle, reverse_handle, mutations_handle,
+                   sequence_type, gc_bias=False, mode="default", seed=0, item_base=0, engine=None):
+    """iss/generator.py:21-66: n_pairs pairs of one record written to the three handles (binary or text)."""
+    from .engine import philox_key
+
+    logger = logging.getLogger(__name__)
+    logger.debug("Cpu #%s: Generating %s read pairs" % (cpu_number, n_pairs))
+    if not int(error_model.read_length) < len(record.seq):
+        logger.warning("%s shorter than read length for this ErrorModel" % record.id)
+        logger.warning("Skipping %s. You will have less reads than specified" % record.id)
+        return
+    eng = engine or _engine_for(record, error_model)
+    item = (record.gpu_index, int(cpu_number), int(n_pairs), 0, int(item_base), philox_key(seed, cpu_number))
+
+    def put(handle, view):
+        data = bytes(view)
+        try:
+            handle.write(data)
+        except TypeError:
+            handle.write(data.decode())
+
+    for batch in eng.generate([item], sequence_type=sequence_type, gc_bias=gc_bias):
+        put(forward_handle, batch.r1)
+        put(reverse_handle, batch.r2)
+        if batch.vcf is not None:
+            put(mutations_handle, batch.vcf)
