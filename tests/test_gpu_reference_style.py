@@ -49,9 +49,13 @@ def test_amp():  # iss/test/test_generator.py:94-116
     seq = "TTT" + "A" * 194 + "GGCC" + "A" * 196 + "TTT"
     ref_genome = Record(seq, id="my_amplicon", description="test amplicon")
     fwd, rev, _ = generator.simulate_read(ref_genome, err_mod, 1, 0, "amplicon", seed=42)
+    from insilicoseq_b200.error_models import fragment_table
+
     assert len(fwd.seq) == 301 and len(rev.seq) == 301
-    assert fwd.seq.startswith("TTTAAAAAAAAAAAAAAAAAAAAAAAA")  # amplicon reads start at both ends of the template
-    assert rev.seq.startswith("AAATTTTTTTTTTTTTTTTTTTTTTTT")
+    assert fwd.seq.startswith("TTTAAAAAAA") and rev.seq.startswith("AAATTTTTTT")  # reads start at both ends of the template
+    om = oracle.OracleModel(fixtures.model_path("profile:MiSeq"), 1000, 10, frag_table=fragment_table(1000, 10))
+    o1, o2 = oracle.generate(om, ref_genome.seq, "my_amplicon", oracle.make_key(42, 0), 0, 0, 1, 2, amplicon=True)
+    assert fwd.format() == o1.decode() and rev.format() == o2.decode()
 
 
 def test_unknown_sequence_type():
