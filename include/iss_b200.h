@@ -18,7 +18,7 @@
  * Host arrays passed in are copied before the call returns.  Device memory, streams, pinned ring
  * buffers and the NCCL communicator are owned by the context.  One host thread per context.
  *
- * Random numbers: Philox4x32-10, slot schedule "RNG contract v1" (DESIGN.md section 3).  All model
+ * Random numbers: Philox4x32-10, slot schedule "RNG contract v2" (DESIGN.md section 3).  All model
  * tables are integer thresholds on 32/64-bit Philox words, so the device path has no floating point.
  */
 #ifndef ISS_B200_H

@@ -68,7 +68,7 @@ __host__ __device__ inline void philox_round_keys(uint64_t key, uint32_t rk[20])
     for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
 }
 
-// stream ids of RNG contract v1
+// stream ids of RNG contract v2
 #define ISS_S_PAIR 0u
 #define ISS_K_QUAL 0u
 #define ISS_K_SUBC 1u
@@ -109,6 +109,8 @@ struct ModelHeader {
     uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic, store_mutations;
     int32_t fixed_insert;
     uint32_t n_nz[2];      // positions (< L-1) with a non-zero insertion or deletion threshold
+    uint32_t n_ent;        // indel draw sites with a non-zero threshold (RNG contract v2), all lists together
+    uint32_t ent_begin[5]; // start of: insertion sites fwd, deletion sites fwd, insertion sites rev, deletion sites rev, end
     uint32_t pad;
     int64_t frag_lo;
     uint64_t bin_thr[2][4];
@@ -116,7 +118,7 @@ struct ModelHeader {
     uint32_t err_thr[ISS_QROW];
     // offsets (bytes from blob start)
     uint64_t frag_thr_off, insert_thr_off, qual_thr_off, subst_n_off, subst_thr_off, subst_alt_off, ins_thr_off,
-        ins_nz_off, ins_base_off, del_thr_off, del_nz_off, nzpos_off, basic_thr_off, basic_val_off;
+        ins_nz_off, ins_base_off, del_thr_off, del_nz_off, nzpos_off, basic_thr_off, basic_val_off, ent_off;
 };
 
 // pointer view built on each device from the blob base
@@ -134,6 +136,8 @@ struct DevModel {
     const uint32_t *del_thr;    // [2][L][4]
     const uint8_t *del_nz;      // [2][L]
     const uint16_t *nzpos;      // [2][L]
+    const uint4 *ent;           // [n_ent][2]: {thresholds D (x: insertion lane, or x..w by base for a deletion site)},
+                                //             {x: pos | kind << 16 | o << 17 | per-base non-zero mask << 18 | lane << 22, y: slot rank}
     const uint32_t *basic_thr;
     const uint8_t *basic_val;
 };
@@ -240,6 +244,8 @@ struct GenParams {
     int32_t fixed_insert;
     int64_t frag_lo;
     uint32_t n_nz[2];
+    uint32_t n_ent;
+    uint32_t ent_begin[5];
     uint64_t bin_thr[2][4];
     uint8_t bin_valid[2][4];
     uint32_t err_thr[ISS_QROW];

@@ -17,7 +17,7 @@
 // the output stream, so the aligned middle leaves through the TMA bulk-copy engine
 // (cp.async.bulk.global.shared::cta) while the CTA starts the next tile.
 //
-// All randomness is Philox4x32-10 addressed by (key, pair ordinal, stream, block) -- "RNG contract v1".
+// All randomness is Philox4x32-10 addressed by (key, pair ordinal, stream, block) -- "RNG contract v2".
 // No floating point anywhere: model tables are integer thresholds (include/iss_b200.h).
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -87,6 +87,28 @@ __device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cas
 __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
 
 // bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
+
+// ---- one indel draw site (RNG contract v2): does it fire for current base c?  The site's slot is word rank & 3 of
+//      Philox block rank >> 2 of the INS / DEL stream of its orientation; blocks are cached across consecutive ranks.
+struct EntCache { uint32_t key; Philox4 w; };
+__device__ __forceinline__ uint32_t entry_bits(const GenParams &p, uint32_t n, uint32_t att8, uint32_t Plo, uint32_t Phi, EntCache &cache,
+                                               uint32_t &pos_out, uint32_t &so_out) {
+    // returns the site's mask bits: bit lane (insertion fires) or bits 4+b for every base b whose deletion fires
+    const uint4 thr = __ldg(p.m.ent + 2u * n), mt = __ldg(p.m.ent + 2u * n + 1u);
+    const uint32_t so = (mt.x >> 17) & 1u, kind = (mt.x >> 16) & 1u, blk = mt.y >> 2;
+    pos_out = mt.x & 0xFFFFu;
+    so_out = so;
+    const uint32_t ck = (so << 31) | (kind << 30) | blk;
+    if (ck != cache.key) {
+        cache.key = ck;
+        cache.w = philox4x32_10_rk(blk, iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
+    }
+    const uint32_t word = pick(cache.w, mt.y & 3u);
+    if (kind == 0u) return (word <= thr.x) ? (1u << ((mt.x >> 22) & 3u)) : 0u;
+    const uint32_t nz = (mt.x >> 18) & 15u;
+    return ((((nz & 1u) && word <= thr.x) ? 1u : 0u) | (((nz & 2u) && word <= thr.y) ? 2u : 0u) |
+            (((nz & 4u) && word <= thr.z) ? 4u : 0u) | (((nz & 8u) && word <= thr.w) ? 8u : 0u)) << 4;
+}
 
 // ---- mbarrier / TMA bulk-copy helpers (genome windows: global -> shared, completion counted on an mbarrier) -------
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
@@ -454,33 +476,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         const uint32_t Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
         const uint32_t att8 = valid ? (u32p(l.sAtt)[pair] << 8) : 0;
         uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
-        const uint32_t nnz_all = p.n_nz[0] + p.n_nz[1];
-        if (valid && nnz_all) {
-            const uint32_t n_begin = (q4 * nnz_all) >> (p.split_shift + 1u), n_end = ((q4 + 1u) * nnz_all) >> (p.split_shift + 1u);
+        if (valid && p.n_ent) {
+            const uint32_t n_begin = (q4 * p.n_ent) >> (p.split_shift + 1u), n_end = ((q4 + 1u) * p.n_ent) >> (p.split_shift + 1u);
             uint32_t fired = 0;  // bit so set when read orientation so has an event
-            uint32_t cached = 0xFFFFFFFFu;
-            Philox4 dblk = {0, 0, 0, 0};
+            EntCache cache;
+            cache.key = 0xFFFFFFFFu;
             for (uint32_t n = n_begin; n < n_end; ++n) {
-                const uint32_t so = n >= p.n_nz[0] ? 1u : 0u;
-                if ((fired >> so) & 1u) continue;
-                const uint32_t pos = p.m.nzpos[so * L + (n - so * p.n_nz[0])];
+                uint32_t pos, so;
+                const uint32_t bits = entry_bits(p, n, att8, Plo, Phi, cache, pos, so);
+                if (!bits || ((fired >> so) & 1u)) continue;
                 const uint32_t c = (imgp(l, so) + u32p(l.sSeqOff)[so * T + pair])[pos];
                 if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
-                const uint32_t tb = so * L + pos;
-                const uint32_t m = p.m.ins_nz[tb];
-                bool hit = false;
-                if (m) {
-                    const Philox4 w = philox4x32_10_rk(pos, iss_read_stream(so, ISS_K_INS) | att8, Plo, Phi, p.rk);
-                    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.ins_thr) + tb);
-                    hit = ((m & 1u) && w.x <= t.x) | ((m & 2u) && w.y <= t.y) | ((m & 4u) && w.z <= t.z) | ((m & 8u) && w.w <= t.w);
-                }
-                const uint32_t code = base_code(c);
-                if ((p.m.del_nz[tb] >> code) & 1u) {
-                    const uint32_t ck = (so << 30) | (pos >> 2);
-                    if (ck != cached) { cached = ck; dblk = philox4x32_10_rk(pos >> 2, iss_read_stream(so, ISS_K_DEL) | att8, Plo, Phi, p.rk); }
-                    hit |= pick(dblk, pos & 3u) <= __ldg(p.m.del_thr + tb * 4 + code);
-                }
-                if (hit) fired |= 1u << so;
+                if ((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) fired |= 1u << so;
             }
             for (uint32_t so = 0; so < 2; ++so)
                 if (((fired >> so) & 1u) && atomicExch(&u32p(l.sFlag)[so * T + pair], 1u) == 0u)
@@ -494,39 +501,30 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 // and does not depend on the evolving sequence -- only WHICH deletion threshold applies depends on the
                 // current base -- so the mask holds the insertion lanes that fire and, per base, whether a deletion
                 // fires.  The masks live in the (still unused) substitution list.
-                uint8_t *masks = reinterpret_cast<uint8_t *>(u32p(l.sErr));
-                const uint32_t ngrp = (L + 2u) >> 2;  // groups of 4 loop positions 0..L-2
+                uint32_t *masks32 = u32p(l.sErr);
+                uint8_t *masks = reinterpret_cast<uint8_t *>(masks32);
+                const uint32_t n_o0 = p.ent_begin[2] - p.ent_begin[0], n_o1 = p.ent_begin[4] - p.ent_begin[2];
+                const uint32_t ngrp = (((n_o0 > n_o1) ? n_o0 : n_o1) + 3u) >> 2;  // groups of 4 consecutive sites (one Philox block each)
                 for (uint32_t base = 0; base < nslow; base += p.slow_slots) {
                     const uint32_t nround = (nslow - base < p.slow_slots) ? (nslow - base) : p.slow_slots;
+                    for (uint32_t i = tid; i < ((nround * L + 3u) >> 2); i += blockDim.x) masks32[i] = 0;
+                    __syncthreads();
                     for (uint32_t idx = tid; idx < nround * ngrp; idx += blockDim.x) {
                         const uint32_t sidx = idx / ngrp, g = idx - sidx * ngrp;
                         const uint32_t srd = u32p(l.sSlow)[base + sidx];
                         const uint32_t so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
                         const uint64_t sP = u64p(l.sP)[sp_];
                         const uint32_t sa8 = u32p(l.sAtt)[sp_] << 8;
-                        Philox4 dblk = {0, 0, 0, 0};
-                        bool have_d = false;
-                        for (uint32_t j = 0; j < 4; ++j) {
-                            const uint32_t nucl = 4u * g + j;
-                            if (nucl + 1u >= L) break;
-                            const uint32_t tb = so * L + nucl;
-                            uint32_t mk = 0;
-                            const uint32_t m = p.m.ins_nz[tb];
-                            if (m) {
-                                const Philox4 w = philox4x32_10_rk(nucl, iss_read_stream(so, ISS_K_INS) | sa8, (uint32_t)sP, (uint32_t)(sP >> 32), p.rk);
-                                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.ins_thr) + tb);
-                                mk = (((m & 1u) && w.x <= t.x) ? 1u : 0u) | (((m & 2u) && w.y <= t.y) ? 2u : 0u) |
-                                     (((m & 4u) && w.z <= t.z) ? 4u : 0u) | (((m & 8u) && w.w <= t.w) ? 8u : 0u);
+                        const uint32_t e0 = p.ent_begin[2u * so], e1 = p.ent_begin[2u * so + 2u];
+                        EntCache cache;
+                        cache.key = 0xFFFFFFFFu;
+                        for (uint32_t n = e0 + 4u * g; n < e1 && n < e0 + 4u * g + 4u; ++n) {
+                            uint32_t pos, eo;
+                            const uint32_t bits = entry_bits(p, n, sa8, (uint32_t)sP, (uint32_t)(sP >> 32), cache, pos, eo);
+                            if (bits) {
+                                const uint32_t bi = sidx * L + pos;
+                                atomicOr(&masks32[bi >> 2], bits << (8u * (bi & 3u)));
                             }
-                            const uint32_t dz = p.m.del_nz[tb];
-                            if (dz) {
-                                if (!have_d) { dblk = philox4x32_10_rk(g, iss_read_stream(so, ISS_K_DEL) | sa8, (uint32_t)sP, (uint32_t)(sP >> 32), p.rk); have_d = true; }
-                                const uint32_t word = pick(dblk, j);
-                                const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.del_thr) + tb);
-                                mk |= (((dz & 1u) && word <= t.x) ? 16u : 0u) | (((dz & 2u) && word <= t.y) ? 32u : 0u) |
-                                      (((dz & 4u) && word <= t.z) ? 64u : 0u) | (((dz & 8u) && word <= t.w) ? 128u : 0u);
-                            }
-                            masks[sidx * L + nucl] = (uint8_t)mk;
                         }
                     }
                     __syncthreads();

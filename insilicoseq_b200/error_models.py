@@ -89,7 +89,7 @@ def phred_to_prob_table(n=QROW):
 def fragment_table(mu, sd):
     """`int(np.random.normal(mu, sd))` (iss/generator.py:122) as an integer inversion table.
 
-    RNG contract v1 defines the draw on the 64-bit word r of PAIR block 2 (w2, w3):
+    RNG contract v2 defines the draw on the 64-bit word r of PAIR block 2 (w2, w3):
         fragment_length = lo + #{k : r >= T[k]},   T[k] = floor(P(int(X) <= lo + k) * 2**64),  X ~ N(mu, sd)
     tabulated on mu +- 8 sd.  sd == 0 degenerates to the constant int(mu)."""
     from scipy.stats import norm
@@ -295,7 +295,7 @@ def basic_phred_table(mean_quality, sd=0.01, cap=0.9999):
 
     The reference draws x ~ N(phred_to_prob(mean_quality), sd) per position and maps it through
     phred(x) = prob_to_phred(min(x, cap)) = int(round(-10 log10(1 - min(x, cap)))) (util.py:32-45), which is
-    non-decreasing in x.  RNG contract v1 defines the normal draw by inversion on the phred integer:
+    non-decreasing in x.  RNG contract v2 defines the normal draw by inversion on the phred integer:
         phred = val[#{k : w >= thr[k]}],   thr[k] = ceil(P(phred < val[k+1]) * 2**32)
     with P(phred >= v) = P(x >= 1 - 10**(-(v - 0.5)/10)).  Returns (thr uint32[n] ascending, val int64[n+1])."""
     from scipy.stats import norm

@@ -299,7 +299,7 @@ def simulate_read(record, error_model, i, cpu_number, sequence_type, seed=0, ite
     """iss/generator.py:98-192 for ONE pair, on the GPU: returns (forward, reverse, mutations).
 
     Same positional arguments as the reference.  The reference draws from the process-global MT19937 state; here the
-    draws are the Philox slots of pair `item_base + i` under key `seed + cpu_number` (RNG contract v1), so the call
+    draws are the Philox slots of pair `item_base + i` under key `seed + cpu_number` (RNG contract v2), so the call
     is a pure function of its arguments.  A record that is not longer than the read length raises AssertionError
     (generator.py:130), an unknown sequence type RuntimeError (:139)."""
     from .engine import philox_key

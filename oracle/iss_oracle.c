@@ -26,7 +26,7 @@
  *   rev_comp                 iss/util.py:48-92
  *   FASTQ text               iss/generator.py:64-65 (Bio.SeqIO "fastq-sanger")
  *   write_mutations          iss/generator.py:598-620
- * RNG: Philox4x32-10, slot schedule "RNG contract v1" (oracle/philox.py).
+ * RNG: Philox4x32-10, slot schedule "RNG contract v2" (oracle/philox.py).
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -55,6 +55,8 @@ typedef struct {
     const double *ins_p;      /* [2][L][4] lanes in the model dict's key order */
     const uint8_t *ins_base;  /* [2][L][4] ASCII base of each lane */
     const double *del_p;      /* [2][L][4] indexed by base code A,C,G,T = 0..3 */
+    const int32_t *ins_rank;  /* [2][L][4] RNG contract v2: slot rank of the site among the entries with p > 0, or -1 */
+    const int32_t *del_rank;  /* [2][L]    slot rank of the position among the positions with any p > 0, or -1 */
     /* basic/perfect models: fixed insert size and host-tabulated phred draws */
     int32_t fixed_insert;     /* >=0: random_insert_size() returns this constant (basic.py:55, perfect.py:44) */
     int32_t qual_mode;        /* 0 kde CDF rows; 1 constant phred (perfect.py:35); 2 table by 32-bit draw (basic) */
@@ -219,8 +221,9 @@ static int introduce_indels(const iss_oracle_model *M, draw_ctx *d, int o, uint8
         if (is_ambiguous_upper(cu)) { position++; continue; }
         for (int lane = 0; lane < 4; ++lane) {
             double p = ins_p[position * 4 + lane];
-            if (!(p > 0.0)) continue; /* u < p is false for p <= 0 or NaN: skipping the slot is exact */
-            double u = draw_u(d, rstream(o, K_INS), (uint32_t)position, (uint32_t)lane);
+            if (!(p > 0.0)) continue; /* u < p is false for p <= 0 or NaN: the site has no slot */
+            const uint32_t r = (uint32_t)M->ins_rank[((size_t)o * L + position) * 4 + lane];
+            double u = draw_u(d, rstream(o, K_INS), r >> 2, r & 3);
             if (u < p) {
                 /* mutable_seq.insert(position + 1, base) */
                 int at = position + 1;
@@ -238,7 +241,8 @@ static int introduce_indels(const iss_oracle_model *M, draw_ctx *d, int o, uint8
         if (code < 0) return ISS_ORACLE_E_CHAR;
         double pd = del_p[position * 4 + code];
         if (pd > 0.0) {
-            double u = draw_u(d, rstream(o, K_DEL), (uint32_t)position >> 2, (uint32_t)position & 3);
+            const uint32_t r = (uint32_t)M->del_rank[(size_t)o * L + position];
+            double u = draw_u(d, rstream(o, K_DEL), r >> 2, r & 3);
             if (u < pd) {
                 /* mutable_seq.pop(position) */
                 memmove(m + position, m + position + 1, (size_t)(n - position - 1));
@@ -430,7 +434,7 @@ static int simulate_pair(const iss_oracle_model *M, const uint8_t *rec, int64_t 
 
 /*
  * Generate pairs i0..i1-1 of one work item (reads_generator + simulate_reads, generator.py:21-95).
- *   pair_base : ordinal of pair i=0 of this item inside its worker (RNG contract v1)
+ *   pair_base : ordinal of pair i=0 of this item inside its worker (RNG contract v2)
  *   out1/out2 : FASTQ sinks of capacity cap bytes each; (len1, len2) receive bytes written
  *   vcf       : optional VCF sink (store_mutations), capacity vcf_cap
  * gc_bias follows generator.py:82-92 literally: gc_fraction is 0..1 so `40 < gc < 60` never holds and the

@@ -53,6 +53,8 @@ class _CModel(ctypes.Structure):
         ("ins_p", ctypes.c_void_p),
         ("ins_base", ctypes.c_void_p),
         ("del_p", ctypes.c_void_p),
+        ("ins_rank", ctypes.c_void_p),
+        ("del_rank", ctypes.c_void_p),
         ("fixed_insert", ctypes.c_int32),
         ("qual_mode", ctypes.c_int32),
         ("const_phred", ctypes.c_int32),
@@ -273,6 +275,23 @@ class OracleModel:
         c.frag_lo = self.frag_lo
         c.n_frag = self.n_frag
         c.store_mutations = int(self.store_mutations)
+        # RNG contract v2: dense slot ranks of the non-zero indel sites over the loop positions 0..L-2
+        L = self.read_length
+        ins_p, del_p = self._arrays["ins_p"], self._arrays["del_p"]
+        ins_rank = np.full((2, L, 4), -1, dtype=np.int32)
+        del_rank = np.full((2, L), -1, dtype=np.int32)
+        for o in range(2):
+            ri = rd = 0
+            for pos in range(L - 1):
+                for lane in range(4):
+                    if ins_p[o, pos, lane] > 0:
+                        ins_rank[o, pos, lane] = ri
+                        ri += 1
+                if (del_p[o, pos] > 0).any():
+                    del_rank[o, pos] = rd
+                    rd += 1
+        self._arrays["ins_rank"] = ins_rank
+        self._arrays["del_rank"] = del_rank
         kind = getattr(self, "kind", "kde")
         c.fixed_insert = -1 if kind == "kde" else 200
         c.qual_mode = {"kde": 0, "perfect": 1, "basic": 2}[kind]

@@ -7,7 +7,7 @@ What it does: imports the UNMODIFIED reference package (`/root/reference/iss`) w
 stand-in `Bio` ahead of it on sys.path, then replaces only the five RNG entry points the hot
 path calls -- random.random, random.randrange, numpy.random.rand, numpy.random.choice,
 numpy.random.normal -- with functions that return the Philox word of the slot belonging to the
-calling site (oracle/philox.py, RNG contract v1).  The calling site is recovered from the
+calling site (oracle/philox.py, RNG contract v2).  The calling site is recovered from the
 caller's frame (function name, source line text, and its locals `position`, `orientation`,
 `nucl_to_insert`, `phred_list`).  Every line of arithmetic that decides a read -- CDF searches,
 Bernoulli tests, list insert/pop semantics, length adjustment, reverse complement, FASTQ text --
@@ -20,8 +20,8 @@ Sites (reference file:line):
   iss/generator.py:135 / 144 / 175      random.randrange   -> PAIR blk1 (w0,w1) / blk1 (w2,w3) / blk2 (w0,w1)
   iss/generator.py:88                   np.random.rand     -> PAIR blk0 w3 (gc_bias)
   iss/generator.py:122                  np.random.normal   -> PAIR blk2 (w2,w3) via integer fragment table
-  iss/error_models/__init__.py:194      random.random      -> INS(o) blk position, lane = key index
-  iss/error_models/__init__.py:209      random.random      -> DEL(o) word position
+  iss/error_models/__init__.py:194      random.random      -> INS(o) word of the site's rank among the non-zero (position, lane) entries
+  iss/error_models/__init__.py:209      random.random      -> DEL(o) word of the position's rank among the positions with a non-zero entry
   iss/error_models/__init__.py:94       random.random      -> QUAL(o) test word of position
   iss/error_models/__init__.py:95-97    np.random.choice   -> SUBC(o) word of position
 """
@@ -155,6 +155,22 @@ class PhiloxDriver:
     def _src(frame):
         return linecache.getline(frame.f_code.co_filename, frame.f_lineno)
 
+    def _ranks(self, tables, kind):
+        """Dense slot ranks of the non-zero indel sites (RNG contract v2), over loop positions 0..L-2."""
+        key = (id(tables), kind)
+        if key not in self._frag_cache:
+            ranks = {}
+            n = len(tables) - 1  # the loop runs over range(read_length - 1)
+            for pos in range(n):
+                if kind == "ins":
+                    for lane, p in enumerate(tables[pos].values()):
+                        if p > 0:
+                            ranks[(pos, lane)] = len(ranks)
+                elif any(p > 0 for p in tables[pos].values()):
+                    ranks[pos] = len(ranks)
+            self._frag_cache[key] = ranks
+        return self._frag_cache[key]
+
     # ---- replacements -----------------------------------------------------------------
     def _random(self):
         f = sys._getframe(1)
@@ -164,11 +180,17 @@ class PhiloxDriver:
             pos = f.f_locals["position"]
             src = self._src(f)
             if "< prob" in src:
-                table = (f.f_locals["insertions"])[pos]
-                lane = list(table.keys()).index(f.f_locals["nucl_to_insert"])
-                return self._u(philox.read_stream(o, philox.K_INS), pos, lane)
+                tables = f.f_locals["insertions"]
+                lane = list(tables[pos].keys()).index(f.f_locals["nucl_to_insert"])
+                r = self._ranks(tables, "ins").get((pos, lane))
+                if r is None:
+                    return 1.0  # probability not > 0: no slot, the test is false for any draw
+                return self._u(philox.read_stream(o, philox.K_INS), r >> 2, r & 3)
             if "deletions[" in src:
-                return self._u(philox.read_stream(o, philox.K_DEL), pos >> 2, pos & 3)
+                r = self._ranks(f.f_locals["deletions"], "del").get(pos)
+                if r is None:
+                    return 1.0
+                return self._u(philox.read_stream(o, philox.K_DEL), r >> 2, r & 3)
             raise RuntimeError("unmapped random.random() site in introduce_indels: %r" % src)
         if name == "mut_sequence":
             o = self._orient(f)

@@ -1,10 +1,10 @@
 """Philox4x32-10 (Salmon et al., SC'11; same constants as Random123 / cuRAND) and the
-draw-slot schedule ("RNG contract v1") shared by every implementation in this repo.
+draw-slot schedule ("RNG contract v2") shared by every implementation in this repo.
 
 TEST INFRASTRUCTURE ONLY (oracle/).  The product computes the same function on the GPU
 (insilicoseq_b200/csrc/philox.cuh); nothing in the product imports this file.
 
-RNG contract v1
+RNG contract v2 (v1 gave every indel site a slot: INS block = position, DEL word = position; v2 ranks the non-zero sites)
 ---------------
 The reference draws from two *sequential* MT19937 streams (stdlib `random`, legacy
 `numpy.random`) seeded with `seed + cpu_number` per worker (iss/generator.py:234-236).
@@ -29,9 +29,11 @@ fixed slot in a counter-based Philox4x32-10 stream:
       k=0 QUAL  block b : w0 phred(2b)  w1 subst-test(2b)  w2 phred(2b+1)  w3 subst-test(2b+1)
                           (kde.py:84 np.random.rand ; error_models/__init__.py:94 random.random)
       k=1 SUBC  block b : w_j substitution choice at position 4b+j   (__init__.py:95-97)
-      k=2 DEL   block b : w_j deletion test at loop position 4b+j    (__init__.py:209)
-      k=3 INS   block p : w_j insertion test at loop position p, j-th key of the
-                          insertion dict (A,T,C,G in every bundled model) (__init__.py:193-194)
+      k=2 DEL   rank r -> word r&3 of block r>>2; r = rank of the loop position among the positions 0..L-2
+                          at which ANY base has a deletion probability > 0            (__init__.py:209)
+      k=3 INS   rank r -> word r&3 of block r>>2; r = rank of (loop position, j-th key of the insertion dict)
+                          among the entries with probability > 0, in (position, j) order  (__init__.py:193-194)
+                A site whose probability is not > 0 has no slot: its test `random() < p` is false whatever is drawn.
 
     uniform()         := w * 2**-32           (exact in f64)
     randrange(a, b)   := a + ((w_lo | w_hi << 32) * (b - a) >> 64); ValueError if b <= a

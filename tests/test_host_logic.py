@@ -144,9 +144,17 @@ if dist is not None:
 def test_world_size_2_sharding_over_gloo(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(GLOO_WORKER)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", str(script), fixtures.ROOT]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    import socket
+
+    for _ in range(2):  # a rendezvous port can be taken between probing and binding; one retry on a fresh port
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), str(script), fixtures.ROOT]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        if out.returncode == 0:
+            break
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
     assert "GLOO_OK" in out.stdout
 

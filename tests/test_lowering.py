@@ -117,7 +117,7 @@ def test_basic_and_perfect_lowering():
 def test_worker_items_bookkeeping():
     items = eng_mod.worker_items([(0, 5), (1, 3), (2, 0), (0, 4)], cpu_number=3, seed=7,
                                  record_lengths=[1000, 100, 1000], read_length=126)
-    # record 1 is too short: skipped, but the pair ordinal still advances (RNG contract v1)
+    # record 1 is too short: skipped, but the pair ordinal still advances (RNG contract v2)
     assert items == [(0, 3, 5, 0, 0, 10), (0, 3, 4, 0, 8, 10)]
     assert eng_mod.philox_key(-5, 2) == (2 ** 64 - 3)
 
