@@ -298,7 +298,7 @@ def main():
     # ---- the same with --compress: gzip members produced on the GPU, only compressed bytes cross PCIe ------------
     def step_gz():
         n = 0
-        for b in eng.generate(items, batch_pairs=1 << 18, n_slots=3, compress=True):
+        for b in eng.generate(items, batch_pairs=1 << 18, compress=True):
             n += b.nbytes + b.nbytes2
         return n
 

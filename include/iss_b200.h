@@ -140,7 +140,7 @@ typedef struct {
     uint32_t sequence_type;   /* ISS_SEQ_* (generator.py:134-139,164-171) */
     uint32_t gc_bias;         /* generator.py:82-92 */
     uint64_t batch_pairs;     /* pairs per ring slot; 0 = default */
-    uint32_t n_slots;         /* ring depth (>= 2); 0 = default */
+    uint32_t n_slots;         /* ring depth (>= 2); 0 = default (3; 6 with compress) */
     uint32_t device_only;     /* 1: keep FASTQ in HBM (no D2H) -- kernel-throughput measurements */
     uint32_t tma_gather;      /* 1: stage each read's packed genome window into shared memory with cp.async.bulk + mbarrier
                                  instead of LDG (needs L >= 96).  Measured 1-2 % slower on B200 for both an L2-resident and

@@ -57,6 +57,7 @@ struct Slot {
     DevSegment *h_segs = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_gz = nullptr, ev_end = nullptr;  // ISS_TRACE only: after the compressor, after the queued copies
     int state = 0;  // 0 free, 1 in flight, 2 handed to the consumer
     uint64_t nbytes = 0, n_pairs = 0, first_item = 0, batch_index = 0;
     // --store_mutations: device event list -> host text
@@ -66,11 +67,11 @@ struct Slot {
     uint64_t event_cap = 0;
     uint32_t nseg = 0;
     // opts.compress: staging slots, member sizes/offsets, packed gzip streams, totals read back
-    uint8_t *d_gz_stage[2] = {nullptr, nullptr};
     uint8_t *d_gz_out[2] = {nullptr, nullptr};
-    uint32_t *d_gz_sizes[2] = {nullptr, nullptr};
-    uint64_t *d_gz_offsets[2] = {nullptr, nullptr};
+    uint32_t *d_gz_work[2] = {nullptr, nullptr};
+    uint64_t *d_gz_status[2] = {nullptr, nullptr};
     uint64_t *h_gz_total = nullptr;  // pinned [2]
+    uint64_t gz_pre[2] = {0, 0};     // compressed bytes whose D2H copy was queued before the total was known
     uint64_t gz_chunks_cap = 0;
     uint32_t gz_chunks = 0;
     uint64_t nbytes2 = 0;
@@ -112,6 +113,8 @@ struct iss_ctx {
     size_t smem = 0;
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
+    bool trace = getenv("ISS_TRACE") != nullptr;
+    double gz_ratio[2] = {0.4, 0.4};            // compressed / plain bytes per stream: a first guess, then the last returned batch
     bool active = false, exhausted = false;
     unsigned long long *d_counters = nullptr;
     // benchmarking marks
@@ -139,10 +142,9 @@ void free_slots(iss_ctx *c) {
         if (s.d_segs) cudaFree(s.d_segs);
         if (s.h_segs) cudaFreeHost(s.h_segs);
         for (int k = 0; k < 2; ++k) {
-            if (s.d_gz_stage[k]) cudaFree(s.d_gz_stage[k]);
             if (s.d_gz_out[k]) cudaFree(s.d_gz_out[k]);
-            if (s.d_gz_sizes[k]) cudaFree(s.d_gz_sizes[k]);
-            if (s.d_gz_offsets[k]) cudaFree(s.d_gz_offsets[k]);
+            if (s.d_gz_work[k]) cudaFree(s.d_gz_work[k]);
+            if (s.d_gz_status[k]) cudaFree(s.d_gz_status[k]);
         }
         if (s.h_gz_total) cudaFreeHost(s.h_gz_total);
         if (s.d_scratch) cudaFree(s.d_scratch);
@@ -153,6 +155,8 @@ void free_slots(iss_ctx *c) {
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.ev_gz) cudaEventDestroy(s.ev_gz);
+        if (s.ev_end) cudaEventDestroy(s.ev_end);
     }
     c->slots.clear();
 }
@@ -311,16 +315,31 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     if (c->opts.compress) {
         s.gz_chunks = iss_gz_chunks(bytes);
         for (int k = 0; k < 2; ++k) {
-            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_stage[k], s.d_gz_sizes[k], s.d_gz_offsets[k], s.d_gz_out[k], c->sm_count, s.stream));
-            CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_offsets[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_status[k], s.d_gz_out[k], s.d_gz_work[k], c->sm_count, s.stream));
+            CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_status[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
         }
-        c->stats.kernel_launches += 6;
+        if (c->trace) CU(cudaEventRecord(s.ev_gz, s.stream));
+        // The host learns the compressed size only when the batch is done; queuing the D2H copy after that costs a host
+        // round trip per batch, and a late small copy would also wait behind the other slots' copies in the copy
+        // engine's queue.  Batches of one run compress alike (same model, same read length), so the copy is queued now
+        // for 1 % more than the previous batch's ratio predicts; iss_ctx_next fetches a remainder only if that fell short.
+        for (int k = 0; k < 2; ++k) {
+            s.gz_pre[k] = 0;
+            if (!c->opts.device_only && c->gz_ratio[k] > 0.0) {
+                const uint64_t pre = std::min<uint64_t>(c->slot_cap, (uint64_t)(1.01 * c->gz_ratio[k] * (double)bytes) + 65536u);
+                if (pre) CU(cudaMemcpyAsync(s.h_out[k], s.d_gz_out[k], pre, cudaMemcpyDeviceToHost, s.stream));
+                s.gz_pre[k] = pre;
+                c->stats.d2h_bytes += pre;
+            }
+        }
+        c->stats.kernel_launches += 6;  // histogram, code table and member kernels, per stream
     } else if (!c->opts.device_only) {
         CU(cudaMemcpyAsync(s.h_out[0], s.d_out[0], bytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
         c->stats.d2h_bytes += 2 * bytes;
     }
     CU(cudaEventRecord(s.ev_done, s.stream));
+    if (c->trace) CU(cudaEventRecord(s.ev_end, s.stream));
     s.state = 1;
     s.nbytes = bytes;
     s.n_pairs = pairs;
@@ -718,7 +737,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     iss_gen_opts o{};
     if (opts) o = *opts;
     if (o.batch_pairs == 0) o.batch_pairs = 1u << 18;
-    if (o.n_slots == 0) o.n_slots = 3;
+    if (o.n_slots == 0) o.n_slots = o.compress ? 6 : 3;  // the compressed path has the longer per-batch chain (compress, then copy)
     if (o.n_slots < 2 && !o.device_only) o.n_slots = 2;
     if (o.n_slots > 16) o.n_slots = 16;
     if (const char *e = getenv("ISS_TMA_GATHER")) o.tma_gather = (e[0] == '1');  // A/B switch for benchmarks
@@ -763,7 +782,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     const uint32_t grid = (uint32_t)(c->sm_count * bps);
     const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
     const uint32_t max_segs = 1u << 16;
-    const bool realloc = c->slots.size() != o.n_slots || (o.compress && (c->slots.empty() || !c->slots[0].d_gz_stage[0])) || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
+    const bool realloc = c->slots.size() != o.n_slots || (o.compress && (c->slots.empty() || !c->slots[0].d_gz_out[0])) || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
                          (bool)c->opts.device_only != (c->slots.size() && c->slots[0].h_out[0] == nullptr);
     if (realloc) {
         free_slots(c);
@@ -784,10 +803,9 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             if (o.compress) {
                 s.gz_chunks_cap = iss_gz_chunks(slot_cap) + 1;
                 for (int k = 0; k < 2; ++k) {
-                    CU(cudaMalloc(&s.d_gz_stage[k], s.gz_chunks_cap * ISS_GZ_STRIDE));
                     CU(cudaMalloc(&s.d_gz_out[k], s.gz_chunks_cap * ISS_GZ_STRIDE));
-                    CU(cudaMalloc(&s.d_gz_sizes[k], s.gz_chunks_cap * sizeof(uint32_t)));
-                    CU(cudaMalloc(&s.d_gz_offsets[k], (s.gz_chunks_cap + 1) * sizeof(uint64_t)));
+                    CU(cudaMalloc(&s.d_gz_work[k], ISS_GZ_WORK_WORDS * sizeof(uint32_t)));  // the call scratch
+                    CU(cudaMalloc(&s.d_gz_status[k], (s.gz_chunks_cap + 1) * sizeof(uint64_t)));
                 }
                 CU(cudaMallocHost(&s.h_gz_total, 2 * sizeof(uint64_t)));
             }
@@ -797,6 +815,8 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             CU(cudaEventCreate(&s.ev_k0));
             CU(cudaEventCreate(&s.ev_k1));
             CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+            CU(cudaEventCreate(&s.ev_gz));
+            CU(cudaEventCreate(&s.ev_end));
         }
         c->slot_cap = slot_cap;
         c->max_segs = max_segs;
@@ -852,6 +872,16 @@ int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
     CU(cudaEventSynchronize(s.ev_done));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
+    if (c->trace && c->marks[0]) {  // ISS_TRACE=1: device timeline of the batch relative to mark 0 (ms)
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        cudaEventElapsedTime(&t0, c->marks[0], s.ev_k0);
+        cudaEventElapsedTime(&t1, c->marks[0], s.ev_k1);
+        if (c->opts.compress) cudaEventElapsedTime(&t2, c->marks[0], s.ev_gz);
+        cudaEventElapsedTime(&t3, c->marks[0], s.ev_end);
+        cudaGetLastError();
+        fprintf(stderr, "[iss trace] batch %llu slot %u: kernel %.3f..%.3f  gz_end %.3f  queued_copies_end %.3f\n",
+                (unsigned long long)s.batch_index, si, t0, t1, t2, t3);
+    }
     c->stats.kernel_ms += ms;
     s.state = 2;
     b->r1 = c->opts.device_only ? s.d_out[0] : s.h_out[0];
@@ -861,15 +891,23 @@ int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
     if (c->opts.compress) {  // sizes are known only now: fetch exactly the compressed bytes
         b->nbytes = s.h_gz_total[0];
         b->nbytes2 = s.h_gz_total[1];
+        if (ISS_GZ_FAILED(b->nbytes) || ISS_GZ_FAILED(b->nbytes2)) return fail(ISS_E_STATE, "internal: gzip member placement timed out");
         if (c->opts.device_only) {
             b->r1 = s.d_gz_out[0];
             b->r2 = s.d_gz_out[1];
         } else {
             if (b->nbytes > c->slot_cap || b->nbytes2 > c->slot_cap) return fail(ISS_E_STATE, "internal: gzip stream larger than the slot");
-            CU(cudaMemcpyAsync(s.h_out[0], s.d_gz_out[0], b->nbytes, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaMemcpyAsync(s.h_out[1], s.d_gz_out[1], b->nbytes2, cudaMemcpyDeviceToHost, s.stream));
-            CU(cudaStreamSynchronize(s.stream));
-            c->stats.d2h_bytes += b->nbytes + b->nbytes2;
+            const uint64_t tot[2] = {b->nbytes, b->nbytes2};
+            bool more = false;
+            for (int k = 0; k < 2; ++k) {
+                if (s.nbytes) c->gz_ratio[k] = (double)tot[k] / (double)s.nbytes;
+                if (tot[k] > s.gz_pre[k]) {
+                    CU(cudaMemcpyAsync(s.h_out[k] + s.gz_pre[k], s.d_gz_out[k] + s.gz_pre[k], tot[k] - s.gz_pre[k], cudaMemcpyDeviceToHost, s.stream));
+                    c->stats.d2h_bytes += tot[k] - s.gz_pre[k];
+                    more = true;
+                }
+            }
+            if (more) CU(cudaStreamSynchronize(s.stream));
         }
     }
     b->vcf = nullptr;
@@ -945,23 +983,23 @@ int iss_ctx_gzip(iss_ctx *c, const uint8_t *in, uint64_t n, uint8_t *out, uint64
     if (!c || (!in && n) || !out || !out_n) return fail(ISS_E_ARG, "null argument");
     if (int rc = set_device(c)) return rc;
     const uint32_t nc = iss_gz_chunks(n);
-    uint8_t *d_in = nullptr, *d_stage = nullptr, *d_out = nullptr;
-    uint32_t *d_sizes = nullptr;
-    uint64_t *d_off = nullptr;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint32_t *d_work = nullptr;
+    uint64_t *d_status = nullptr;
     CU(cudaMalloc(&d_in, n + 16));
-    CU(cudaMalloc(&d_stage, (uint64_t)(nc + 1) * ISS_GZ_STRIDE));
     CU(cudaMalloc(&d_out, (uint64_t)(nc + 1) * ISS_GZ_STRIDE));
-    CU(cudaMalloc(&d_sizes, (nc + 1) * sizeof(uint32_t)));
-    CU(cudaMalloc(&d_off, (nc + 2) * sizeof(uint64_t)));
+    CU(cudaMalloc(&d_work, ISS_GZ_WORK_WORDS * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_status, (nc + 2) * sizeof(uint64_t)));
     if (n) CU(cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
-    CU(iss_gz_compress(d_in, n, d_stage, d_sizes, d_off, d_out, c->sm_count, 0));
+    CU(iss_gz_compress(d_in, n, d_status, d_out, d_work, c->sm_count, 0));
     uint64_t total = 0;
-    CU(cudaMemcpy(&total, d_off + nc, sizeof total, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&total, d_status + nc, sizeof total, cudaMemcpyDeviceToHost));
     int rc = ISS_OK;
-    if (total > cap) rc = fail(ISS_E_ARG, "output buffer too small");
+    if (ISS_GZ_FAILED(total)) rc = fail(ISS_E_STATE, "internal: gzip member placement timed out");
+    else if (total > cap) rc = fail(ISS_E_ARG, "output buffer too small");
     else if (total) CU(cudaMemcpy(out, d_out, total, cudaMemcpyDeviceToHost));
     *out_n = total;
-    cudaFree(d_in); cudaFree(d_stage); cudaFree(d_out); cudaFree(d_sizes); cudaFree(d_off);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_work); cudaFree(d_status);
     return rc;
 }
 

@@ -191,7 +191,7 @@ def test_work_item_split_across_submits():
 def test_gpu_gzip_roundtrip_arbitrary_bytes():
     """The GPU gzip is checked by decompression with Python's gzip: FASTQ text, empty input, a single
     symbol, all byte values, incompressible data (stored-block fallback), a skewed distribution that needs the 15-bit
-    length limit, and sizes around the 64 KB member boundary."""
+    length limit, sizes around the 64 KB member boundary, and a long non-uniform stream."""
     import gzip
 
     from insilicoseq_b200.engine import Engine
@@ -206,6 +206,9 @@ def test_gpu_gzip_roundtrip_arbitrary_bytes():
                b"@r_1/1\nACGT\n+\nIIII\n" * 10000, rng.bytes(65535), rng.bytes(65536), rng.bytes(65537), b"x" * 65536, b"y" * 65537]
     fq = open(os.path.join(fixtures.GOLDEN, "miseq_legacy_indels", "R1.fastq"), "rb").read() * 40
     samples.append(fq)
+    # the code of a call comes from a strided sample (> 4 MB: not every 16 KB piece is looked at); a stream that changes
+    # character half way must still round-trip, whatever the sample saw
+    samples.append(b"ACGT" * 1_500_000 + rng.bytes(3_000_000) + b"\x00\xff" * 70_001)
     with Engine(0) as e:
         for data in samples:
             z = e.gzip(data)

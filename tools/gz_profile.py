@@ -10,5 +10,5 @@ with eng_mod.Engine(0) as e:
     e.set_model(error_models.KDErrorModel(os.path.join(error_models.PROFILE_DIR, "miSeq_0.npz")).truncate(150))
     items = eng_mod.worker_items([(0, 1 << 20)], 0, 42, e.record_lengths, e.read_length)
     for rep in range(3):
-        n = sum(b.nbytes + b.nbytes2 for b in e.generate(items, batch_pairs=1 << 18, n_slots=3, compress=True))
+        n = sum(b.nbytes + b.nbytes2 for b in e.generate(items, batch_pairs=1 << 18, compress=True))
     print("compressed bytes", n)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Attribute ncu per-SASS metrics to source lines: tools/ncu_lines.py <report.ncu-rep> [top]
-(uses nvdisasm -g line info of the in-tree .so; prints the busiest source lines by stall samples)."""
+(uses nvdisasm -g line info of the in-tree .so; prints the busiest source lines by stall samples).
+ISS_KERNEL_FILE (default iss_kernels) and ISS_KERNEL_SYM (default the 256-thread generate kernel) choose another kernel."""
 import csv
 import os
 import re
@@ -14,19 +15,21 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "insilicoseq_b200/csrc/libiss_b200.so")], cwd=tmp,
                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-cub = [f for f in os.listdir(tmp) if f.startswith("iss_kernels.") and f.endswith(".cubin")][0]
+KFILE = os.environ.get("ISS_KERNEL_FILE", "iss_kernels")
+cub = [f for f in os.listdir(tmp) if f.startswith(KFILE + ".") and f.endswith(".cubin")][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(sass) if l.startswith(".text._Z19iss_generate_kernelILi%s" % os.environ.get("ISS_KERNEL_THREADS", "256"))][0]
+SYM = os.environ.get("ISS_KERNEL_SYM", "_Z19iss_generate_kernelILi%s" % os.environ.get("ISS_KERNEL_THREADS", "256"))
+start = [i for i, l in enumerate(sass) if l.startswith(".text." + SYM)][0]
 ins, cur, inl = [], None, None
 for l in sass[start + 1:]:
     if (l.startswith(".text.") or l.startswith("\t.section")) and ins:
         break
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(.*)', l)
     if m:
-        own = m.group(1).endswith("iss_kernels.cu")
+        own = m.group(1).endswith(KFILE + ".cu")
         cur = int(m.group(2)) if own else "H:%s:%s" % (m.group(1).split("/")[-1], m.group(2))
         mm = re.search(r'inlined at "([^"]+)", line (\d+)', m.group(3))
-        inl = int(mm.group(2)) if mm and mm.group(1).endswith("iss_kernels.cu") else None
+        inl = int(mm.group(2)) if mm and mm.group(1).endswith(KFILE + ".cu") else None
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
@@ -60,7 +63,7 @@ for (off, line, inl_, text), r in zip(ins, data):
         b[1] += f(r[idx["# Samples"]])
 ti = sum(a[0] for a in agg.values())
 ts = sum(a[1] for a in agg.values())
-src = open(os.path.join(ROOT, "insilicoseq_b200/csrc/iss_kernels.cu")).read().split("\n")
+src = open(os.path.join(ROOT, "insilicoseq_b200/csrc/%s.cu" % KFILE)).read().split("\n")
 print("warp-instructions %.4g  samples %d" % (ti, ts))
 for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     text = src[key - 1].strip()[:100] if isinstance(key, int) else str(key)
