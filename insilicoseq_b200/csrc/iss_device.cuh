@@ -109,8 +109,8 @@ struct ModelHeader {
     uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic, store_mutations;
     int32_t fixed_insert;
     uint32_t n_nz[2];      // positions (< L-1) with a non-zero insertion or deletion threshold
-    uint32_t n_ent;        // indel draw sites with a non-zero threshold (RNG contract v2), all lists together
-    uint32_t ent_begin[5]; // start of: insertion sites fwd, deletion sites fwd, insertion sites rev, deletion sites rev, end
+    uint32_t n_grp;        // groups of 4 indel draw sites (= one Philox block; RNG contract v2), all lists together
+    uint32_t grp_begin[5]; // first group of: insertion sites fwd, deletion sites fwd, insertion sites rev, deletion sites rev; end
     uint32_t pad;
     int64_t frag_lo;
     uint64_t bin_thr[2][4];
@@ -136,8 +136,8 @@ struct DevModel {
     const uint32_t *del_thr;    // [2][L][4]
     const uint8_t *del_nz;      // [2][L]
     const uint16_t *nzpos;      // [2][L]
-    const uint4 *ent;           // [n_ent][2]: {thresholds D (x: insertion lane, or x..w by base for a deletion site)},
-                                //             {x: pos | kind << 16 | o << 17 | per-base non-zero mask << 18 | lane << 22, y: slot rank}
+    const uint4 *ent;           // [n_grp][2]: {reject thresholds of the group's 4 sites: the insertion threshold, or the
+                                //             largest of a deletion site's 4}, {site: pos | valid << 16 | insertion lane << 17}
     const uint32_t *basic_thr;
     const uint8_t *basic_val;
 };
@@ -244,8 +244,8 @@ struct GenParams {
     int32_t fixed_insert;
     int64_t frag_lo;
     uint32_t n_nz[2];
-    uint32_t n_ent;
-    uint32_t ent_begin[5];
+    uint32_t n_grp;
+    uint32_t grp_begin[5];
     uint64_t bin_thr[2][4];
     uint8_t bin_valid[2][4];
     uint32_t err_thr[ISS_QROW];

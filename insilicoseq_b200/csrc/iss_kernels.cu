@@ -48,6 +48,9 @@ __device__ __forceinline__ uint32_t complement_ascii(uint32_t c) { return (uint3
 __device__ __forceinline__ uint32_t pick(const Philox4 &w, uint32_t j) {
     return j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
 }
+__device__ __forceinline__ uint32_t pick(const uint4 &w, uint32_t j) {
+    return j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
+}
 __device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
 // Quality rows are stored as a 2-level 8-ary search tree (ISS_QBT_STRIDE = 96 words per row, 128 B aligned, built by
@@ -88,26 +91,16 @@ __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_
 
 // bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
 
-// ---- one indel draw site (RNG contract v2): does it fire for current base c?  The site's slot is word rank & 3 of
-//      Philox block rank >> 2 of the INS / DEL stream of its orientation; blocks are cached across consecutive ranks.
-struct EntCache { uint32_t key; Philox4 w; };
-__device__ __forceinline__ uint32_t entry_bits(const GenParams &p, uint32_t n, uint32_t att8, uint32_t Plo, uint32_t Phi, EntCache &cache,
-                                               uint32_t &pos_out, uint32_t &so_out) {
-    // returns the site's mask bits: bit lane (insertion fires) or bits 4+b for every base b whose deletion fires
-    const uint4 thr = __ldg(p.m.ent + 2u * n), mt = __ldg(p.m.ent + 2u * n + 1u);
-    const uint32_t so = (mt.x >> 17) & 1u, kind = (mt.x >> 16) & 1u, blk = mt.y >> 2;
-    pos_out = mt.x & 0xFFFFu;
-    so_out = so;
-    const uint32_t ck = (so << 31) | (kind << 30) | blk;
-    if (ck != cache.key) {
-        cache.key = ck;
-        cache.w = philox4x32_10_rk(blk, iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
-    }
-    const uint32_t word = pick(cache.w, mt.y & 3u);
-    if (kind == 0u) return (word <= thr.x) ? (1u << ((mt.x >> 22) & 3u)) : 0u;
-    const uint32_t nz = (mt.x >> 18) & 15u;
-    return ((((nz & 1u) && word <= thr.x) ? 1u : 0u) | (((nz & 2u) && word <= thr.y) ? 2u : 0u) |
-            (((nz & 4u) && word <= thr.z) ? 4u : 0u) | (((nz & 8u) && word <= thr.w) ? 8u : 0u)) << 4;
+// ---- one indel draw site (RNG contract v2) that passed the group's reject test: which events does its draw allow?
+//      Returns bit `lane` for an insertion site, bits 4 + b for every base b whose deletion fires at a deletion site.
+__device__ __noinline__ uint32_t site_bits(const GenParams &p, uint32_t so, uint32_t kind, uint32_t word, uint32_t thr, uint32_t meta) {
+    if (!((meta >> 16) & 1u) || word > thr) return 0u;  // padding, or this site of the group did not pass
+    if (kind == 0u) return 1u << ((meta >> 17) & 3u);
+    const uint32_t tb = so * p.L + (meta & 0xFFFFu);
+    const uint32_t nz = p.m.del_nz[tb];
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p.m.del_thr) + tb);
+    return ((((nz & 1u) && word <= t.x) ? 1u : 0u) | (((nz & 2u) && word <= t.y) ? 2u : 0u) |
+            (((nz & 4u) && word <= t.z) ? 4u : 0u) | (((nz & 8u) && word <= t.w) ? 8u : 0u)) << 4;
 }
 
 // ---- mbarrier / TMA bulk-copy helpers (genome windows: global -> shared, completion counted on an mbarrier) -------
@@ -476,18 +469,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         const uint32_t Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
         const uint32_t att8 = valid ? (u32p(l.sAtt)[pair] << 8) : 0;
         uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
-        if (valid && p.n_ent) {
-            const uint32_t n_begin = (q4 * p.n_ent) >> (p.split_shift + 1u), n_end = ((q4 + 1u) * p.n_ent) >> (p.split_shift + 1u);
+        if (valid && p.n_grp) {
+            const uint32_t g_begin = (q4 * p.n_grp) >> (p.split_shift + 1u), g_end = ((q4 + 1u) * p.n_grp) >> (p.split_shift + 1u);
             uint32_t fired = 0;  // bit so set when read orientation so has an event
-            EntCache cache;
-            cache.key = 0xFFFFFFFFu;
-            for (uint32_t n = n_begin; n < n_end; ++n) {
-                uint32_t pos, so;
-                const uint32_t bits = entry_bits(p, n, att8, Plo, Phi, cache, pos, so);
-                if (!bits || ((fired >> so) & 1u)) continue;
-                const uint32_t c = (imgp(l, so) + u32p(l.sSeqOff)[so * T + pair])[pos];
-                if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
-                if ((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) fired |= 1u << so;
+            for (uint32_t g = g_begin; g < g_end; ++g) {
+                const uint32_t li = (g >= p.grp_begin[1] ? 1u : 0u) + (g >= p.grp_begin[2] ? 1u : 0u) + (g >= p.grp_begin[3] ? 1u : 0u);
+                const uint32_t so = li >> 1, kind = li & 1u;
+                const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
+                const Philox4 w = philox4x32_10_rk(g - p.grp_begin[li], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
+                if ((w.x <= t.x) | (w.y <= t.y) | (w.z <= t.z) | (w.w <= t.w)) {  // rare: some site may fire
+                    const uint8_t *sq = imgp(l, so) + u32p(l.sSeqOff)[so * T + pair];
+#pragma unroll 1
+                    for (uint32_t r = 0; r < 4; ++r) {
+                        const uint32_t meta = pick(mt, r);
+                        const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
+                        if (!bits) continue;
+                        const uint32_t c = sq[meta & 0xFFFFu];
+                        if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
+                        if ((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) fired |= 1u << so;
+                    }
+                }
             }
             for (uint32_t so = 0; so < 2; ++so)
                 if (((fired >> so) & 1u) && atomicExch(&u32p(l.sFlag)[so * T + pair], 1u) == 0u)
@@ -503,26 +504,29 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 // fires.  The masks live in the (still unused) substitution list.
                 uint32_t *masks32 = u32p(l.sErr);
                 uint8_t *masks = reinterpret_cast<uint8_t *>(masks32);
-                const uint32_t n_o0 = p.ent_begin[2] - p.ent_begin[0], n_o1 = p.ent_begin[4] - p.ent_begin[2];
-                const uint32_t ngrp = (((n_o0 > n_o1) ? n_o0 : n_o1) + 3u) >> 2;  // groups of 4 consecutive sites (one Philox block each)
+                const uint32_t n_o0 = p.grp_begin[2] - p.grp_begin[0], n_o1 = p.grp_begin[4] - p.grp_begin[2];
+                const uint32_t ngrp = (n_o0 > n_o1) ? n_o0 : n_o1;  // groups of 4 sites (one Philox block each) per read
                 for (uint32_t base = 0; base < nslow; base += p.slow_slots) {
                     const uint32_t nround = (nslow - base < p.slow_slots) ? (nslow - base) : p.slow_slots;
                     for (uint32_t i = tid; i < ((nround * L + 3u) >> 2); i += blockDim.x) masks32[i] = 0;
                     __syncthreads();
                     for (uint32_t idx = tid; idx < nround * ngrp; idx += blockDim.x) {
-                        const uint32_t sidx = idx / ngrp, g = idx - sidx * ngrp;
+                        const uint32_t sidx = idx / ngrp, gq = idx - sidx * ngrp;
                         const uint32_t srd = u32p(l.sSlow)[base + sidx];
                         const uint32_t so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
+                        const uint32_t g = p.grp_begin[2u * so] + gq;
+                        if (g >= p.grp_begin[2u * so + 2u]) continue;
+                        const uint32_t kind = g >= p.grp_begin[2u * so + 1u] ? 1u : 0u;
                         const uint64_t sP = u64p(l.sP)[sp_];
-                        const uint32_t sa8 = u32p(l.sAtt)[sp_] << 8;
-                        const uint32_t e0 = p.ent_begin[2u * so], e1 = p.ent_begin[2u * so + 2u];
-                        EntCache cache;
-                        cache.key = 0xFFFFFFFFu;
-                        for (uint32_t n = e0 + 4u * g; n < e1 && n < e0 + 4u * g + 4u; ++n) {
-                            uint32_t pos, eo;
-                            const uint32_t bits = entry_bits(p, n, sa8, (uint32_t)sP, (uint32_t)(sP >> 32), cache, pos, eo);
+                        const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
+                        const Philox4 w = philox4x32_10_rk(g - p.grp_begin[2u * so + kind], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | (u32p(l.sAtt)[sp_] << 8),
+                                                           (uint32_t)sP, (uint32_t)(sP >> 32), p.rk);
+#pragma unroll 1
+                        for (uint32_t r = 0; r < 4; ++r) {
+                            const uint32_t meta = pick(mt, r);
+                            const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
                             if (bits) {
-                                const uint32_t bi = sidx * L + pos;
+                                const uint32_t bi = sidx * L + (meta & 0xFFFFu);
                                 atomicOr(&masks32[bi >> 2], bits << (8u * (bi & 3u)));
                             }
                         }

@@ -270,8 +270,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.L = h.L; p.qual_mode = h.qual_mode; p.n_insert = h.n_insert; p.frag_mode = h.frag_mode; p.n_frag = h.n_frag;
     p.const_phred = h.const_phred; p.n_basic = h.n_basic; p.fixed_insert = h.fixed_insert; p.frag_lo = h.frag_lo;
     p.n_nz[0] = h.n_nz[0]; p.n_nz[1] = h.n_nz[1];
-    p.n_ent = h.n_ent;
-    memcpy(p.ent_begin, h.ent_begin, sizeof p.ent_begin);
+    p.n_grp = h.n_grp;
+    memcpy(p.grp_begin, h.grp_begin, sizeof p.grp_begin);
     memcpy(p.bin_thr, h.bin_thr, sizeof p.bin_thr);
     memcpy(p.bin_valid, h.bin_valid, sizeof p.bin_valid);
     memcpy(p.err_thr, h.err_thr, sizeof p.err_thr);
@@ -554,33 +554,35 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
         h.n_nz[o] = cnt;
     }
     // RNG contract v2: the indel draw sites with a non-zero threshold, ranked in loop order per (orientation, kind);
-    // rank r reads word r & 3 of Philox block r >> 2.  Lists: insertion fwd, deletion fwd, insertion rev, deletion rev.
-    struct Ent { uint32_t thr[4]; uint32_t meta, rank, pad0, pad1; };
-    std::vector<Ent> ents;
-    for (uint32_t o = 0; o < 2; ++o) {
-        h.ent_begin[2 * o] = (uint32_t)ents.size();
-        uint32_t rank = 0;
-        for (uint32_t pos = 0; pos + 1 < L; ++pos)
-            for (uint32_t lane = 0; lane < 4; ++lane)
-                if ((m->ins_nz[o * L + pos] >> lane) & 1u) {
-                    Ent e{};
-                    e.thr[0] = m->ins_thr[(o * L + pos) * 4 + lane];
-                    e.meta = pos | (0u << 16) | (o << 17) | (lane << 22);
-                    e.rank = rank++;
-                    ents.push_back(e);
+    // rank r reads word r & 3 of Philox block r >> 2.  Lists: insertion fwd, deletion fwd, insertion rev, deletion rev,
+    // each padded to whole groups of 4 sites with sites that never fire (valid = 0).  A group carries what the scan
+    // needs to reject it -- word > threshold for all 4 sites -- and the rare survivor is evaluated from the full tables.
+    struct Grp { uint32_t thr[4]; uint32_t meta[4]; };
+    std::vector<Grp> grps;
+    for (uint32_t o = 0; o < 2; ++o)
+        for (uint32_t kind = 0; kind < 2; ++kind) {
+            h.grp_begin[2 * o + kind] = (uint32_t)grps.size();
+            uint32_t rank = 0;
+            auto add = [&](uint32_t thr, uint32_t meta) {
+                if ((rank & 3u) == 0) grps.push_back(Grp{});
+                grps.back().thr[rank & 3u] = thr;
+                grps.back().meta[rank & 3u] = meta;
+                ++rank;
+            };
+            for (uint32_t pos = 0; pos + 1 < L; ++pos) {
+                const uint32_t tb = o * L + pos;
+                if (kind == 0) {
+                    for (uint32_t lane = 0; lane < 4; ++lane)
+                        if ((m->ins_nz[tb] >> lane) & 1u) add(m->ins_thr[tb * 4 + lane], pos | (1u << 16) | (lane << 17));
+                } else if (m->del_nz[tb] & 15u) {
+                    uint32_t tmax = 0;
+                    for (uint32_t b = 0; b < 4; ++b)
+                        if ((m->del_nz[tb] >> b) & 1u) tmax = std::max(tmax, m->del_thr[tb * 4 + b]);
+                    add(tmax, pos | (1u << 16));
                 }
-        h.ent_begin[2 * o + 1] = (uint32_t)ents.size();
-        rank = 0;
-        for (uint32_t pos = 0; pos + 1 < L; ++pos)
-            if (m->del_nz[o * L + pos] & 15u) {
-                Ent e{};
-                for (int b = 0; b < 4; ++b) e.thr[b] = m->del_thr[(o * L + pos) * 4 + b];
-                e.meta = pos | (1u << 16) | (o << 17) | ((uint32_t)(m->del_nz[o * L + pos] & 15u) << 18);
-                e.rank = rank++;
-                ents.push_back(e);
             }
-    }
-    h.ent_begin[4] = h.n_ent = (uint32_t)ents.size();
+        }
+    h.grp_begin[4] = h.n_grp = (uint32_t)grps.size();
     uint64_t off = align_up(sizeof(ModelHeader), 16);
     auto place = [&](uint64_t bytes) { uint64_t at = off; off = align_up(off + std::max<uint64_t>(bytes, 16), 16); return at; };
     const uint64_t qual_bytes = m->qual_mode == ISS_QUAL_KDE ? (2ull * 4 * L + 1) * ISS_QBT_STRIDE * 4 : 0;
@@ -598,7 +600,7 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     h.nzpos_off = place(2ull * L * 2);
     h.basic_thr_off = place(4ull * m->n_basic);
     h.basic_val_off = place(1ull * m->n_basic + 1);
-    h.ent_off = place(sizeof(Ent) * ents.size());
+    h.ent_off = place(sizeof(Grp) * grps.size());
     h.total_bytes = off;
     std::vector<uint8_t> blob(off, 0);
     memcpy(blob.data(), &h, sizeof h);
@@ -625,7 +627,7 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     put(h.del_thr_off, m->del_thr, 2ull * L * 4 * 4);
     put(h.del_nz_off, m->del_nz, 2ull * L);
     put(h.nzpos_off, nzpos.data(), 2ull * L * 2);
-    put(h.ent_off, ents.data(), sizeof(Ent) * ents.size());
+    put(h.ent_off, grps.data(), sizeof(Grp) * grps.size());
     put(h.basic_thr_off, m->basic_thr, 4ull * m->n_basic);
     put(h.basic_val_off, m->basic_val, 1ull * m->n_basic + (m->basic_val ? 1 : 0));
     if (c->d_model) { cudaFree(c->d_model); c->d_model = nullptr; }
