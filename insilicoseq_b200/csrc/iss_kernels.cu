@@ -661,6 +661,12 @@ cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
     return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
 }
 
+cudaError_t iss_kernel_carveout(int percent) {  // shared-memory share of the SM's unified L1/shared array
+    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+}
+
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
     if (threads > 256) iss_generate_kernel<512, 2><<<grid, threads, smem, stream>>>(p);

@@ -781,6 +781,11 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         if (bps4 >= bps) { split_shift = 2; bps = bps4; }
     }
     c->split_shift = split_shift;
+    if (const char *e = getenv("ISS_BPS")) {  // A/B switch for benchmarks: fewer CTAs per SM (with ISS_CARVEOUT: more L1)
+        const int cap = atoi(e);
+        if (cap >= 1 && cap < bps) bps = cap;
+    }
+    if (const char *e = getenv("ISS_CARVEOUT")) CU(iss_kernel_carveout(atoi(e)));
     const uint32_t grid = (uint32_t)(c->sm_count * bps);
     const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
     const uint32_t max_segs = 1u << 16;
