@@ -765,6 +765,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     uint32_t T = 64;
     uint32_t img_cap = 0;
     size_t smem = 0;
+    c->err_cap = 1024;
     for (;; T -= 32) {
         img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
         smem = iss_tile_smem_bytes(T, img_cap, c->err_cap);
