@@ -108,17 +108,16 @@ struct ModelHeader {
     uint64_t total_bytes;
     uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic, store_mutations;
     int32_t fixed_insert;
-    uint32_t n_nz[2];      // positions (< L-1) with a non-zero insertion or deletion threshold
     uint32_t n_grp;        // groups of 4 indel draw sites (= one Philox block; RNG contract v2), all lists together
     uint32_t grp_begin[5]; // first group of: insertion sites fwd, deletion sites fwd, insertion sites rev, deletion sites rev; end
-    uint32_t pad;
+    uint32_t pad[3];
     int64_t frag_lo;
     uint64_t bin_thr[2][4];
     uint8_t bin_valid[2][4];
     uint32_t err_thr[ISS_QROW];
     // offsets (bytes from blob start)
-    uint64_t frag_thr_off, insert_thr_off, qual_thr_off, subst_n_off, subst_thr_off, subst_alt_off, ins_thr_off,
-        ins_nz_off, ins_base_off, del_thr_off, del_nz_off, nzpos_off, basic_thr_off, basic_val_off, ent_off;
+    uint64_t frag_thr_off, insert_thr_off, qual_thr_off, subst_n_off, subst_thr_off, subst_alt_off, ins_base_off,
+        del_thr_off, del_nz_off, basic_thr_off, basic_val_off, ent_off;
 };
 
 // pointer view built on each device from the blob base
@@ -130,12 +129,9 @@ struct DevModel {
     const uint8_t *subst_n;     // [2][L][4]
     const uint64_t *subst_thr;  // [2][L][4][4]
     const uint8_t *subst_alt;   // [2][L][4][4]
-    const uint32_t *ins_thr;    // [2][L][4]
-    const uint8_t *ins_nz;      // [2][L]
-    const uint8_t *ins_base;    // [2][L][4]
+    const uint8_t *ins_base;    // [2][L][4] inserted base per lane (the thresholds live in `ent`)
     const uint32_t *del_thr;    // [2][L][4]
     const uint8_t *del_nz;      // [2][L]
-    const uint16_t *nzpos;      // [2][L]
     const uint4 *ent;           // [n_grp][2]: {reject thresholds of the group's 4 sites: the insertion threshold, or the
                                 //             largest of a deletion site's 4}, {site: pos | valid << 16 | insertion lane << 17}
     const uint32_t *basic_thr;
@@ -243,7 +239,6 @@ struct GenParams {
     uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic;
     int32_t fixed_insert;
     int64_t frag_lo;
-    uint32_t n_nz[2];
     uint32_t n_grp;
     uint32_t grp_begin[5];
     uint64_t bin_thr[2][4];

@@ -197,12 +197,9 @@ int rebuild_views(iss_ctx *c) {
         c->mview.subst_n = b + h.subst_n_off;
         c->mview.subst_thr = reinterpret_cast<const uint64_t *>(b + h.subst_thr_off);
         c->mview.subst_alt = b + h.subst_alt_off;
-        c->mview.ins_thr = reinterpret_cast<const uint32_t *>(b + h.ins_thr_off);
-        c->mview.ins_nz = b + h.ins_nz_off;
         c->mview.ins_base = b + h.ins_base_off;
         c->mview.del_thr = reinterpret_cast<const uint32_t *>(b + h.del_thr_off);
         c->mview.del_nz = b + h.del_nz_off;
-        c->mview.nzpos = reinterpret_cast<const uint16_t *>(b + h.nzpos_off);
         c->mview.ent = reinterpret_cast<const uint4 *>(b + h.ent_off);
         c->mview.basic_thr = reinterpret_cast<const uint32_t *>(b + h.basic_thr_off);
         c->mview.basic_val = b + h.basic_val_off;
@@ -269,7 +266,6 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     const ModelHeader &h = c->mh;
     p.L = h.L; p.qual_mode = h.qual_mode; p.n_insert = h.n_insert; p.frag_mode = h.frag_mode; p.n_frag = h.n_frag;
     p.const_phred = h.const_phred; p.n_basic = h.n_basic; p.fixed_insert = h.fixed_insert; p.frag_lo = h.frag_lo;
-    p.n_nz[0] = h.n_nz[0]; p.n_nz[1] = h.n_nz[1];
     p.n_grp = h.n_grp;
     memcpy(p.grp_begin, h.grp_begin, sizeof p.grp_begin);
     memcpy(p.bin_thr, h.bin_thr, sizeof p.bin_thr);
@@ -428,10 +424,17 @@ int iss_ctx_create(int device, iss_ctx **out) {
     iss_ctx *c = new iss_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    CU(iss_kernel_configure(kMaxSmem));
-    CU(iss_gz_init_device());
-    CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+    const int rc = [&]() -> int {
+        CU(iss_kernel_configure(kMaxSmem));
+        CU(iss_gz_init_device());
+        CU(cudaMalloc(&c->d_counters, 4 * sizeof(unsigned long long)));
+        CU(cudaMemset(c->d_counters, 0, 4 * sizeof(unsigned long long)));
+        return ISS_OK;
+    }();
+    if (rc != ISS_OK) {
+        iss_ctx_destroy(c);
+        return rc;
+    }
     *out = c;
     return ISS_OK;
 }
@@ -545,16 +548,8 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
         return fail(ISS_E_ARG, "substitution / indel tables are required");
     if (m->qual_mode == ISS_QUAL_KDE && (!m->qual_thr || !m->bin_thr || !m->bin_valid)) return fail(ISS_E_ARG, "kde tables missing");
     if (m->n_insert && !m->insert_thr) return fail(ISS_E_ARG, "insert_thr missing");
-    // positions (< L-1: the indel loop runs over range(L-1)) with any non-zero threshold
-    std::vector<uint16_t> nzpos(2 * (size_t)L, 0);
-    for (int o = 0; o < 2; ++o) {
-        uint32_t cnt = 0;
-        for (uint32_t pos = 0; pos + 1 < L; ++pos)
-            if (m->ins_nz[o * L + pos] | m->del_nz[o * L + pos]) nzpos[o * L + cnt++] = (uint16_t)pos;
-        h.n_nz[o] = cnt;
-    }
     // RNG contract v2: the indel draw sites with a non-zero threshold, ranked in loop order per (orientation, kind);
-    // rank r reads word r & 3 of Philox block r >> 2.  Lists: insertion fwd, deletion fwd, insertion rev, deletion rev,
+    // rank r reads word r & 3 of Philox block r >> 2; only positions < L-1 count (the indel loop runs over range(L-1)).  Lists: insertion fwd, deletion fwd, insertion rev, deletion rev,
     // each padded to whole groups of 4 sites with sites that never fire (valid = 0).  A group carries what the scan
     // needs to reject it -- word > threshold for all 4 sites -- and the rare survivor is evaluated from the full tables.
     struct Grp { uint32_t thr[4]; uint32_t meta[4]; };
@@ -592,12 +587,9 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     h.subst_n_off = place(2ull * L * 4);
     h.subst_thr_off = place(2ull * L * 4 * ISS_MAX_ALT * 8);
     h.subst_alt_off = place(2ull * L * 4 * ISS_MAX_ALT);
-    h.ins_thr_off = place(2ull * L * 4 * 4);
-    h.ins_nz_off = place(2ull * L);
     h.ins_base_off = place(2ull * L * 4);
     h.del_thr_off = place(2ull * L * 4 * 4);
     h.del_nz_off = place(2ull * L);
-    h.nzpos_off = place(2ull * L * 2);
     h.basic_thr_off = place(4ull * m->n_basic);
     h.basic_val_off = place(1ull * m->n_basic + 1);
     h.ent_off = place(sizeof(Grp) * grps.size());
@@ -621,12 +613,9 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     put(h.subst_n_off, m->subst_n, 2ull * L * 4);
     put(h.subst_thr_off, m->subst_thr, 2ull * L * 4 * ISS_MAX_ALT * 8);
     put(h.subst_alt_off, m->subst_alt, 2ull * L * 4 * ISS_MAX_ALT);
-    put(h.ins_thr_off, m->ins_thr, 2ull * L * 4 * 4);
-    put(h.ins_nz_off, m->ins_nz, 2ull * L);
     put(h.ins_base_off, m->ins_base, 2ull * L * 4);
     put(h.del_thr_off, m->del_thr, 2ull * L * 4 * 4);
     put(h.del_nz_off, m->del_nz, 2ull * L);
-    put(h.nzpos_off, nzpos.data(), 2ull * L * 2);
     put(h.ent_off, grps.data(), sizeof(Grp) * grps.size());
     put(h.basic_thr_off, m->basic_thr, 4ull * m->n_basic);
     put(h.basic_val_off, m->basic_val, 1ull * m->n_basic + (m->basic_val ? 1 : 0));
@@ -994,18 +983,20 @@ int iss_ctx_gzip(iss_ctx *c, const uint8_t *in, uint64_t n, uint8_t *out, uint64
     uint8_t *d_in = nullptr, *d_out = nullptr;
     uint32_t *d_work = nullptr;
     uint64_t *d_status = nullptr;
-    CU(cudaMalloc(&d_in, n + 16));
-    CU(cudaMalloc(&d_out, (uint64_t)(nc + 1) * ISS_GZ_STRIDE));
-    CU(cudaMalloc(&d_work, ISS_GZ_WORK_WORDS * sizeof(uint32_t)));
-    CU(cudaMalloc(&d_status, (nc + 2) * sizeof(uint64_t)));
-    if (n) CU(cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
-    CU(iss_gz_compress(d_in, n, d_status, d_out, d_work, c->sm_count, 0));
     uint64_t total = 0;
-    CU(cudaMemcpy(&total, d_status + nc, sizeof total, cudaMemcpyDeviceToHost));
-    int rc = ISS_OK;
-    if (ISS_GZ_FAILED(total)) rc = fail(ISS_E_STATE, "internal: gzip member placement timed out");
-    else if (total > cap) rc = fail(ISS_E_ARG, "output buffer too small");
-    else if (total) CU(cudaMemcpy(out, d_out, total, cudaMemcpyDeviceToHost));
+    int rc = [&]() -> int {
+        CU(cudaMalloc(&d_in, n + 16));
+        CU(cudaMalloc(&d_out, (uint64_t)(nc + 1) * ISS_GZ_STRIDE));
+        CU(cudaMalloc(&d_work, ISS_GZ_WORK_WORDS * sizeof(uint32_t)));
+        CU(cudaMalloc(&d_status, (nc + 2) * sizeof(uint64_t)));
+        if (n) CU(cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
+        CU(iss_gz_compress(d_in, n, d_status, d_out, d_work, c->sm_count, 0));
+        CU(cudaMemcpy(&total, d_status + nc, sizeof total, cudaMemcpyDeviceToHost));
+        if (ISS_GZ_FAILED(total)) return fail(ISS_E_STATE, "internal: gzip member placement timed out");
+        if (total > cap) return fail(ISS_E_ARG, "output buffer too small");
+        if (total) CU(cudaMemcpy(out, d_out, total, cudaMemcpyDeviceToHost));
+        return ISS_OK;
+    }();
     *out_n = total;
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_work); cudaFree(d_status);
     return rc;

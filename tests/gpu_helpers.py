@@ -14,7 +14,7 @@ def product_model(case):
                                      case.get("fragment_sd"), bool(case.get("store_mutations")))
 
 
-def run_product(case, device=0, batch_pairs=0, engine=None, model=None, tma_gather=False):
+def run_product(case, device=0, batch_pairs=0, engine=None, model=None, tma_gather=False, compress=False):
     """Returns (R1 bytes, R2 bytes, stats) of one worker, reference worker_iterator semantics."""
     recs = fixtures.materialise_records(case)
     own = engine is None
@@ -26,7 +26,7 @@ def run_product(case, device=0, batch_pairs=0, engine=None, model=None, tma_gath
         items = eng_mod.worker_items(case["work"], case["cpu"], case["seed"], e.record_lengths, e.read_length)
         r1, r2, vcf = [], [], []
         for b in e.generate(items, sequence_type=case.get("sequence_type", "metagenomics"),
-                            gc_bias=bool(case.get("gc_bias")), batch_pairs=batch_pairs, tma_gather=tma_gather):
+                            gc_bias=bool(case.get("gc_bias")), batch_pairs=batch_pairs, tma_gather=tma_gather, compress=compress):
             r1.append(b.r1.tobytes())
             r2.append(b.r2.tobytes())
             if b.vcf is not None:
