@@ -192,6 +192,20 @@ def workload_config(n):
             "l2": "each step streams ~6.5 GB of FASTQ per GPU through L2 (126 MB); the 1.25 MB packed genome is L2-resident by design"}
 
 
+def philox_blocks_per_pair(model, L):
+    """Philox4x32-10 calls per pair under RNG contract v2, substitution-choice blocks excluded:
+    3 PAIR blocks + ceil(L/2) QUAL blocks per read + one block per group of 4 indel sites that can fire."""
+    arrays = model.device_tables().arrays
+    ins = np.asarray(arrays["ins_nz"]).reshape(2, L)
+    dele = np.asarray(arrays["del_nz"]).reshape(2, L)
+    groups = 0
+    for o in range(2):
+        n_ins = sum(bin(int(x) & 15).count("1") for x in ins[o, :L - 1])
+        n_del = int(np.count_nonzero(dele[o, :L - 1] & 15))
+        groups += (n_ins + 3) // 4 + (n_del + 3) // 4
+    return 3 + 2 * ((L + 1) // 2) + groups
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +237,7 @@ def main():
         model = error_models.KDErrorModel(os.path.join(error_models.PROFILE_DIR, MODEL_FILE)).truncate(READ_LEN)
         eng.set_genome([(GENOME_NAME, make_genome())])
         eng.set_model(model)
+        philox_blocks = philox_blocks_per_pair(model, READ_LEN)
     if world > 1:
         uid = parallel.share_from_root(dist, eng_mod.Engine.unique_id() if rank == 0 else None, rank)
         eng.comm_init_rank(world, rank, uid)
@@ -337,7 +352,8 @@ def main():
                          "traffic": traffic, "peak_source": peak_src, "kernel": "iss_generate_kernel",
                          "algorithmic_bytes_per_launch": algo_bytes / max(launches, 1),
                          "avg_launch_ms": k_ms / max(launches, 1),
-                         "note": "the kernel is integer-issue bound, not HBM bound (SURVEY.md 8d); see DESIGN.md section 6"},
+                         "note": "the kernel is integer-issue bound, not HBM bound (SURVEY.md 8d); see DESIGN.md section 6",
+                         "philox_blocks_per_pair": philox_blocks, "philox_blocks_per_s": philox_blocks * value},
             "clocks": clk,
             "host": {"numa_node_rank0": numa_node, "logical_cpus": os.cpu_count(), "usable_cpus": usable_cores()},
         }

@@ -191,3 +191,18 @@ def test_draft_and_coverage_paths_match_live_reference(tmp_path):
     y = rab.draft(list(ids), [str(draft1)], rab.lognormal, str(tmp_path / "o2"))
     assert set(x) == set(y) and all(abs(x[k] - y[k]) < 1e-15 for k in x)  # set() order inside draft() is not stable
     assert abundance.to_coverage(1000, 0.5, 126, 5000) == rab.to_coverage(1000, 0.5, 126, 5000)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) needs no GPU: one JSON line with the
+    contract's keys, the C port of the reference path as `cpu_baseline.kind == "port"`."""
+    out = subprocess.run([sys.executable, os.path.join(fixtures.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "150bp_read_pairs_per_sec" and d["unit"] == "pairs/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
