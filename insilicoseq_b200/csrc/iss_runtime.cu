@@ -274,7 +274,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.segs = s.d_segs;
     p.nseg = nseg;
     p.tile_pairs = c->tile_pairs;
-    p.tile_shift = c->tile_pairs == 64 ? 6u : 5u;
+    p.tile_shift = c->tile_pairs == 128 ? 7u : (c->tile_pairs == 64 ? 6u : 5u);
     p.split_shift = c->split_shift;
     p.total_pairs = pairs;
     p.key = batch_key;
@@ -752,10 +752,13 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     const uint64_t batch_pairs = std::min<uint64_t>(o.batch_pairs, total);
     // tile geometry: T pairs per CTA so that both stream images + bookkeeping fit in shared memory
     uint32_t T = 64;
+    if (const char *e = getenv("ISS_TILE")) {  // A/B switch for benchmarks: 128 pairs per tile (512-thread CTAs, 2 per SM)
+        if (atoi(e) == 128) T = 128;
+    }
     uint32_t img_cap = 0;
     size_t smem = 0;
     c->err_cap = 1024;
-    for (;; T -= 32) {
+    for (;; T >>= 1) {
         img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
         smem = iss_tile_smem_bytes(T, img_cap, c->err_cap);
         if (smem <= kMaxSmem) break;
