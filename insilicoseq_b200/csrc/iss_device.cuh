@@ -259,7 +259,7 @@ struct GenParams {
     uint32_t err_cap;         // entries of the substitution list
     uint32_t amplicon;
     uint32_t gc_bias;
-    uint32_t chunk_magic;     // ceil(2^32 / nchunk) for idx / nchunk
+    uint32_t chunk_magic;     // ceil(2^32 / nchunk) for idx / nchunk (unused when nchunk == 1: the value would be 2^32)
     uint32_t nchunk;          // ceil(L / 16)
     uint8_t *scratch;         // slow-path scratch: gridDim.x * ISS_SLOW_SLOTS * scratch_stride bytes
     uint32_t scratch_stride;  // >= 5L + 8

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         {
             const uint32_t nitems = 2u * T * p.nchunk;
             for (uint32_t idx = tid; idx < nitems; idx += blockDim.x) {
-                const uint32_t rd = __umulhi(idx, p.chunk_magic);
+                const uint32_t rd = p.nchunk == 1u ? idx : __umulhi(idx, p.chunk_magic);  // ceil(2^32 / 1) does not fit 32 bits
                 const uint32_t j = idx - rd * p.nchunk;
                 const uint32_t ro = rd >= T ? 1u : 0u, rp = rd - ro * T;
                 if (rp >= npairs) continue;

@@ -63,6 +63,25 @@ def write_stress_model(path, base_npz, seed, dense):
         np.savez_compressed(fh, **out)
 
 
+def write_full_model(path, base_npz, seed):
+    """Every position carries all four insertion lanes and a deletion probability for every base (small values, so reads
+    still differ): the indel site lists are as long as they can get -- 4 (L-1) insertion sites and L-1 deletion sites."""
+    d = np.load(base_npz, allow_pickle=True)
+    L = int(d["read_length"])
+    rng = np.random.RandomState(seed)
+    out = {k: d[k] for k in d.files}
+    for orient in ("forward", "reverse"):
+        ins = np.empty(L, dtype=object)
+        dele = np.empty(L, dtype=object)
+        for pos in range(L):
+            ins[pos] = {b: float(rng.rand() * 0.02) for b in "ATCG"}
+            dele[pos] = {b: float(rng.rand() * 0.05) for b in "ATCG"}
+        out["ins_" + orient] = ins
+        out["del_" + orient] = dele
+    with open(path, "wb") as fh:
+        np.savez_compressed(fh, **out)
+
+
 def sha(b):
     return hashlib.sha256(b).hexdigest()
 
@@ -74,6 +93,8 @@ def build_cases():
     write_stress_model(os.path.join(MODELS, "stress20.npz"), os.path.join(MODELS, "ecoli.npz"), 5, dense=0.5)
     write_stress_model(os.path.join(MODELS, "stress20_sparse.npz"), os.path.join(MODELS, "ecoli.npz"), 6, dense=0.12)
     oracle.truncate_profile(os.path.join(REF_PROFILES, "miSeq_0.npz"), os.path.join(MODELS, "miseq_150.npz"), 150)
+    write_full_model(os.path.join(MODELS, "full20.npz"), os.path.join(MODELS, "ecoli.npz"), 7)
+    oracle.truncate_profile(os.path.join(MODELS, "stress20.npz"), os.path.join(MODELS, "stress3.npz"), 3)
 
     cases = []
 
@@ -123,6 +144,13 @@ def build_cases():
                       records=[rec("my_genome", 1000, 133)], work=[[0, 60]], inline=True))
     cases.append(dict(name="perfect_mode", model="perfect", seed=9, cpu=0,
                       records=[rec("pg", 2500, 134)], work=[[0, 400]], inline=True))
+    cases.append(dict(name="full_indel_tables", model="models/full20.npz", seed=2718, cpu=5, store_mutations=True,
+                      records=[rec("f1", 700, 141), rec("f2", 64, 142)], work=[[0, 160], [1, 40]], inline=True))
+    cases.append(dict(name="read_length_3", model="models/stress3.npz", seed=31, cpu=0,
+                      records=[rec("r3", 300, 143, frac_lower=0.2, n_runs=2, iupac="RN")], work=[[0, 300]], inline=True))
+    cases.append(dict(name="long_names_cpu_digits", model="profile:NovaSeq", seed=4242, cpu=40950,
+                      records=[rec("NZ_" + "contig.with.a.long.name|" * 3 + "end", 2600, 144), rec("x", 1900, 145)],
+                      work=[[0, 33], [1, 70]], inline=True))
     return cases
 
 
