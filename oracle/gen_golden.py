@@ -95,6 +95,8 @@ def build_cases():
     oracle.truncate_profile(os.path.join(REF_PROFILES, "miSeq_0.npz"), os.path.join(MODELS, "miseq_150.npz"), 150)
     write_full_model(os.path.join(MODELS, "full20.npz"), os.path.join(MODELS, "ecoli.npz"), 7)
     oracle.truncate_profile(os.path.join(MODELS, "stress20.npz"), os.path.join(MODELS, "stress3.npz"), 3)
+    for n in (2, 16, 17):  # around the 16-base chunk of the gather and the smallest length the indel loop accepts
+        oracle.truncate_profile(os.path.join(MODELS, "stress20.npz"), os.path.join(MODELS, "stress%d.npz" % n), n)
 
     cases = []
 
@@ -148,6 +150,10 @@ def build_cases():
                       records=[rec("f1", 700, 141), rec("f2", 64, 142)], work=[[0, 160], [1, 40]], inline=True))
     cases.append(dict(name="read_length_3", model="models/stress3.npz", seed=31, cpu=0,
                       records=[rec("r3", 300, 143, frac_lower=0.2, n_runs=2, iupac="RN")], work=[[0, 300]], inline=True))
+    for n in (2, 16, 17):
+        cases.append(dict(name="read_length_%d" % n, model="models/stress%d.npz" % n, seed=100 + n, cpu=1, store_mutations=(n == 17),
+                          records=[rec("q%d" % n, 200 + n, 150 + n, frac_lower=0.1, n_runs=1, iupac="N"), rec("pure%d" % n, 90, 160 + n)],
+                          work=[[0, 90], [1, 70]], inline=True))
     cases.append(dict(name="long_names_cpu_digits", model="profile:NovaSeq", seed=4242, cpu=40950,
                       records=[rec("NZ_" + "contig.with.a.long.name|" * 3 + "end", 2600, 144), rec("x", 1900, 145)],
                       work=[[0, 33], [1, 70]], inline=True))
