@@ -23,30 +23,50 @@ class Record(object):
         return "Record(id=%r, len=%d)" % (self.id, len(self.seq))
 
 
+_WS = b" \t\n\r\x0b\x0c"  # what bytes.split() treats as white space
+
+
 def parse(handle):
-    """Yield Record objects from a path or an open text/binary handle."""
-    close = False
+    """Yield Record objects from a path or an open text/binary handle.
+
+    A path is memory-mapped and cut at line-initial '>' with `find`; a record's sequence is its body with white space
+    deleted by one `bytes.translate` (C speed), so a multi-gigabase FASTA is not walked line by line in Python."""
     if isinstance(handle, (str, bytes)) or hasattr(handle, "__fspath__"):
-        handle = open(handle, "rb")
-        close = True
-    try:
-        title = None
-        chunks = []
-        for line in handle:
-            if isinstance(line, str):
-                line = line.encode("ascii")
-            if line.startswith(b">"):
-                if title is not None:
-                    yield _make(title, chunks)
-                title = line[1:].rstrip()
-                chunks = []
-            elif title is not None:
-                chunks.append(b"".join(line.split()))
-        if title is not None:
-            yield _make(title, chunks)
-    finally:
-        if close:
-            handle.close()
+        import mmap
+
+        with open(handle, "rb") as fh:
+            try:
+                buf = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except ValueError:  # empty file
+                return
+            try:
+                for rec in _records(buf):
+                    yield rec
+            finally:
+                buf.close()
+        return
+    data = handle.read()
+    if isinstance(data, str):
+        data = data.encode("ascii")
+    for rec in _records(data):
+        yield rec
+
+
+def _records(buf):
+    n = len(buf)
+    if n == 0:
+        return
+    pos = 0 if buf[0:1] == b">" else buf.find(b"\n>") + 1  # text before the first title line is ignored
+    if pos == 0 and buf[0:1] != b">":
+        return
+    while pos < n:
+        nxt = buf.find(b"\n>", pos)
+        end = nxt + 1 if nxt >= 0 else n
+        eol = buf.find(b"\n", pos, end)
+        if eol < 0:
+            eol = end
+        yield _make(bytes(buf[pos + 1:eol]).rstrip(), [bytes(buf[eol + 1:end]).translate(None, _WS)])
+        pos = end
 
 
 def _make(title, chunks):

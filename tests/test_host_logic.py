@@ -206,3 +206,34 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_fasta_reader_matches_line_by_line_definition(tmp_path):
+    """fasta.parse cuts a memory-mapped file at line-initial '>' and strips white space with one translate per record; the
+    definition it must agree with is the line-by-line one (Bio.SeqIO: id = first token of the title, sequence = the
+    following lines without white space), on paths, binary handles and text handles."""
+    import random
+
+    def by_lines(data):
+        title, chunks, out = None, [], []
+        for line in io.BytesIO(data):
+            if line.startswith(b">"):
+                if title is not None:
+                    out.append((title, b"".join(chunks)))
+                title, chunks = line[1:].rstrip(), []
+            elif title is not None:
+                chunks.append(b"".join(line.split()))
+        if title is not None:
+            out.append((title, b"".join(chunks)))
+        return [((t.decode().split(None, 1) or [""])[0], t.decode(), s) for t, s in out]
+
+    rng = random.Random(5)
+    pieces = [b">", b"\n", b"\r\n", b"ACGT", b"acgtn", b" ", b"\t", b">id desc here", b"\n>", b"\n\n", b"N" * 7, b">x", b"AC>GT",
+              b"\x0b", b"\x0c", b"\r"]
+    path = tmp_path / "f.fa"
+    for _ in range(1500):
+        data = b"".join(rng.choice(pieces) for _ in range(rng.randint(0, 14)))
+        want = by_lines(data)
+        path.write_bytes(data)
+        for src in (str(path), io.BytesIO(data), io.StringIO(data.decode("ascii"))):
+            assert [(r.id, r.description, r.seq) for r in fasta.parse(src)] == want, data
