@@ -100,3 +100,35 @@ def test_live_reference_agrees_with_fixture():
     with tempfile.TemporaryDirectory() as tmp:
         r1, r2, vcf = gen_golden.run_reference(case, tmp)
     assert r1 == exp["R1"] and r2 == exp["R2"]
+
+
+@pytest.mark.reference
+@pytest.mark.parametrize("seed", range(8))
+def test_c_oracle_matches_live_reference_on_random_models(seed, tmp_path):
+    """Fuzz pin of the C restatement: random read length, random indel tables (sparse to full, p = 1.0 entries), random
+    genome with lower case / IUPAC runs and a record too short for the model; the UNMODIFIED reference under the shared
+    Philox stream and oracle/iss_oracle.c must write the same FASTQ and VCF bytes."""
+    import patched_reference as pr
+
+    if not pr.reference_available():
+        pytest.skip("reference not mounted")
+    import gen_golden
+
+    rng = np.random.RandomState(1000 + seed)
+    L = int(rng.randint(2, 21))
+    stress = str(tmp_path / "stress.npz")
+    gen_golden.write_stress_model(stress, fixtures.model_path("models/ecoli.npz"), 50 + seed, dense=float(rng.choice([0.05, 0.3, 0.7, 1.0])))
+    model = str(tmp_path / "m.npz")
+    oracle.truncate_profile(stress, model, L)
+    case = dict(name="fuzz%d" % seed, model=model, seed=int(rng.randint(0, 1 << 30)), cpu=int(rng.randint(0, 300)),
+                store_mutations=bool(seed & 1), gc_bias=bool(seed == 5), sequence_type="amplicon" if seed == 6 else "metagenomics",
+                records=[{"id": "fz%d" % seed, "synth_seed": 900 + seed, "length": int(rng.randint(max(3 * L + 5, 60), 600)),
+                          "sprinkle": {"frac_lower": 0.2, "n_runs": 2, "iupac": "RYSWN"}},
+                         {"id": "short", "synth_seed": 950 + seed, "length": max(1, L - 1)},
+                         {"id": "plain", "synth_seed": 970 + seed, "length": 4 * L + 11}],
+                work=[[0, 70], [1, 3], [2, 40]])
+    r1, r2, vcf = gen_golden.run_reference(case, str(tmp_path))
+    c1, c2, cv = gen_golden.run_c_oracle(case)
+    assert len(r1) > 0 and c1 == r1 and c2 == r2
+    if case["store_mutations"]:
+        assert cv == vcf
