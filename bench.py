@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step (default: the BASELINE workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="kernel A/B runs: only the device-resident leg")
     args = ap.parse_args()
     from insilicoseq_b200 import parallel
 
@@ -297,6 +298,14 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
 
+    if args.device_only:
+        if rank == 0:
+            print(json.dumps({"metric": "150bp_read_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                              "roofline": {"avg_launch_ms": k_ms / max(launches, 1), "achieved": achieved, "frac": achieved / peak},
+                              "partial": "device-only A/B run"}))
+        eng.close()
+        return
     # ---- end to end through the public API, host ring included ("e2e") -------------------------------------
     step_e2e()
     barrier()

@@ -10,7 +10,7 @@
 
 #define ISS_QROW 64
 #define ISS_MAX_ALT 4
-#define ISS_QBT_STRIDE 96  // words per quality row in the device search-tree layout (see iss_kernels.cu)
+#define ISS_Q16_MAX_GROUPS 8  // a 16-bit quality row = 8 splitters + up to 8 groups of 8 entries (see iss_kernels.cu)
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Slot schedule: DESIGN.md section 3 / oracle/philox.py.
@@ -116,8 +116,14 @@ struct ModelHeader {
     uint8_t bin_valid[2][4];
     uint32_t err_thr[ISS_QROW];
     // offsets (bytes from blob start)
-    uint64_t frag_thr_off, insert_thr_off, qual_thr_off, subst_n_off, subst_thr_off, subst_alt_off, ins_base_off,
+    uint64_t frag_thr_off, insert_thr_off, qual_exact_off, subst_n_off, subst_thr_off, subst_alt_off, ins_base_off,
         del_thr_off, del_nz_off, basic_thr_off, basic_val_off, ent_off;
+    // 16-bit quality rows (kernel phase 4): per orientation [L + 1 positions][q16_nb rows of the populated bins][q16_rs bytes]
+    uint64_t q16_off[2];
+    uint32_t q16_nb[2];       // populated quality bins of the orientation (rows per position)
+    uint32_t q16_rs;          // bytes per row: 16 * (1 + groups), rounded to an odd multiple of 16
+    uint32_t q16_groups;      // 8-entry groups per row: ceil((max live thresholds + 1) / 8)
+    uint8_t q16_cbin[2][4];   // bin -> row index among the populated bins
 };
 
 // pointer view built on each device from the blob base
@@ -125,7 +131,8 @@ struct DevModel {
     const ModelHeader *h;
     const uint64_t *frag_thr;
     const uint32_t *insert_thr;
-    const uint32_t *qual_thr;   // [2][4][L][ISS_QBT_STRIDE] search-tree rows
+    const uint32_t *qual_exact; // [2][4][L][ISS_QROW] sorted 32-bit thresholds (tie fallback of the 16-bit search)
+    const uint8_t *q16[2];      // 16-bit rows of orientation o, position-major (one bulk copy per 2 positions)
     const uint8_t *subst_n;     // [2][L][4]
     const uint64_t *subst_thr;  // [2][L][4][4]
     const uint8_t *subst_alt;   // [2][L][4][4]
@@ -193,18 +200,24 @@ struct Lay {
     uint32_t sWin;     // u64[2T] window start inside the record (fs / rs)
     uint32_t sSeg;     // u32[T]
     uint32_t sAtt;     // u32[T]
-    uint32_t sQrow;    // u32[2T] element offset of the read's quality rows
-    uint32_t sSeqOff;  // u32[2T] offset of the sequence line inside the stream image
-    uint32_t sEnc;     // u32[2T]
+    uint32_t sQrow;    // u32[2T] quality rows of the read: byte offset of its bin's row inside a position | bin << 16
+    uint32_t sRel;     // u32[T]  low 32 bits of (stream offset of the record + header length): the sequence line sits at
+                       //         image offset  (a0 - (uint32)g0) + sRel[pair]  in both stream images
+    uint32_t sEnc;     // u32[T]
     uint32_t sSlow;    // u32[2T]
     uint32_t sFlag;    // u32[2T] read already queued for the sequential indel replay
     uint32_t sErr;     // u32[err_cap]
     uint32_t sErrThr;  // u32[64]
-    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 3 bytes of the tile's last record
+    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 2 gather-mbarrier parity, 3 bytes of the tile's last record; +16: mbarrier of the TMA genome gather
+    uint32_t sQtot;    // u32[n_streams] blocks the stream's producer lane stages during the whole launch
+    uint32_t sBar;     // u64[n_streams][q_stages][2]: {full, empty} mbarriers of the quality-row pipeline
+    uint32_t sQst;     // [n_streams][q_stages][q_stage_cap] staged 16-bit quality rows (2 positions per stage)
     uint32_t total;    // bytes of dynamic shared memory
 };
 
-__host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uint32_t err_cap) {
+// n_streams = 2 * S position streams per tile (orientation x part); q_stages = ring depth per stream (power of two)
+__host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uint32_t err_cap, uint32_t n_streams, uint32_t q_stages,
+                                               uint32_t q_stage_cap) {
     Lay l;
     uint32_t q = 0;
     l.img[0] = q; q += img_cap;
@@ -217,13 +230,16 @@ __host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uin
     l.sSeg = q; q += 4u * T;
     l.sAtt = q; q += 4u * T;
     l.sQrow = q; q += 8u * T;
-    l.sSeqOff = q; q += 8u * T;
-    l.sEnc = q; q += 8u * T;
+    l.sRel = q; q += 4u * T;
+    l.sEnc = q; q += 4u * T;
     l.sSlow = q; q += 8u * T;
     l.sFlag = q; q += 8u * T;
     l.sErr = q; q += 4u * err_cap;
     l.sErrThr = q; q += 4u * ISS_QROW;
     l.sCtl = q; q += 32u;
+    l.sQtot = q; q += 4u * ((n_streams + 3u) & ~3u);
+    l.sBar = q; q += 16u * n_streams * q_stages;
+    l.sQst = q; q += n_streams * q_stages * q_stage_cap;
     l.total = q;
     return l;
 }
@@ -255,6 +271,14 @@ struct GenParams {
     Lay lay;
     uint8_t *out1;
     uint8_t *out2;
+    // quality-row pipeline (phase 4): every position stream (orientation x part) of a tile walks the same rows for every
+    // tile, so its producer lane keeps a ring of q_stages bulk copies (cp.async.bulk + mbarrier) q_dist blocks ahead
+    uint32_t q_stage_shift;   // log2(q_stages)
+    uint32_t q_dist;          // prefetch distance in blocks of 2 positions (1 .. q_stages - 1)
+    uint32_t q_stage_cap;     // bytes reserved per stage (>= q_stage_bytes[o], multiple of 16)
+    uint32_t q_stage_bytes[2];  // 2 * q16_nb[o] * q16_rs: the rows of one block of orientation o
+    uint32_t q_pos_stride[2];   // q16_nb[o] * q16_rs
+    uint32_t q_row_off[2][4];   // bin -> byte offset of its row inside a position (q16_cbin * q16_rs)
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)
     uint32_t err_cap;         // entries of the substitution list
     uint32_t amplicon;

@@ -53,28 +53,54 @@ __device__ __forceinline__ uint32_t pick(const uint4 &w, uint32_t j) {
 }
 __device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
 
-// Quality rows are stored as a 2-level 8-ary search tree (ISS_QBT_STRIDE = 96 words per row, 128 B aligned, built by
-// the runtime from the sorted 64-entry row r[]):
-//   words 0..7    splitters s_k = r[8k+7], k = 0..6, pad
-//   words 8..71   the eight 8-entry leaf groups, group g stored at physical slot (5 - g) & 7, so that the first
-//                 128-byte line holds the splitters and groups 5,4,3 (= phred 24..47): one line per draw for q >= 24
-// #{j < 64 : w > r[j]} = 8*cA + cB with cA = #{k : w > s_k}, cB = #{j < 7 : w > r[8cA + j]}; both counts are 3-step
-// binary searches in registers.  One dependent load stage.
-__device__ __forceinline__ uint32_t cnt7(uint32_t w, const uint4 &lo, const uint4 &hi) {
-    // sorted t0..t6 = lo.x lo.y lo.z lo.w hi.x hi.y hi.z
-    uint32_t c = (w > lo.w) ? 4u : 0u;
-    const uint32_t m1 = c ? hi.y : lo.y;
-    c += (w > m1) ? 2u : 0u;
-    const uint32_t m2 = (c & 4u) ? ((c & 2u) ? hi.z : hi.x) : ((c & 2u) ? lo.z : lo.x);
-    c += (w > m2) ? 1u : 0u;
+__device__ __forceinline__ uint64_t *u64p(uint32_t off) { return reinterpret_cast<uint64_t *>(iss_smem + off); }
+__device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cast<uint32_t *>(iss_smem + off); }
+__device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
+
+// Quality rows (kde.py:82-85: q = searchsorted(cdf_pos, u) = #{j : w > thr[j]}) are searched on the top 16 bits of the
+// draw.  A row is 8 splitters + G groups of 8 sorted u16 entries e[j] = thr[j] >> 16, two per 32-bit word:
+//   bytes  0..15   splitters s_k = e[8k + 7], k = 0..6, then 0xFFFF
+//   bytes 16..     group g = e[8g .. 8g + 7]
+// #{j : w16 > e[j]} = 8 cA + cB with cA = #{k : w16 > s_k} and cB = #{j < 7 : w16 > e[8 cA + j]}: two 16-byte shared
+// memory loads (the rows of the block were staged by cp.async.bulk, see phase 4) and two 3-step searches in
+// registers.  With w16 != e[j] the 16-bit order is the 32-bit order; the entry the search stops at, t = e[8 cA + cB], is
+// the only place a tie can start (the row is sorted), so t == w16 sends the draw to the exact 32-bit row.
+__device__ __forceinline__ uint4 lds128(uint32_t off) { return *reinterpret_cast<const uint4 *>(iss_smem + off); }
+
+// v = 8 sorted u16 (t0 = low half of v.x ... t7 = high half of v.w), kh = w16 << 16.
+// Returns c = #{j < 7 : w16 > t_j} and cand = t_c.  A high half compares as a whole register: kh > (t_hi << 16 | t_lo)
+// <=> w16 > t_hi, exactly.
+__device__ __forceinline__ uint32_t cnt8x16(uint32_t kh, uint32_t w16, const uint4 &v, uint32_t &cand) {
+    const bool p1 = kh > v.y;                              // t3
+    const uint32_t m = p1 ? v.z : v.x, mo = p1 ? v.w : v.y;
+    const bool p2 = kh > m;                                // t5 or t1
+    const uint32_t lr = p2 ? mo : m;                       // the word holding t_c (low) and t_{c+1} (high), c = 4 p1 + 2 p2
+    const uint32_t lo = lr & 0xFFFFu;
+    const bool p3 = w16 > lo;
+    cand = p3 ? (lr >> 16) : lo;
+    return (p1 ? 4u : 0u) + (p2 ? 2u : 0u) + (p3 ? 1u : 0u);
+}
+// exact count for a draw whose top 16 bits equal an entry's: entries below c16 are smaller for sure
+__device__ __noinline__ uint32_t qual_exact_count(const uint32_t *__restrict__ row, uint32_t w, uint32_t c16) {
+    uint32_t c = c16;
+    while (c < ISS_QROW && w > __ldg(row + c)) ++c;
     return c;
 }
-__device__ __forceinline__ uint32_t qbt_search(const uint32_t *__restrict__ row, uint32_t w) {
-    const uint4 *r4 = reinterpret_cast<const uint4 *>(row);
-    const uint32_t cA = cnt7(w, __ldg(r4), __ldg(r4 + 1));
-    const uint32_t slot = (5u - cA) & 7u;
-    const uint32_t cB = cnt7(w, __ldg(r4 + 2 + 2u * slot), __ldg(r4 + 3 + 2u * slot));
-    return 8u * cA + cB;
+// row_off: offset of the read's staged row from iss_smem.  A tie (~ 41 / 65536 of the draws) goes to the 64 sorted
+// 32-bit thresholds of the same row (orientation o, the read's bin, position pos), located only then.
+__device__ __noinline__ uint32_t qual_tie(const GenParams &p, uint32_t rd, uint32_t pos, uint32_t w, uint32_t c16) {
+    const uint32_t o = rd >= p.tile_pairs ? 1u : 0u;
+    const uint32_t bin = u32p(p.lay.sQrow)[rd] >> 16;
+    return qual_exact_count(p.m.qual_exact + (((size_t)(o * 4u + bin) * p.L + pos) << 6), w, c16);
+}
+__device__ __forceinline__ uint32_t q16_search(const GenParams &p, uint32_t row_off, uint32_t w, uint32_t rd, uint32_t pos) {
+    const uint32_t w16 = w >> 16, kh = w & 0xFFFF0000u;
+    uint32_t cand;
+    const uint32_t cA = cnt8x16(kh, w16, lds128(row_off), cand);
+    const uint32_t cB = cnt8x16(kh, w16, lds128(row_off + 16u + 16u * cA), cand);
+    uint32_t q = 8u * cA + cB;
+    if (cand == w16) q = qual_tie(p, rd, pos, w, q);
+    return q;
 }
 
 __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
@@ -85,9 +111,6 @@ __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t en
     return __ldg(g.ascii + abs_pos);
 }
 
-__device__ __forceinline__ uint64_t *u64p(uint32_t off) { return reinterpret_cast<uint64_t *>(iss_smem + off); }
-__device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cast<uint32_t *>(iss_smem + off); }
-__device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
 
 // bytes of dynamic shared memory for a launch (host mirror in iss_kernels.h: iss_tile_smem_bytes)
 
@@ -132,7 +155,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, ui
 // touches ([wabs - 15, wabs + L + 46) in bases), placed 16-byte aligned inside the record's (not yet written) quality line.
 __device__ __forceinline__ uint64_t stage_src_byte(uint64_t wabs) { return ((wabs - 16u) >> 2) & ~(uint64_t)15u; }
 __device__ __forceinline__ uint32_t stage_dst_off(uint32_t img_off, uint32_t seq_off, uint32_t L) {
-    return ((img_off + seq_off + L + 3u + 15u) & ~15u);  // absolute offset from iss_smem
+    return ((img_off + seq_off + L + 3u + 15u) & ~15u);  // offset from iss_smem
 }
 
 // ---- mutation events (--store_mutations, error_models/__init__.py:98-108,197-207,211-221) -------------------
@@ -153,10 +176,10 @@ __device__ __forceinline__ void emit_event(const GenParams &p, uint64_t gpair, u
 }
 
 // ---- substitution of one (read, position) ---------------------------------------------------------
-__device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rd, uint32_t pos) {
+__device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rel0, uint32_t rd, uint32_t pos) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
-    uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
+    uint8_t *seq = imgp(l, o) + rel0 + u32p(l.sRel)[pair];
     const uint32_t c = seq[pos];
     if (!is_acgt(c)) return;  // "RYWSMKHBVDN" are never substituted (__init__.py:94)
     const uint32_t code = base_code(c);
@@ -174,15 +197,17 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
     if (p.store_mutations) {
         // recorded only when the new base differs from the read BEFORE indels ("original", generator.py:155,186)
         const uint64_t wabs = u64p(l.sWabs)[rd];
-        const uint32_t enc = u32p(l.sEnc)[rd];
+        const uint32_t enc = u32p(l.sEnc)[pair];
         const uint32_t orig = o ? complement_ascii(genome_ascii(p.g, enc, wabs + (L - 1u - pos))) : genome_ascii(p.g, enc, wabs + pos);
         if (alt != orig) emit_event(p, gp0 + pair, o, 1u, pos, 0u, c, alt, 0u, (uint32_t)seq[L + 3u + pos] - 33u);
     }
     seq[pos] = (uint8_t)alt;
 }
 
-__device__ __noinline__ void apply_substitution_overflow(const GenParams &p, uint64_t gp0, uint32_t rd, uint32_t pos) {
-    apply_substitution(p, p.lay, gp0, rd, pos);  // substitution list full: rare, kept out of the hot loop's code
+__device__ __noinline__ void apply_substitution_overflow(const GenParams &p, uint32_t tile, uint32_t rd, uint32_t pos) {
+    // substitution list full: rare, kept out of the hot loop's code (and its live registers: the tile constants are rebuilt here)
+    const uint32_t g0lo = (uint32_t)u64p(p.lay.sOff)[0];
+    apply_substitution(p, p.lay, (uint64_t)tile * p.tile_pairs, (g0lo & 15u) - g0lo, rd, pos);
 }
 
 // ---- sequential replay of introduce_indels + adjust_seq_length for one read ---------------------------
@@ -191,11 +216,11 @@ __device__ __noinline__ void apply_substitution_overflow(const GenParams &p, uin
 //   insertion at index nucl+1  == push on the LIFO (a later lane lands in front of an earlier one)
 //   pop(nucl)                  == drop cur; the next element takes index nucl WITHOUT being examined
 //   IndexError at seq[nucl]    == the stream is exhausted: nothing further is drawn
-__device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rd, uint8_t *scratch,
+__device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rel0, uint32_t rd, uint8_t *scratch,
                               const uint8_t *mask /* shared: per position, bits 0-3 insertion lanes that fire, 4-7 deletion fires for base b */) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
-    uint8_t *seq = imgp(l, o) + u32p(l.sSeqOff)[rd];
+    uint8_t *seq = imgp(l, o) + rel0 + u32p(l.sRel)[pair];
     uint8_t *orig = scratch;
     uint8_t *stk = scratch + L;
     for (uint32_t k = 0; k < L; ++k) orig[k] = seq[k];
@@ -231,7 +256,7 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
         seq[outlen++] = (uint8_t)x;
     }
     if (outlen < L) {  // extension from the reference sequence (:141-155)
-        const uint32_t enc = u32p(l.sEnc)[rd];
+        const uint32_t enc = u32p(l.sEnc)[pair];
         const uint64_t win = u64p(l.sWin)[rd], reclen = u64p(l.sRecLen)[pair];
         const uint64_t rec_abs = u64p(l.sWabs)[rd] - win;  // absolute index of the record's first base
         uint32_t e = 0;
@@ -252,35 +277,81 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
 
 }  // namespace
 
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, int kQShift>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const Lay &l = p.lay;
     if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
-    const uint32_t mbar = smem_addr(iss_smem + l.sCtl + 16u);  // 8-byte mbarrier behind the control words
-    if (tid == 0 && p.tma_gather) mbar_init(mbar, 2u * T);      // every (pair, orientation) thread arrives once per tile
-    uint32_t tile_parity = 0;
-    const uint64_t ntiles = (p.total_pairs + T - 1) / T;
-    bool store_pending = false;
+    const uint32_t smem0 = smem_addr(iss_smem);
+    const uint32_t mbar = smem0 + l.sCtl + 16u;                 // 8-byte mbarrier behind the control words
+    if (tid == 0) {
+        u32p(l.sCtl)[2] = 0;
+        if (p.tma_gather) mbar_init(mbar, 2u * T);  // every (pair, orientation) thread arrives once per tile
+    }
+    const uint32_t ntiles = (uint32_t)((p.total_pairs + T - 1) / T);  // a batch is far below 2^32 tiles
     // roles: q4 = 0..2S-1 -> orientation o = q4 / S, position part = q4 % S; rd = index of the read in the tile
     const uint32_t q4 = tid >> p.tile_shift, pair = tid & (T - 1u);
     const uint32_t S = 1u << p.split_shift;
     const uint32_t o = q4 >> p.split_shift, half = q4 & (S - 1u), rd = o * T + pair;
 
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t gp0 = tile * T;
+    // ---- quality-row pipeline.  Thread (o, part) walks the Philox QUAL blocks [b_begin, b_end) of its reads, and so do
+    //      the other T - 1 threads of its position stream q4 -- for EVERY tile.  The rows a stream needs are therefore a
+    //      fixed cyclic sequence: block b -> the rows of positions 2b, 2b + 1 for the populated bins of orientation o,
+    //      contiguous in the model blob.  The stream's first lane keeps q_dist blocks in flight with cp.async.bulk into a
+    //      ring of q_stages shared-memory stages; `full` mbarriers carry the byte counts, `empty` ones (one arrival per
+    //      warp of the stream) hand a stage back.  `it` counts the stream's blocks since the kernel started.
+    const bool kde = p.qual_mode == ISS_QUAL_KDE_MODE;
+    const uint32_t nblk = (L + 1u) >> 1;
+    const uint32_t b_begin = (half * nblk) >> p.split_shift, b_end = ((half + 1u) * nblk) >> p.split_shift;
+    constexpr uint32_t K = 1u << kQShift;  // stages of the ring (p.q_stage_shift == kQShift)
+    const uint32_t bar0 = smem0 + l.sBar + q4 * (K << 4);        // {full, empty} x K of this stream
+    const uint32_t stage0 = l.sQst + q4 * (K * p.q_stage_cap);   // offset of the stream's ring from iss_smem
+    const uint32_t stage_bytes = p.q_stage_bytes[o];
+    uint32_t it = 0;
+    if (kde) {
+        if (tid == 0) {
+            const uint32_t nbar = (2u << p.split_shift) * K;
+            for (uint32_t k = 0; k < nbar; ++k) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + l.sBar + 16u * k), "r"(1u) : "memory");
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + l.sBar + 16u * k + 8u), "r"(T >> 5) : "memory");
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (pair == 0)  // the producer lane of the stream: blocks it will ever stage (kept in shared memory, next to its barriers)
+            u32p(l.sQtot)[q4] = blockIdx.x < ntiles ? ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * (b_end - b_begin) : 0u;
+        __syncthreads();
+    }
+    // stage fill number f (block (f mod n) of the stream's cycle) -> ring stage f mod K, use f / K of that stage
+    auto q_issue = [&](uint32_t f, uint32_t blk) {
+        const uint32_t stg = f & (K - 1u), use = f >> kQShift;
+        const uint32_t fb = bar0 + (stg << 4);
+        if (use) mbar_wait(fb + 8u, (use - 1u) & 1u);  // every warp of the stream is done with the previous use
+        mbar_arrive_expect_tx(fb, stage_bytes);
+        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * stage_bytes, stage_bytes, fb);
+    };
+    if (kde && pair == 0) {
+        const uint32_t it_total = u32p(l.sQtot)[q4];
+        uint32_t blk = b_begin;
+        for (uint32_t f = 0; f < p.q_dist && f < it_total; ++f) {
+            q_issue(f, blk);
+            if (++blk == b_end) blk = b_begin;
+        }
+    }
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t gp0 = (uint64_t)tile * T;
         const uint32_t npairs = (uint32_t)((p.total_pairs - gp0 < (uint64_t)T) ? (p.total_pairs - gp0) : (uint64_t)T);
         const bool valid = pair < npairs;
 
-        // ---- phase 0: the previous tile's bulk stores must have finished READING shared memory
+        // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97).  Nothing here touches the stream
+        //      images, which the previous tile's copy-out may still be reading; its bulk stores are waited for by thread 0
+        //      before the barrier that ends the phase.
         if (tid == 0) {
-            if (store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // returns at once when nothing is pending
             u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0;
+            u32p(l.sCtl)[2] ^= 1u;  // phase parity of the gather mbarrier for this tile (1, 0, 1, ... ; read as parity ^ 1)
         }
         if (tid < 2u * T) u32p(l.sFlag)[tid] = 0;
-        __syncthreads();
-
-        // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97)
         if (tid < npairs) {
             const uint64_t gp = gp0 + tid;
             uint32_t lo = 0, hi = p.nseg;
@@ -339,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             }
             if (rs < 0 || fe > len) { atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_RANGE); rs = 0; if (fe > len) fs = 0; }
             uint32_t binf = 0, binr = 0;
-            if (p.qual_mode == ISS_QUAL_KDE_MODE) {  // np.random.choice(range(4), p=norm_mean)
+            if (kde) {  // np.random.choice(range(4), p=norm_mean)
                 for (int j = 0; j < 4; ++j) {
                     binf += ((uint64_t)b0.y >= p.bin_thr[0][j]) ? 1u : 0u;
                     binr += ((uint64_t)b0.z >= p.bin_thr[1][j]) ? 1u : 0u;
@@ -348,8 +419,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 if (binr == 4) binr = 3;
                 if (!p.bin_valid[0][binf] || !p.bin_valid[1][binr]) atomicOr(p.counters + 2, (unsigned long long)ISS_DEVERR_QUALBIN);
             }
-            u32p(l.sQrow)[tid] = (binf * L) * ISS_QBT_STRIDE;
-            u32p(l.sQrow)[T + tid] = ((4u + binr) * L) * ISS_QBT_STRIDE;
+            u32p(l.sQrow)[tid] = p.q_row_off[0][binf] | (binf << 16);
+            u32p(l.sQrow)[T + tid] = p.q_row_off[1][binr] | (binr << 16);
             u64p(l.sP)[tid] = P;
             u32p(l.sSeg)[tid] = lo;
             u32p(l.sAtt)[tid] = att;
@@ -359,20 +430,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             u64p(l.sWabs)[tid] = rec->data_off + (uint64_t)fs;
             u64p(l.sWabs)[T + tid] = rec->data_off + (uint64_t)rs;
             u32p(l.sEnc)[tid] = rec->enc;
-            u32p(l.sEnc)[T + tid] = rec->enc;
             const uint64_t off = sg->out_base + iss_cf(i, sg->fixed_len);
+            const uint32_t nd = iss_digits(i);
             u64p(l.sOff)[tid] = off;
-            if (tid == npairs - 1) u32p(l.sCtl)[3] = sg->fixed_len + iss_digits(i);  // bytes of the last record
+            u32p(l.sRel)[tid] = (uint32_t)off + rec->name_len + nd + sg->cpu_digits + 6u;  // "@" name "_" i "_" cpu "/1\n"
+            if (tid == npairs - 1) u32p(l.sCtl)[3] = sg->fixed_len + nd;  // bytes of the last record
         }
         __syncthreads();
-        const uint64_t g0 = u64p(l.sOff)[0];
-        const uint32_t a0 = (uint32_t)(g0 & 15u);
-        const uint32_t tile_bytes = (uint32_t)(u64p(l.sOff)[npairs - 1] - g0) + u32p(l.sCtl)[3];
+        // image offset of a byte = rel0 + low 32 bits of its stream offset; the tile's first record starts at a0 = g0 & 15
+        const uint32_t rel0 = ((uint32_t)u64p(l.sOff)[0] & 15u) - (uint32_t)u64p(l.sOff)[0];
 
         // ---- phase 2a: record skeleton, one thread per read:  "@{name}_{i}_{cpu}/{1|2}\n" ... "\n+\n" ... "\n"
         if (valid && half == 0) {
             const DevSegment *sg = p.segs + u32p(l.sSeg)[pair];
-            uint8_t *img = imgp(l, o) + a0 + (uint32_t)(u64p(l.sOff)[pair] - g0);
+            uint8_t *img = imgp(l, o) + rel0 + (uint32_t)u64p(l.sOff)[pair];
             const uint64_t i = u64p(l.sP)[pair] - sg->item_base;
             const DevRecord *rec = p.g.recs + sg->rec;
             uint32_t w = 0;
@@ -396,8 +467,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             img[w++] = '/';
             img[w++] = (uint8_t)('1' + o);
             img[w++] = '\n';
-            const uint32_t seq_off = (uint32_t)(img - imgp(l, o)) + w;
-            u32p(l.sSeqOff)[rd] = seq_off;
             img[w + L] = '\n';
             img[w + L + 1] = '+';
             img[w + L + 2] = '\n';
@@ -406,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 if (rec->enc == ISS_ENC_2BIT) {  // TMA: packed window -> the record's quality line (overwritten in phase 4)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_arrive_expect_tx(mbar, p.stage_bytes);
-                    bulk_load(smem_addr(iss_smem + stage_dst_off(l.img[o], seq_off, L)),
+                    bulk_load(smem0 + stage_dst_off(l.img[o], rel0 + u32p(l.sRel)[pair], L),
                               reinterpret_cast<const uint8_t *>(p.g.packed) + stage_src_byte(u64p(l.sWabs)[rd]), p.stage_bytes, mbar);
                 } else {
                     mbar_arrive(mbar);
@@ -415,30 +484,31 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         } else if (p.tma_gather && half == 0) {
             mbar_arrive(mbar);  // lanes of a partial tile keep the arrival count constant
         }
-        __syncthreads();
-        if (p.tma_gather) { mbar_wait(mbar, tile_parity); tile_parity ^= 1u; }
+        if (p.tma_gather) mbar_wait(mbar, u32p(l.sCtl)[2] ^ 1u);
 
-        // ---- phase 2b: gather the windows, flattened over (read, 16-base chunk)
+        // ---- phase 2b: gather the windows, flattened over (read, 16-base chunk).  The sequence lines are disjoint from
+        //      the skeleton bytes, so no barrier separates the two.
         {
             const uint32_t nitems = 2u * T * p.nchunk;
             for (uint32_t idx = tid; idx < nitems; idx += blockDim.x) {
-                const uint32_t rd = p.nchunk == 1u ? idx : __umulhi(idx, p.chunk_magic);  // ceil(2^32 / 1) does not fit 32 bits
-                const uint32_t j = idx - rd * p.nchunk;
-                const uint32_t ro = rd >= T ? 1u : 0u, rp = rd - ro * T;
+                const uint32_t grd = p.nchunk == 1u ? idx : __umulhi(idx, p.chunk_magic);  // ceil(2^32 / 1) does not fit 32 bits
+                const uint32_t j = idx - grd * p.nchunk;
+                const uint32_t ro = grd >= T ? 1u : 0u, rp = grd - ro * T;
                 if (rp >= npairs) continue;
-                uint8_t *seq = imgp(l, ro) + u32p(l.sSeqOff)[rd];
-                const uint64_t wabs = u64p(l.sWabs)[rd];
-                if (u32p(l.sEnc)[rd] == ISS_ENC_2BIT) {
+                const uint32_t so = rel0 + u32p(l.sRel)[rp];
+                uint8_t *seq = imgp(l, ro) + so;
+                const uint64_t wabs = u64p(l.sWabs)[grd];
+                if (u32p(l.sEnc)[rp] == ISS_ENC_2BIT) {
                     const uint64_t q = ro ? (wabs + L - 16u * j - 16u) : (wabs + 16u * j);
                     const uint32_t sh = ((uint32_t)q & 15u) * 2u;
                     uint32_t w0, w1;
                     if (p.tma_gather) {  // words of the span staged by TMA in the record's quality line
-                        const uint32_t *st = u32p(stage_dst_off(l.img[ro], u32p(l.sSeqOff)[rd], L));
+                        const uint32_t *st = u32p(stage_dst_off(l.img[ro], so, L));
                         const uint32_t wi = (uint32_t)((q >> 4) - (stage_src_byte(wabs) >> 2));
                         w0 = st[wi];
                         w1 = st[wi + 1];
                     } else {
-                        const uint32_t wi = (uint32_t)(q >> 4);
+                        const uint64_t wi = q >> 4;  // 64-bit word index: packed genomes beyond 2^36 bases stay addressable
                         w0 = __ldg(p.g.packed + wi);
                         w1 = __ldg(p.g.packed + wi + 1);
                     }
@@ -468,7 +538,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         const uint64_t P = valid ? u64p(l.sP)[pair] : 0;
         const uint32_t Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
         const uint32_t att8 = valid ? (u32p(l.sAtt)[pair] << 8) : 0;
-        uint8_t *seq = imgp(l, o) + (valid ? u32p(l.sSeqOff)[rd] : 0);
+        const uint32_t seq_off = rel0 + (valid ? u32p(l.sRel)[pair] : 0);
+        uint8_t *seq = imgp(l, o) + seq_off;
         if (valid && p.n_grp) {
             const uint32_t g_begin = (q4 * p.n_grp) >> (p.split_shift + 1u), g_end = ((q4 + 1u) * p.n_grp) >> (p.split_shift + 1u);
             uint32_t fired = 0;  // bit so set when read orientation so has an event
@@ -478,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
                 const Philox4 w = philox4x32_10_rk(g - p.grp_begin[li], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
                 if ((w.x <= t.x) | (w.y <= t.y) | (w.z <= t.z) | (w.w <= t.w)) {  // rare: some site may fire
-                    const uint8_t *sq = imgp(l, so) + u32p(l.sSeqOff)[so * T + pair];
+                    const uint8_t *sq = imgp(l, so) + seq_off;
 #pragma unroll 1
                     for (uint32_t r = 0; r < 4; ++r) {
                         const uint32_t meta = pick(mt, r);
@@ -533,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                     }
                     __syncthreads();
                     if (tid < nround)
-                        replay_indels(p, l, gp0, u32p(l.sSlow)[base + tid],
+                        replay_indels(p, l, gp0, rel0, u32p(l.sSlow)[base + tid],
                                       p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride, masks + tid * L);
                     __syncthreads();
                 }
@@ -542,33 +613,43 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         }
 
         // ---- phase 4: phred scores + substitution tests.  Thread (o, part) walks its part of the read's Philox QUAL
-        //      blocks; the 32 lanes of a warp are 32 pairs at the same position, so they share <= 3 quality rows.
-        if (valid) {
+        //      blocks; the 32 lanes of a warp are 32 pairs at the same position, reading <= 4 staged quality rows.
+        {
             uint8_t *qual = seq + L + 3;
             const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
-            const uint32_t nblk = (L + 1u) >> 1;
-            const uint32_t b_begin = (half * nblk) >> p.split_shift, b_end = ((half + 1u) * nblk) >> p.split_shift;
-            if (p.qual_mode == ISS_QUAL_KDE_MODE) {
-                const uint32_t *rows = p.m.qual_thr + u32p(l.sQrow)[rd];
-                for (uint32_t b = b_begin; b < b_end; ++b) {
-                    const uint32_t pos = 2u * b;
-                    const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
-                    const uint32_t q0 = qbt_search(rows + (size_t)pos * ISS_QBT_STRIDE, w.x);
-                    qual[pos] = (uint8_t)(q0 + 33u);
-                    if (w.y > u32p(l.sErrThr)[q0]) {
-                        const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                        if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, gp0, rd, pos);
+            if (kde) {
+                const uint32_t row0 = stage0 + (valid ? (u32p(l.sQrow)[rd] & 0xFFFFu) : 0u);  // the read's row in stage 0, position 0
+                for (uint32_t b = b_begin; b < b_end; ++b, ++it) {
+                    if (pair == 0 && it + p.q_dist < u32p(l.sQtot)[q4]) {  // producer lane: keep the ring q_dist blocks ahead
+                        uint32_t blk = b + p.q_dist;
+                        while (blk >= b_end) blk -= b_end - b_begin;
+                        q_issue(it + p.q_dist, blk);
                     }
-                    if (pos + 1u < L) {
-                        const uint32_t q1 = qbt_search(rows + (size_t)(pos + 1u) * ISS_QBT_STRIDE, w.z);
-                        qual[pos + 1u] = (uint8_t)(q1 + 33u);
-                        if (w.w > u32p(l.sErrThr)[q1]) {
+                    const uint32_t stg = it & (K - 1u);
+                    mbar_wait(bar0 + (stg << 4), (it >> kQShift) & 1u);
+                    if (valid) {
+                        const uint32_t pos = 2u * b;
+                        const uint32_t r0 = row0 + stg * p.q_stage_cap;
+                        const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
+                        const uint32_t q0 = q16_search(p, r0, w.x, rd, pos);
+                        qual[pos] = (uint8_t)(q0 + 33u);
+                        if (w.y > u32p(l.sErrThr)[q0]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution_overflow(p, gp0, rd, pos + 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, tile, rd, pos);
+                        }
+                        if (pos + 1u < L) {
+                            const uint32_t q1 = q16_search(p, r0 + p.q_pos_stride[o], w.z, rd, pos + 1u);
+                            qual[pos + 1u] = (uint8_t)(q1 + 33u);
+                            if (w.w > u32p(l.sErrThr)[q1]) {
+                                const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution_overflow(p, tile, rd, pos + 1u);
+                            }
                         }
                     }
+                    __syncwarp();
+                    if ((tid & 31u) == 0) mbar_arrive(bar0 + (stg << 4) + 8u);  // this warp is done with the stage
                 }
-            } else {
+            } else if (valid) {
                 for (uint32_t b = b_begin; b < b_end; ++b) {
                     const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
 #pragma unroll
@@ -586,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         qual[pos] = (uint8_t)(q + 33u);
                         if (wt > u32p(l.sErrThr)[q]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, gp0, rd, pos);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, tile, rd, pos);
                         }
                     }
                 }
@@ -600,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             const uint32_t nerr = nerr_all < p.err_cap ? nerr_all : p.err_cap;
             for (uint32_t e = tid; e < nerr; e += blockDim.x) {
                 const uint32_t v = u32p(l.sErr)[e];
-                apply_substitution(p, l, gp0, v >> 16, v & 0xFFFFu);
+                apply_substitution(p, l, gp0, rel0, v >> 16, v & 0xFFFFu);
             }
             if (tid == 0 && nerr_all) atomicAdd(p.counters + 1, (unsigned long long)nerr_all);
         }
@@ -611,6 +692,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         // ---- phase 6: copy-out.  [g0, g0 + tile_bytes) of each stream; the 16 B aligned middle goes through the
         //      bulk-copy engine, the ragged head/tail (< 16 B each) through plain byte stores.
         {
+            const uint64_t g0 = u64p(l.sOff)[0];
+            const uint32_t a0 = (uint32_t)(g0 & 15u);
+            const uint32_t tile_bytes = (uint32_t)(u64p(l.sOff)[npairs - 1] - g0) + u32p(l.sCtl)[3];
             uint32_t head = (16u - a0) & 15u;
             if (head > tile_bytes) head = tile_bytes;
             const uint32_t mid = (tile_bytes - head) & ~15u;
@@ -631,7 +715,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                              "r"(smem_addr(imgp(l, 1) + a0 + head)), "r"(mid)
                              : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                store_pending = true;
             }
 #else
             for (uint32_t idx = tid; idx < 2u * (mid >> 4); idx += blockDim.x) {
@@ -642,9 +725,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             }
 #endif
         }
-        // the next iteration's phase-0 barrier orders these reads before any new write to the images
+        // the next tile's phase-1 barrier orders these reads before any new write to the images
     }
-    if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {
@@ -653,31 +736,43 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 }
 
 // ---- host-visible launch helpers --------------------------------------------------------------------
-size_t iss_tile_smem_bytes(uint32_t T, uint32_t img_cap, uint32_t err_cap) { return iss_make_layout(T, img_cap, err_cap).total; }
+size_t iss_tile_smem_bytes(const Lay &l) { return l.total; }
+
+#define ISS_FOR_EACH_KERNEL(X) X(256, 4, 1) X(512, 2, 1) X(256, 4, 2) X(512, 2, 2)
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
-    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+#define X(T_, B_, Q_)                                                                                                        \
+    if (cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<T_, B_, Q_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); e != cudaSuccess) return e;
+    ISS_FOR_EACH_KERNEL(X)
+#undef X
+    return cudaSuccess;
 }
 
 cudaError_t iss_kernel_carveout(int percent) {  // shared-memory share of the SM's unified L1/shared array
-    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+#define X(T_, B_, Q_)                                                                                                        \
+    if (cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<T_, B_, Q_>, cudaFuncAttributePreferredSharedMemoryCarveout, percent); e != cudaSuccess) return e;
+    ISS_FOR_EACH_KERNEL(X)
+#undef X
+    return cudaSuccess;
 }
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
-    if (threads > 256) iss_generate_kernel<512, 2><<<grid, threads, smem, stream>>>(p);
-    else iss_generate_kernel<256, 4><<<grid, threads, smem, stream>>>(p);
+    const bool big = threads > 256, deep = p.q_stage_shift == 2;
+    if (big && deep) iss_generate_kernel<512, 2, 2><<<grid, threads, smem, stream>>>(p);
+    else if (big) iss_generate_kernel<512, 2, 1><<<grid, threads, smem, stream>>>(p);
+    else if (deep) iss_generate_kernel<256, 4, 2><<<grid, threads, smem, stream>>>(p);
+    else iss_generate_kernel<256, 4, 1><<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, size_t smem, int *blocks_per_sm) {
+cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_stage_shift, size_t smem, int *blocks_per_sm) {
     const int threads = (int)((2u << split_shift) * T);
-    if (threads > 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2>, threads, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4>, threads, smem);
+    const bool big = threads > 256, deep = q_stage_shift == 2;
+    if (big && deep) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2>, threads, smem);
+    if (big) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 1>, threads, smem);
+    if (deep) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 2>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 1>, threads, smem);
 }
 
 cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {

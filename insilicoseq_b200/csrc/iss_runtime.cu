@@ -109,7 +109,9 @@ struct iss_ctx {
     uint64_t cur_item = 0, cur_off = 0;  // planner cursor
     uint64_t batch_pairs = 0, slot_cap = 0, max_rec = 0;
     uint32_t n_slots = 0, max_segs = 0;
-    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 1024, grid = 0, split_shift = 1;
+    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 768, grid = 0, split_shift = 1;
+    uint32_t q_stage_shift = 1, q_dist = 1, q_stage_cap = 0;  // quality-row pipeline: ring depth 2^shift, prefetch distance, bytes per stage
+    Lay lay{};
     size_t smem = 0;
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
@@ -193,7 +195,9 @@ int rebuild_views(iss_ctx *c) {
         c->mview.h = reinterpret_cast<const ModelHeader *>(b);
         c->mview.frag_thr = reinterpret_cast<const uint64_t *>(b + h.frag_thr_off);
         c->mview.insert_thr = reinterpret_cast<const uint32_t *>(b + h.insert_thr_off);
-        c->mview.qual_thr = reinterpret_cast<const uint32_t *>(b + h.qual_thr_off);
+        c->mview.qual_exact = reinterpret_cast<const uint32_t *>(b + h.qual_exact_off);
+        c->mview.q16[0] = b + h.q16_off[0];
+        c->mview.q16[1] = b + h.q16_off[1];
         c->mview.subst_n = b + h.subst_n_off;
         c->mview.subst_thr = reinterpret_cast<const uint64_t *>(b + h.subst_thr_off);
         c->mview.subst_alt = b + h.subst_alt_off;
@@ -279,7 +283,15 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.total_pairs = pairs;
     p.key = batch_key;
     philox_round_keys(batch_key, p.rk);
-    p.lay = iss_make_layout(c->tile_pairs, c->img_cap, c->err_cap);
+    p.lay = c->lay;
+    p.q_stage_shift = c->q_stage_shift;
+    p.q_dist = c->q_dist;
+    p.q_stage_cap = c->q_stage_cap;
+    for (uint32_t o = 0; o < 2; ++o) {
+        p.q_pos_stride[o] = h.q16_nb[o] * h.q16_rs;
+        p.q_stage_bytes[o] = 2u * p.q_pos_stride[o];
+        for (uint32_t b = 0; b < 4; ++b) p.q_row_off[o][b] = h.q16_cbin[o][b] * h.q16_rs;
+    }
     p.out1 = s.d_out[0];
     p.out2 = s.d_out[1];
     p.img_cap = c->img_cap;
@@ -290,7 +302,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.chunk_magic = (uint32_t)((0x100000000ull + p.nchunk - 1) / p.nchunk);
     p.scratch = s.d_scratch;
     p.scratch_stride = (uint32_t)align_up(5ull * L + 8, 16);
-    p.slow_slots = std::max<uint32_t>(1u, std::min<uint32_t>(ISS_SLOW_SLOTS, 4u * c->err_cap / L));
+    p.slow_slots = std::max<uint32_t>(1u, std::min<uint32_t>(ISS_SLOW_SLOTS, 4u * c->err_cap / L));  // L > 4 * err_cap is refused at submit
     p.gc_thr = 3865470567u;  // ceil(0.90 * 2^32): u < 0.90  <=>  w < gc_thr   (generator.py:88)
     p.counters = c->d_counters;
     p.store_mutations = c->mh.store_mutations;
@@ -580,10 +592,42 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     h.grp_begin[4] = h.n_grp = (uint32_t)grps.size();
     uint64_t off = align_up(sizeof(ModelHeader), 16);
     auto place = [&](uint64_t bytes) { uint64_t at = off; off = align_up(off + std::max<uint64_t>(bytes, 16), 16); return at; };
-    const uint64_t qual_bytes = m->qual_mode == ISS_QUAL_KDE ? (2ull * 4 * L + 1) * ISS_QBT_STRIDE * 4 : 0;
+    // 16-bit quality rows (layout: iss_kernels.cu).  Only populated bins get rows; G groups of 8 cover the live
+    // thresholds of every row plus one pad entry, so the last splitter of a row is always 0xFFFF.
+    const bool kde = m->qual_mode == ISS_QUAL_KDE;
+    uint32_t q_groups = 1;
+    if (kde) {
+        uint32_t max_live = 0;
+        for (uint32_t o = 0; o < 2; ++o)
+            for (uint32_t b = 0; b < 4; ++b) {
+                if (!m->bin_valid[o * 4 + b]) continue;
+                for (uint64_t pos = 0; pos < L; ++pos) {
+                    const uint32_t *src = m->qual_thr + ((uint64_t)(o * 4 + b) * L + pos) * ISS_QROW;
+                    uint32_t live = 0;
+                    for (int j = 0; j < ISS_QROW; ++j) {
+                        if (j && src[j] < src[j - 1]) return fail(ISS_E_ARG, "qual_thr rows must be sorted");
+                        if (src[j] != 0xFFFFFFFFu) live = (uint32_t)j + 1;
+                    }
+                    max_live = std::max(max_live, live);
+                }
+            }
+        if (max_live >= ISS_QROW) return fail(ISS_E_ARG, "qual_thr rows need at least one 0xFFFFFFFF pad entry");
+        q_groups = (max_live + 1 + 7) / 8;
+        for (uint32_t o = 0; o < 2; ++o) {
+            uint32_t nb = 0;
+            for (uint32_t b = 0; b < 4; ++b) {
+                h.q16_cbin[o][b] = (uint8_t)nb;
+                if (m->bin_valid[o * 4 + b]) ++nb;
+            }
+            h.q16_nb[o] = std::max(nb, 1u);
+        }
+    }
+    h.q16_groups = q_groups;
+    h.q16_rs = 16u * ((1u + q_groups) | 1u);  // an odd number of 16-byte units: the rows of a position start in different banks
     h.frag_thr_off = place(8ull * m->n_frag);
     h.insert_thr_off = place(4ull * m->n_insert);
-    h.qual_thr_off = place(qual_bytes);
+    h.qual_exact_off = place(kde ? 2ull * 4 * L * ISS_QROW * 4 : 0);
+    for (uint32_t o = 0; o < 2; ++o) h.q16_off[o] = place(kde ? (uint64_t)(L + 1) * h.q16_nb[o] * h.q16_rs : 0);
     h.subst_n_off = place(2ull * L * 4);
     h.subst_thr_off = place(2ull * L * 4 * ISS_MAX_ALT * 8);
     h.subst_alt_off = place(2ull * L * 4 * ISS_MAX_ALT);
@@ -599,15 +643,21 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     auto put = [&](uint64_t at, const void *src, uint64_t bytes) { if (src && bytes) memcpy(blob.data() + at, src, bytes); };
     put(h.frag_thr_off, m->frag_thr, 8ull * m->n_frag);
     put(h.insert_thr_off, m->insert_thr, 4ull * m->n_insert);
-    if (qual_bytes) {  // [2][4][L][64] sorted rows -> 2-level 8-ary search-tree rows (layout: iss_kernels.cu)
-        uint32_t *dst = reinterpret_cast<uint32_t *>(blob.data() + h.qual_thr_off);
-        for (uint64_t row = 0; row < 8ull * L + 1; ++row) {  // +1: an all-pad row so that row L of the last table may be prefetched
-            uint32_t *t = dst + row * ISS_QBT_STRIDE;
-            for (int j = 0; j < ISS_QBT_STRIDE; ++j) t[j] = 0xFFFFFFFFu;
-            if (row == 8ull * L) break;
-            const uint32_t *src = m->qual_thr + row * ISS_QROW;
-            for (int k = 0; k < 7; ++k) t[k] = src[8 * k + 7];
-            for (int g = 0; g < 8; ++g) memcpy(t + 8 + 8 * ((5 - g) & 7), src + 8 * g, 32);
+    if (kde) {
+        put(h.qual_exact_off, m->qual_thr, 2ull * 4 * L * ISS_QROW * 4);
+        for (uint32_t o = 0; o < 2; ++o) {
+            uint8_t *base = blob.data() + h.q16_off[o];
+            memset(base, 0xFF, (size_t)(L + 1) * h.q16_nb[o] * h.q16_rs);  // pad rows / the pad position behind an odd L never count
+            for (uint32_t b = 0; b < 4; ++b) {
+                if (!m->bin_valid[o * 4 + b]) continue;
+                for (uint64_t pos = 0; pos < L; ++pos) {
+                    const uint32_t *src = m->qual_thr + ((uint64_t)(o * 4 + b) * L + pos) * ISS_QROW;
+                    uint16_t *row = reinterpret_cast<uint16_t *>(base + (pos * h.q16_nb[o] + h.q16_cbin[o][b]) * h.q16_rs);
+                    for (uint32_t k = 0; k < 7; ++k) row[k] = k < q_groups ? (uint16_t)(src[8 * k + 7] >> 16) : (uint16_t)0xFFFFu;
+                    row[7] = 0xFFFFu;
+                    for (uint32_t j = 0; j < 8 * q_groups; ++j) row[8 + j] = (uint16_t)(src[j] >> 16);
+                }
+            }
         }
     }
     put(h.subst_n_off, m->subst_n, 2ull * L * 4);
@@ -757,23 +807,44 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     }
     uint32_t img_cap = 0;
     size_t smem = 0;
-    c->err_cap = 1024;
+    c->err_cap = 768;
+    // quality-row pipeline geometry: one stage = the 16-bit rows of 2 positions for the populated bins of an orientation
+    const bool kde = c->mh.qual_mode == ISS_QUAL_KDE;
+    uint32_t q_shift = 1, q_dist = 1;
+    if (const char *e = getenv("ISS_QSTAGES")) {  // A/B switch for benchmarks: ring depth 2 or 4
+        if (atoi(e) == 4) q_shift = 2;
+    }
+    if (const char *e = getenv("ISS_QDIST")) q_dist = (uint32_t)std::max(1, std::min(atoi(e), (1 << q_shift) - 1));
+    const uint32_t q_cap = kde ? 2u * std::max(c->mh.q16_nb[0], c->mh.q16_nb[1]) * c->mh.q16_rs : 0u;
+    auto layout = [&](uint32_t T_, uint32_t split) {
+        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, 2u << split, kde ? (1u << q_shift) : 0u, q_cap);
+    };
+    Lay lay{};
     for (;; T >>= 1) {
         img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
-        smem = iss_tile_smem_bytes(T, img_cap, c->err_cap);
+        lay = layout(T, 1);
+        smem = lay.total;
         if (smem <= kMaxSmem) break;
         if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
     }
+    if (4ull * c->err_cap < L) return fail(ISS_E_ARG, "read length too long for the indel replay scratch");
     int bps = 0;
     uint32_t split_shift = 1;
-    CU(iss_occupancy(T, split_shift, smem, &bps));
+    CU(iss_occupancy(T, split_shift, q_shift, smem, &bps));
     if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
     if (bps <= 2 && T == 64) {  // long reads: the images leave room for <= 2 CTAs/SM -> 4 threads per read keep 32 warps/SM
         int bps4 = 0;
-        CU(iss_occupancy(T, 2, smem, &bps4));
-        if (bps4 >= bps) { split_shift = 2; bps = bps4; }
+        const Lay lay4 = layout(T, 2);
+        if (lay4.total <= kMaxSmem) {
+            CU(iss_occupancy(T, 2, q_shift, lay4.total, &bps4));
+            if (bps4 >= bps) { split_shift = 2; bps = bps4; lay = lay4; smem = lay4.total; }
+        }
     }
     c->split_shift = split_shift;
+    c->lay = lay;
+    c->q_stage_shift = q_shift;
+    c->q_dist = q_dist;
+    c->q_stage_cap = q_cap;
     if (const char *e = getenv("ISS_BPS")) {  // A/B switch for benchmarks: fewer CTAs per SM (with ISS_CARVEOUT: more L1)
         const int cap = atoi(e);
         if (cap >= 1 && cap < bps) bps = cap;
