@@ -41,6 +41,7 @@ extern "C" {
 #define ISS_E_SHORT 5     /* record not longer than the read length (reference: AssertionError, generator.py:130) */
 #define ISS_E_DEVICE 6    /* device-side failure flag (negative window, empty quality bin ...) */
 #define ISS_E_NOMEM 7
+#define ISS_E_IO 8        /* an output file could not be opened or written (reference: logger.error + sys.exit(1), generator.py:230-232) */
 
 typedef struct iss_ctx iss_ctx;
 
@@ -173,7 +174,45 @@ typedef struct {
 int iss_ctx_next(iss_ctx *ctx, iss_batch *batch, int *have);
 int iss_ctx_release(iss_ctx *ctx, const iss_batch *batch);
 
+/* Drops whatever is left of the current submit: waits for the batches in flight, frees every slot, and leaves the context
+ * ready for a new set_genome / set_model / submit.  Also the way out after a failed iss_ctx_submit / iss_ctx_next. */
+int iss_ctx_abort(iss_ctx *ctx);
+
+/* ---- files (replaces worker_iterator's SeqIO.write loop and, for plain FASTQ, the parent's concatenate) ---------------
+ * iss/generator.py:64-66,227-238 write {prefix}_R1.fastq, _R2.fastq, .vcf from Python objects; iss/app.py:123-133 then
+ * copies every byte again into the final files.  iss_ctx_write_files runs submit + next/release itself and pwrite()s every
+ * finished batch from the pinned ring slot with a pool of native threads.  With append == 0 the bytes of this call go to
+ * [offset_r1, ...) of path_r1 (and likewise R2): plain FASTQ sizes are closed-form (iss_fastq_bytes), so several workers /
+ * GPUs can write one final file at disjoint offsets and no concatenation pass is needed.  VCF text is always appended. */
+typedef struct {
+    const char *path_r1;      /* NULL: that stream is produced and copied to the host but not written */
+    const char *path_r2;
+    const char *path_vcf;
+    uint64_t offset_r1;       /* append == 0: file offset of this call's first R1 / R2 byte */
+    uint64_t offset_r2;
+    uint32_t append;          /* 1: write at the end of the file (compressed streams: sizes are not known in advance) */
+    uint32_t truncate;        /* 1: O_TRUNC on open (a worker's private file, like the reference's open(..., "w")) */
+    uint32_t writer_threads;  /* pwrite threads; 0 = default (4) */
+    uint32_t reserved;
+} iss_file_sink;
+
+typedef struct {
+    uint64_t bytes_r1, bytes_r2, bytes_vcf;
+    uint64_t n_pairs, n_batches;
+    double wall_ms;           /* whole call, host clock */
+    double write_ms;          /* part of it spent waiting for the writers */
+} iss_write_stats;
+
+int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_items, const iss_gen_opts *opts,
+                        const iss_file_sink *sink, iss_write_stats *out);
+
 /* ---- measurement ------------------------------------------------------------------------------ */
+/* Sustained device -> pinned host copy rate (GB/s, CUDA events) into a ring of ring_bytes allocated like the output ring
+ * (alloc_mode: 0 cudaMallocHost, 1 mmap + mbind(GPU node) + cudaHostRegister, 2 write-combined), copies of chunk_bytes.
+ * *node receives the NUMA node that backs the ring (-1 unknown).  Called concurrently for several devices it measures the
+ * host side of the 8-GPU end-to-end figure (tools/d2h_probe.py). */
+int iss_probe_d2h(int device, int alloc_mode, uint64_t ring_bytes, uint64_t chunk_bytes, double seconds, double *gbps, int *node);
+
 typedef struct {
     uint64_t pairs;            /* pairs generated since context creation */
     uint64_t fastq_bytes;      /* R1 + R2 bytes produced */
@@ -185,6 +224,8 @@ typedef struct {
     uint64_t subst_errors;     /* substitution events */
     uint64_t genome_bytes_device;
     uint64_t model_bytes_device;
+    int32_t ring_numa_node;    /* NUMA node backing the pinned output ring (-1: unknown / not bound) */
+    uint32_t ring_alloc_mode;  /* 0 cudaMallocHost, 1 mmap + mbind(GPU node) + cudaHostRegister, 2 write-combined */
 } iss_stats;
 int iss_ctx_stats(iss_ctx *ctx, iss_stats *out);
 

@@ -10,7 +10,7 @@ ISS_QROW = 64
 ISS_MAX_ALT = 4
 ISS_UNIQUE_ID_BYTES = 128
 
-ISS_OK, ISS_E_CUDA, ISS_E_ARG, ISS_E_STATE, ISS_E_CHAR, ISS_E_SHORT, ISS_E_DEVICE, ISS_E_NOMEM = range(8)
+ISS_OK, ISS_E_CUDA, ISS_E_ARG, ISS_E_STATE, ISS_E_CHAR, ISS_E_SHORT, ISS_E_DEVICE, ISS_E_NOMEM, ISS_E_IO = range(9)
 
 
 class IssRecord(ctypes.Structure):
@@ -55,7 +55,20 @@ class IssStats(ctypes.Structure):
     _fields_ = [("pairs", ctypes.c_uint64), ("fastq_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
                 ("h2d_bytes", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("kernel_ms", ctypes.c_double),
                 ("slow_reads", ctypes.c_uint64), ("subst_errors", ctypes.c_uint64),
-                ("genome_bytes_device", ctypes.c_uint64), ("model_bytes_device", ctypes.c_uint64)]
+                ("genome_bytes_device", ctypes.c_uint64), ("model_bytes_device", ctypes.c_uint64),
+                ("ring_numa_node", ctypes.c_int32), ("ring_alloc_mode", ctypes.c_uint32)]
+
+
+class IssFileSink(ctypes.Structure):
+    _fields_ = [("path_r1", ctypes.c_char_p), ("path_r2", ctypes.c_char_p), ("path_vcf", ctypes.c_char_p),
+                ("offset_r1", ctypes.c_uint64), ("offset_r2", ctypes.c_uint64), ("append", ctypes.c_uint32),
+                ("truncate", ctypes.c_uint32), ("writer_threads", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+class IssWriteStats(ctypes.Structure):
+    _fields_ = [("bytes_r1", ctypes.c_uint64), ("bytes_r2", ctypes.c_uint64), ("bytes_vcf", ctypes.c_uint64),
+                ("n_pairs", ctypes.c_uint64), ("n_batches", ctypes.c_uint64), ("wall_ms", ctypes.c_double),
+                ("write_ms", ctypes.c_double)]
 
 
 EXPORTS = {
@@ -76,6 +89,11 @@ EXPORTS = {
                                       ctypes.POINTER(IssGenOpts)]),
     "iss_ctx_next": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssBatch), ctypes.POINTER(ctypes.c_int)]),
     "iss_ctx_release": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssBatch)]),
+    "iss_ctx_abort": (ctypes.c_int, [ctypes.c_void_p]),
+    "iss_ctx_write_files": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssWorkItem), ctypes.c_uint64,
+                                           ctypes.POINTER(IssGenOpts), ctypes.POINTER(IssFileSink), ctypes.POINTER(IssWriteStats)]),
+    "iss_probe_d2h": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double,
+                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]),
     "iss_ctx_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssStats)]),
     "iss_ctx_sync": (ctypes.c_int, [ctypes.c_void_p]),
     "iss_ctx_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),

@@ -13,7 +13,7 @@ import sys
 import threading
 
 from . import fasta, parallel, util
-from .engine import Engine
+from .engine import Engine, worker_items
 from .generator import (generate_work_divider, load_error_model, load_genomes, load_readcount_or_abundance,
                         register_records, worker_iterator)
 from .version import __version__
@@ -41,7 +41,12 @@ def generate_reads(args):
     logger.info("Generating %s reads" % n_reads)
 
     temp_file_list = [f"{args.output}.iss.tmp.{i}" for i in range(args.cpus)]
+    fq = ".fastq.gz" if args.compress else ".fastq"  # --compress: gzip members come off the GPU, they concatenate
+    out_r1, out_r2 = args.output + "_R1" + fq, args.output + "_R2" + fq
     engines = []
+    threads = []
+    stop = threading.Event()  # set on Ctrl-C or when a device thread fails: workers finish their current chunk and return
+    in_place = not args.compress  # plain FASTQ: chunk sizes are closed-form, the GPUs write the final files at their offsets
     try:
         records = list(fasta.parse(genome_file))
         n_read_pairs = n_reads // 2
@@ -62,18 +67,34 @@ def generate_reads(args):
         if n_gpus > 1:  # one NCCL broadcast of the packed genome + model tables, then no communication
             Engine.comm_init_all(engines)
             Engine.bcast_all(engines, 0)
+            for e in engines[1:]:
+                e.adopt_records(engines[0])
         seed = args.seed if args.seed is not None else random.SystemRandom().getrandbits(62)
+        sinks = {}
+        if in_place:  # byte offset of every chunk in the final files = FASTQ bytes of the chunks before it
+            at = 0
+            for cpu_number, (work, _prefix) in jobs:
+                items = worker_items([(engines[0].record_index(rec), n) for rec, n, _ in work], cpu_number, seed,
+                                     engines[0].record_lengths, engines[0].read_length)
+                sinks[cpu_number] = dict(path_r1=out_r1, path_r2=out_r2, offset_r1=at, offset_r2=at)
+                at += engines[0].fastq_bytes(items)
+            for path in (out_r1, out_r2):
+                with open(path, "wb") as fh:
+                    fh.truncate(at)
         errors = []
 
         def run_device(d):
             try:
                 parallel.bind_to_device_numa(d)
                 for cpu_number, (work, prefix) in jobs:
+                    if stop.is_set():
+                        return
                     if parallel.chunk_owner(cpu_number, n_gpus) == d:
                         worker_iterator(work, error_model, cpu_number, prefix, seed, args.sequence_type, args.gc_bias,
-                                        engine=engines[d], compress=args.compress)
+                                        engine=engines[d], compress=args.compress, sink=sinks.get(cpu_number), stop=stop)
             except BaseException as e:  # noqa: BLE001 - re-raised in the parent thread
                 errors.append(e)
+                stop.set()
 
         threads = [threading.Thread(target=run_device, args=(d,)) for d in range(n_gpus)]
         for t in threads:
@@ -82,31 +103,38 @@ def generate_reads(args):
             t.join()
         if errors:
             raise errors[0]
-        fq = ".fastq.gz" if args.compress else ".fastq"  # --compress: gzip members come off the GPU, they concatenate
         for cpu_number in range(len(jobs), args.cpus):  # workers that got no chunk still leave (empty) files
-            for suffix in ("_R1" + fq, "_R2" + fq, ".vcf"):
+            for suffix in (() if in_place else ("_R1" + fq, "_R2" + fq)) + (".vcf",):
                 open(temp_file_list[cpu_number] + suffix, "wb").close()
     except KeyboardInterrupt as e:
         logger.error("iss generate interrupted: %s" % e)
+        stop.set()
+        for t in threads:  # the device threads own their contexts until they return: wait before anything is torn down
+            t.join()
         tmp = [t + s for t in temp_file_list for s in ("_R1.fastq", "_R2.fastq", "_R1.fastq.gz", "_R2.fastq.gz", ".vcf")]
         tmp.append(genome_file)
         util.cleanup([t for t in tmp if os.path.exists(t)])
         sys.exit(1)
     else:
-        fq = ".fastq.gz" if args.compress else ".fastq"
-        temp_R1 = [t + "_R1" + fq for t in temp_file_list]
-        temp_R2 = [t + "_R2" + fq for t in temp_file_list]
         temp_mut = [t + ".vcf" for t in temp_file_list]
-        util.concatenate(temp_R1, args.output + "_R1" + fq)
-        util.concatenate(temp_R2, args.output + "_R2" + fq)
+        temp_fq = []
+        if not in_place:
+            temp_R1 = [t + "_R1" + fq for t in temp_file_list]
+            temp_R2 = [t + "_R2" + fq for t in temp_file_list]
+            util.concatenate(temp_R1, out_r1)
+            util.concatenate(temp_R2, out_r2)
+            temp_fq = temp_R1 + temp_R2
         if args.store_mutations:
             util.concatenate(temp_mut, args.output + ".vcf",
                              "##fileformat=VCFv4.1\n" + "\t".join(["#CHROM", "POS", "ID", "REF", "ALT", "QUAL", "FILTER", "INFO"]))
-        util.cleanup(temp_R1 + temp_R2 + temp_mut + [genome_file])
+        util.cleanup(temp_fq + temp_mut + [genome_file])
         if args.compress and args.store_mutations:  # the FASTQ files were compressed on the GPU (util.py:255-268 for the small VCF)
             util.compress(args.output + ".vcf")
         logger.info("Read generation complete")
     finally:
+        stop.set()
+        for t in threads:
+            t.join()
         for e in engines:
             e.close()
 

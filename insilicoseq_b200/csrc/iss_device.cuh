@@ -10,7 +10,7 @@
 
 #define ISS_QROW 64
 #define ISS_MAX_ALT 4
-#define ISS_Q16_MAX_GROUPS 8  // a 16-bit quality row = 8 splitters + up to 8 groups of 8 entries (see iss_kernels.cu)
+#define ISS_Q16_ROW_BYTES 132  // a 16-bit quality row: ISS_QROW u16 entries + 4 bytes, so that the rows of a position start in different banks
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Slot schedule: DESIGN.md section 3 / oracle/philox.py.
@@ -118,11 +118,10 @@ struct ModelHeader {
     // offsets (bytes from blob start)
     uint64_t frag_thr_off, insert_thr_off, qual_exact_off, subst_n_off, subst_thr_off, subst_alt_off, ins_base_off,
         del_thr_off, del_nz_off, basic_thr_off, basic_val_off, ent_off;
-    // 16-bit quality rows (kernel phase 4): per orientation [L + 1 positions][q16_nb rows of the populated bins][q16_rs bytes]
+    // 16-bit quality rows (kernel phase 4): per orientation [L + 1 positions][q16_ps bytes: q16_nb rows of ISS_Q16_ROW_BYTES]
     uint64_t q16_off[2];
     uint32_t q16_nb[2];       // populated quality bins of the orientation (rows per position)
-    uint32_t q16_rs;          // bytes per row: 16 * (1 + groups), rounded to an odd multiple of 16
-    uint32_t q16_groups;      // 8-entry groups per row: ceil((max live thresholds + 1) / 8)
+    uint32_t q16_ps[2];       // bytes per position: q16_nb * ISS_Q16_ROW_BYTES rounded up to 16 (bulk copies are 16-byte granular)
     uint8_t q16_cbin[2][4];   // bin -> row index among the populated bins
 };
 
@@ -208,16 +207,19 @@ struct Lay {
     uint32_t sFlag;    // u32[2T] read already queued for the sequential indel replay
     uint32_t sErr;     // u32[err_cap]
     uint32_t sErrThr;  // u32[64]
-    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 2 gather-mbarrier parity, 3 bytes of the tile's last record; +16: mbarrier of the TMA genome gather
-    uint32_t sQtot;    // u32[n_streams] blocks the stream's producer lane stages during the whole launch
-    uint32_t sBar;     // u64[n_streams][q_stages][2]: {full, empty} mbarriers of the quality-row pipeline
-    uint32_t sQst;     // [n_streams][q_stages][q_stage_cap] staged 16-bit quality rows (2 positions per stage)
+    uint32_t sTie;     // u32[tie_cap] positions whose 16-bit quality search met a tie (read << 16 | position)
+    uint32_t sTie2;    // u32[tie_cap] those of them that turned out to be substitution errors
+    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 2 gather-mbarrier parity, 3 bytes of the tile's last record, 4 nTie, 5 nTie2;
+                       //         +24: mbarrier of the TMA genome gather
+    uint32_t sBar;     // u64[n_streams][2 stages][2]: {full, empty} mbarriers of the quality-row pipeline
+    uint32_t sQst;     // [n_streams][2 stages][q_stage_cap] staged 16-bit quality rows (2 positions per stage)
     uint32_t total;    // bytes of dynamic shared memory
 };
 
-// n_streams = 2 * S position streams per tile (orientation x part); q_stages = ring depth per stream (power of two)
-__host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uint32_t err_cap, uint32_t n_streams, uint32_t q_stages,
+// n_streams = 2 * S position streams per tile (orientation x part), each with two stages of q_stage_cap bytes (0: no pipeline)
+__host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uint32_t err_cap, uint32_t tie_cap, uint32_t n_streams,
                                                uint32_t q_stage_cap) {
+    const uint32_t q_stages = q_stage_cap ? 2u : 0u;
     Lay l;
     uint32_t q = 0;
     l.img[0] = q; q += img_cap;
@@ -236,8 +238,9 @@ __host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uin
     l.sFlag = q; q += 8u * T;
     l.sErr = q; q += 4u * err_cap;
     l.sErrThr = q; q += 4u * ISS_QROW;
+    l.sTie = q; q += 4u * tie_cap;
+    l.sTie2 = q; q += 4u * tie_cap;
     l.sCtl = q; q += 32u;
-    l.sQtot = q; q += 4u * ((n_streams + 3u) & ~3u);
     l.sBar = q; q += 16u * n_streams * q_stages;
     l.sQst = q; q += n_streams * q_stages * q_stage_cap;
     l.total = q;
@@ -272,15 +275,14 @@ struct GenParams {
     uint8_t *out1;
     uint8_t *out2;
     // quality-row pipeline (phase 4): every position stream (orientation x part) of a tile walks the same rows for every
-    // tile, so its producer lane keeps a ring of q_stages bulk copies (cp.async.bulk + mbarrier) q_dist blocks ahead
-    uint32_t q_stage_shift;   // log2(q_stages)
-    uint32_t q_dist;          // prefetch distance in blocks of 2 positions (1 .. q_stages - 1)
+    // tile; its producer lane stages them one block ahead with cp.async.bulk + mbarriers (two stages per stream)
     uint32_t q_stage_cap;     // bytes reserved per stage (>= q_stage_bytes[o], multiple of 16)
-    uint32_t q_stage_bytes[2];  // 2 * q16_nb[o] * q16_rs: the rows of one block of orientation o
-    uint32_t q_pos_stride[2];   // q16_nb[o] * q16_rs
-    uint32_t q_row_off[2][4];   // bin -> byte offset of its row inside a position (q16_cbin * q16_rs)
+    uint32_t q_stage_bytes[2];  // 2 * q16_ps[o]: the rows of one block of orientation o
+    uint32_t q_pos_stride[2];   // q16_ps[o]
+    uint32_t q_row_off[2][4];   // bin -> byte offset of its row inside a position (q16_cbin * ISS_Q16_ROW_BYTES)
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)
     uint32_t err_cap;         // entries of the substitution list
+    uint32_t tie_cap;         // entries of the tie queue (exact pass)
     uint32_t amplicon;
     uint32_t gc_bias;
     uint32_t chunk_magic;     // ceil(2^32 / nchunk) for idx / nchunk (unused when nchunk == 1: the value would be 2^32)

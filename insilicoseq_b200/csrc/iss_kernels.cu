@@ -58,49 +58,53 @@ __device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cas
 __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
 
 // Quality rows (kde.py:82-85: q = searchsorted(cdf_pos, u) = #{j : w > thr[j]}) are searched on the top 16 bits of the
-// draw.  A row is 8 splitters + G groups of 8 sorted u16 entries e[j] = thr[j] >> 16, two per 32-bit word:
-//   bytes  0..15   splitters s_k = e[8k + 7], k = 0..6, then 0xFFFF
-//   bytes 16..     group g = e[8g .. 8g + 7]
-// #{j : w16 > e[j]} = 8 cA + cB with cA = #{k : w16 > s_k} and cB = #{j < 7 : w16 > e[8 cA + j]}: two 16-byte shared
-// memory loads (the rows of the block were staged by cp.async.bulk, see phase 4) and two 3-step searches in
-// registers.  With w16 != e[j] the 16-bit order is the 32-bit order; the entry the search stops at, t = e[8 cA + cB], is
-// the only place a tie can start (the row is sorted), so t == w16 sends the draw to the exact 32-bit row.
-__device__ __forceinline__ uint4 lds128(uint32_t off) { return *reinterpret_cast<const uint4 *>(iss_smem + off); }
+// draw: a row is the 64 sorted entries e[j] = thr[j] >> 16 as u16 (pad = 0xFFFF; e[63] is always pad), staged into shared
+// memory by cp.async.bulk (phase 4).  Branch-free lower bound, the byte offset of e[count] being the accumulator:
+//     for s in 32, 16, 8, 4, 2, 1:  if (w16 > e[count + s - 1]) count += s          (LDS.U16 + ISETP + predicated IADD)
+// With w16 != e[j] for all j the 16-bit order is the 32-bit order.  The row is sorted, so a tie can only start at the entry
+// the search stops at: e[count] == w16 (~ 41 / 65536 of the draws) defers the position to the exact pass (phase 4b), which
+// evaluates it on the 32-bit row -- nothing is called from the hot loop.
+// row_off: offset of the read's staged row from iss_smem
+// row: shared-window address of the read's staged row (smem_addr(iss_smem) + offset)
+__device__ __forceinline__ uint32_t q16_search(uint32_t row, uint32_t w16, bool &tie) {
+    uint32_t a = row;
+#define ISS_Q16_STEP(S)                                                                                              \
+    {                                                                                                                \
+        uint32_t e;                                                                                                  \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(e) : "r"(a));                                       \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(a) : "r"(w16), "r"(e)); \
+    }
+    ISS_Q16_STEP(32) ISS_Q16_STEP(16) ISS_Q16_STEP(8) ISS_Q16_STEP(4) ISS_Q16_STEP(2) ISS_Q16_STEP(1)
+#undef ISS_Q16_STEP
+    uint32_t e;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
+    tie = e == w16;
+    return (a - row) >> 1;
+}
 
-// v = 8 sorted u16 (t0 = low half of v.x ... t7 = high half of v.w), kh = w16 << 16.
-// Returns c = #{j < 7 : w16 > t_j} and cand = t_c.  A high half compares as a whole register: kh > (t_hi << 16 | t_lo)
-// <=> w16 > t_hi, exactly.
-__device__ __forceinline__ uint32_t cnt8x16(uint32_t kh, uint32_t w16, const uint4 &v, uint32_t &cand) {
-    const bool p1 = kh > v.y;                              // t3
-    const uint32_t m = p1 ? v.z : v.x, mo = p1 ? v.w : v.y;
-    const bool p2 = kh > m;                                // t5 or t1
-    const uint32_t lr = p2 ? mo : m;                       // the word holding t_c (low) and t_{c+1} (high), c = 4 p1 + 2 p2
-    const uint32_t lo = lr & 0xFFFFu;
-    const bool p3 = w16 > lo;
-    cand = p3 ? (lr >> 16) : lo;
-    return (p1 ? 4u : 0u) + (p2 ? 2u : 0u) + (p3 ? 1u : 0u);
+// queue (read, position) for the exact pass; a full queue makes the whole tile take it (ctl word 5)
+__device__ __forceinline__ void defer_position(const Lay &l, uint32_t cap, uint32_t rd, uint32_t pos) {
+    const uint32_t slot = atomicAdd(&u32p(l.sCtl)[4], 1u);
+    if (slot < cap) u32p(l.sTie)[slot] = (rd << 16) | pos;
 }
-// exact count for a draw whose top 16 bits equal an entry's: entries below c16 are smaller for sure
-__device__ __noinline__ uint32_t qual_exact_count(const uint32_t *__restrict__ row, uint32_t w, uint32_t c16) {
-    uint32_t c = c16;
-    while (c < ISS_QROW && w > __ldg(row + c)) ++c;
-    return c;
-}
-// row_off: offset of the read's staged row from iss_smem.  A tie (~ 41 / 65536 of the draws) goes to the 64 sorted
-// 32-bit thresholds of the same row (orientation o, the read's bin, position pos), located only then.
-__device__ __noinline__ uint32_t qual_tie(const GenParams &p, uint32_t rd, uint32_t pos, uint32_t w, uint32_t c16) {
+
+// The definition the fast paths must agree with: phred of (read rd, position pos) for the quality draw wq, from the
+// model's full-precision tables (kde.py:82-85 on the 64 sorted 32-bit thresholds; basic.py:41-53; perfect.py:35-42).
+__device__ __noinline__ uint32_t quality_exact(const GenParams &p, uint32_t rd, uint32_t pos, uint32_t wq) {
+    if (p.qual_mode == ISS_QUAL_CONST_MODE) return p.const_phred;
+    if (p.qual_mode == ISS_QUAL_TABLE_MODE) {
+        uint32_t a = 0, e = p.n_basic;
+        while (a < e) { const uint32_t mid = (a + e) >> 1; if (wq >= __ldg(p.m.basic_thr + mid)) a = mid + 1; else e = mid; }
+        return p.m.basic_val[a];
+    }
     const uint32_t o = rd >= p.tile_pairs ? 1u : 0u;
     const uint32_t bin = u32p(p.lay.sQrow)[rd] >> 16;
-    return qual_exact_count(p.m.qual_exact + (((size_t)(o * 4u + bin) * p.L + pos) << 6), w, c16);
-}
-__device__ __forceinline__ uint32_t q16_search(const GenParams &p, uint32_t row_off, uint32_t w, uint32_t rd, uint32_t pos) {
-    const uint32_t w16 = w >> 16, kh = w & 0xFFFF0000u;
-    uint32_t cand;
-    const uint32_t cA = cnt8x16(kh, w16, lds128(row_off), cand);
-    const uint32_t cB = cnt8x16(kh, w16, lds128(row_off + 16u + 16u * cA), cand);
-    uint32_t q = 8u * cA + cB;
-    if (cand == w16) q = qual_tie(p, rd, pos, w, q);
-    return q;
+    const uint32_t *__restrict__ row = p.m.qual_exact + (((size_t)(o * 4u + bin) * p.L + pos) << 6);
+    uint32_t c = 0;
+#pragma unroll 1
+    for (uint32_t s = 32; s >= 1; s >>= 1)
+        if (wq > __ldg(row + c + s - 1u)) c += s;  // row[63] == 0xFFFFFFFF: c <= 63
+    return c;
 }
 
 __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
@@ -204,12 +208,6 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
     seq[pos] = (uint8_t)alt;
 }
 
-__device__ __noinline__ void apply_substitution_overflow(const GenParams &p, uint32_t tile, uint32_t rd, uint32_t pos) {
-    // substitution list full: rare, kept out of the hot loop's code (and its live registers: the tile constants are rebuilt here)
-    const uint32_t g0lo = (uint32_t)u64p(p.lay.sOff)[0];
-    apply_substitution(p, p.lay, (uint64_t)tile * p.tile_pairs, (g0lo & 15u) - g0lo, rd, pos);
-}
-
 // ---- sequential replay of introduce_indels + adjust_seq_length for one read ---------------------------
 // Reference list semantics (error_models/__init__.py:187-226) restated as a stream:
 //   seq = out[0..nucl) ++ [cur] ++ future,   future = LIFO of inserted bases on top of the unread original.
@@ -277,13 +275,13 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
 
 }  // namespace
 
-template <int kThreads, int kMinBlocks, int kQShift>
+template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const Lay &l = p.lay;
     if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
     const uint32_t smem0 = smem_addr(iss_smem);
-    const uint32_t mbar = smem0 + l.sCtl + 16u;                 // 8-byte mbarrier behind the control words
+    const uint32_t mbar = smem0 + l.sCtl + 24u;                 // 8-byte mbarrier behind the control words
     if (tid == 0) {
         u32p(l.sCtl)[2] = 0;
         if (p.tma_gather) mbar_init(mbar, 2u * T);  // every (pair, orientation) thread arrives once per tile
@@ -297,58 +295,52 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
     // ---- quality-row pipeline.  Thread (o, part) walks the Philox QUAL blocks [b_begin, b_end) of its reads, and so do
     //      the other T - 1 threads of its position stream q4 -- for EVERY tile.  The rows a stream needs are therefore a
     //      fixed cyclic sequence: block b -> the rows of positions 2b, 2b + 1 for the populated bins of orientation o,
-    //      contiguous in the model blob.  The stream's first lane keeps q_dist blocks in flight with cp.async.bulk into a
-    //      ring of q_stages shared-memory stages; `full` mbarriers carry the byte counts, `empty` ones (one arrival per
-    //      warp of the stream) hand a stage back.  `it` counts the stream's blocks since the kernel started.
+    //      contiguous in the model blob.  Two shared-memory stages per stream: blocks b_begin, b_begin + 2, ... go through
+    //      stage 0 and b_begin + 1, b_begin + 3, ... through stage 1, for every tile alike (with an odd block count the
+    //      last turn of stage 1 is simply skipped), so the loop is unrolled by two with static stage addresses.  The
+    //      stream's first lane issues one cp.async.bulk per block, one block ahead of the consumers; `full` mbarriers carry
+    //      the byte counts, `empty` ones (one arrival per warp of the stream) hand a stage back.  Phase parities: bit s of
+    //      `qpar` = consumptions of stage s so far, mod 2; the producer's wait on `empty[s]` before its (c + 1)-th fill of
+    //      stage s uses parity (c + 1) & 1, which passes at once on the fresh barrier (c = 0).
     const bool kde = p.qual_mode == ISS_QUAL_KDE_MODE;
     const uint32_t nblk = (L + 1u) >> 1;
     const uint32_t b_begin = (half * nblk) >> p.split_shift, b_end = ((half + 1u) * nblk) >> p.split_shift;
-    constexpr uint32_t K = 1u << kQShift;  // stages of the ring (p.q_stage_shift == kQShift)
-    const uint32_t bar0 = smem0 + l.sBar + q4 * (K << 4);        // {full, empty} x K of this stream
-    const uint32_t stage0 = l.sQst + q4 * (K * p.q_stage_cap);   // offset of the stream's ring from iss_smem
-    const uint32_t stage_bytes = p.q_stage_bytes[o];
-    uint32_t it = 0;
+    const uint32_t bar0 = smem0 + l.sBar + (q4 << 5);            // full[0] +0, empty[0] +8, full[1] +16, empty[1] +24
+    const uint32_t stage0 = l.sQst + q4 * (2u * p.q_stage_cap);  // offset of the stream's two stages from iss_smem
+    uint32_t qpar = 0;
     if (kde) {
         if (tid == 0) {
-            const uint32_t nbar = (2u << p.split_shift) * K;
+            const uint32_t nbar = (2u << p.split_shift) * 2u;
             for (uint32_t k = 0; k < nbar; ++k) {
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + l.sBar + 16u * k), "r"(1u) : "memory");
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + l.sBar + 16u * k + 8u), "r"(T >> 5) : "memory");
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if (pair == 0)  // the producer lane of the stream: blocks it will ever stage (kept in shared memory, next to its barriers)
-            u32p(l.sQtot)[q4] = blockIdx.x < ntiles ? ((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x) * (b_end - b_begin) : 0u;
         __syncthreads();
     }
-    // stage fill number f (block (f mod n) of the stream's cycle) -> ring stage f mod K, use f / K of that stage
-    auto q_issue = [&](uint32_t f, uint32_t blk) {
-        const uint32_t stg = f & (K - 1u), use = f >> kQShift;
-        const uint32_t fb = bar0 + (stg << 4);
-        if (use) mbar_wait(fb + 8u, (use - 1u) & 1u);  // every warp of the stream is done with the previous use
-        mbar_arrive_expect_tx(fb, stage_bytes);
-        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * stage_bytes, stage_bytes, fb);
+    // producer lane only: stage `stg` <- the rows of block `blk`, after every warp of the stream released the stage
+    auto q_fill = [&](uint32_t stg, uint32_t blk, uint32_t done /* consumptions of the stage so far */) {
+        const uint32_t fb = bar0 + (stg << 4), bytes = p.q_stage_bytes[o];
+        mbar_wait(fb + 8u, (done + 1u) & 1u);
+        mbar_arrive_expect_tx(fb, bytes);
+        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * bytes, bytes, fb);
     };
-    if (kde && pair == 0) {
-        const uint32_t it_total = u32p(l.sQtot)[q4];
-        uint32_t blk = b_begin;
-        for (uint32_t f = 0; f < p.q_dist && f < it_total; ++f) {
-            q_issue(f, blk);
-            if (++blk == b_end) blk = b_begin;
-        }
-    }
+    if (kde && pair == 0 && blockIdx.x < ntiles && b_begin < b_end) q_fill(0u, b_begin, 0u);
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t gp0 = (uint64_t)tile * T;
         const uint32_t npairs = (uint32_t)((p.total_pairs - gp0 < (uint64_t)T) ? (p.total_pairs - gp0) : (uint64_t)T);
-        const bool valid = pair < npairs;
+        uint32_t vflag = pair < npairs ? 1u : 0u;
+        asm volatile("" : "+r"(vflag));  // one live register instead of the 64-bit arithmetic above re-done wherever `valid` is used
+        const bool valid = vflag != 0u;
 
         // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97).  Nothing here touches the stream
         //      images, which the previous tile's copy-out may still be reading; its bulk stores are waited for by thread 0
         //      before the barrier that ends the phase.
         if (tid == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // returns at once when nothing is pending
-            u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0;
+            u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0; u32p(l.sCtl)[4] = 0; u32p(l.sCtl)[5] = 0;
             u32p(l.sCtl)[2] ^= 1u;  // phase parity of the gather mbarrier for this tile (1, 0, 1, ... ; read as parity ^ 1)
         }
         if (tid < 2u * T) u32p(l.sFlag)[tid] = 0;
@@ -618,36 +610,53 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             uint8_t *qual = seq + L + 3;
             const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
             if (kde) {
-                const uint32_t row0 = stage0 + (valid ? (u32p(l.sQrow)[rd] & 0xFFFFu) : 0u);  // the read's row in stage 0, position 0
-                for (uint32_t b = b_begin; b < b_end; ++b, ++it) {
-                    if (pair == 0 && it + p.q_dist < u32p(l.sQtot)[q4]) {  // producer lane: keep the ring q_dist blocks ahead
-                        uint32_t blk = b + p.q_dist;
-                        while (blk >= b_end) blk -= b_end - b_begin;
-                        q_issue(it + p.q_dist, blk);
-                    }
-                    const uint32_t stg = it & (K - 1u);
-                    mbar_wait(bar0 + (stg << 4), (it >> kQShift) & 1u);
+                const uint32_t row0 = smem0 + stage0 + (valid ? (u32p(l.sQrow)[rd] & 0xFFFFu) : 0u);  // shared-window address of the read's row in stage 0, first position
+                const bool producer = pair == 0;
+                const bool more_tiles = tile + gridDim.x < ntiles;
+                // one block: wait for its rows, draw + search two positions, hand the stage back
+                auto q_block = [&](uint32_t b, uint32_t stg) {
+                    mbar_wait(bar0 + (stg << 4), (qpar >> stg) & 1u);
+                    qpar ^= 1u << stg;
                     if (valid) {
                         const uint32_t pos = 2u * b;
                         const uint32_t r0 = row0 + stg * p.q_stage_cap;
                         const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
-                        const uint32_t q0 = q16_search(p, r0, w.x, rd, pos);
-                        qual[pos] = (uint8_t)(q0 + 33u);
-                        if (w.y > u32p(l.sErrThr)[q0]) {
-                            const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, tile, rd, pos);
+                        bool tie;
+                        const uint32_t q0 = q16_search(r0, w.x >> 16, tie);
+                        if (tie) {
+                            defer_position(l, p.tie_cap, rd, pos);
+                        } else {
+                            qual[pos] = (uint8_t)(q0 + 33u);
+                            if (w.y > u32p(l.sErrThr)[q0]) {
+                                const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos;  // a full list switches phase 5 to the exact pass
+                            }
                         }
                         if (pos + 1u < L) {
-                            const uint32_t q1 = q16_search(p, r0 + p.q_pos_stride[o], w.z, rd, pos + 1u);
-                            qual[pos + 1u] = (uint8_t)(q1 + 33u);
-                            if (w.w > u32p(l.sErrThr)[q1]) {
-                                const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else apply_substitution_overflow(p, tile, rd, pos + 1u);
+                            const uint32_t q1 = q16_search(r0 + p.q_pos_stride[o], w.z >> 16, tie);
+                            if (tie) {
+                                defer_position(l, p.tie_cap, rd, pos + 1u);
+                            } else {
+                                qual[pos + 1u] = (uint8_t)(q1 + 33u);
+                                if (w.w > u32p(l.sErrThr)[q1]) {
+                                    const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                                    if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u);
+                                }
                             }
                         }
                     }
                     __syncwarp();
                     if ((tid & 31u) == 0) mbar_arrive(bar0 + (stg << 4) + 8u);  // this warp is done with the stage
+                };
+                for (uint32_t b = b_begin; b < b_end; b += 2u) {
+                    const bool second = b + 1u < b_end;
+                    if (producer && second) q_fill(1u, b + 1u, (qpar >> 1) & 1u);
+                    q_block(b, 0u);
+                    if (producer) {  // stage 0 for the next turn: the next pair of blocks, or the first block of the next tile
+                        if (b + 2u < b_end) q_fill(0u, b + 2u, qpar & 1u);
+                        else if (more_tiles) q_fill(0u, b_begin, qpar & 1u);
+                    }
+                    if (second) q_block(b + 1u, 1u);
                 }
             } else if (valid) {
                 for (uint32_t b = b_begin; b < b_end; ++b) {
@@ -667,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         qual[pos] = (uint8_t)(q + 33u);
                         if (wt > u32p(l.sErrThr)[q]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else apply_substitution_overflow(p, tile, rd, pos);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos;
                         }
                     }
                 }
@@ -675,15 +684,64 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         }
         __syncthreads();
 
+        // ---- phase 4b: the exact pass.  Positions whose 16-bit search met a tie are evaluated on the 32-bit row: the draw is
+        //      recomputed (a Philox word is a pure function of its address), the phred written, the error test made.  If the
+        //      queue or the substitution list overflowed (models far outside the bundled ones: ~ every base an error), every
+        //      thread walks its positions again on the exact tables and applies its substitutions directly.
+        const uint32_t ntie = u32p(l.sCtl)[4];
+        const uint32_t nerr_fast = u32p(l.sCtl)[0];
+        const bool redo_all = ntie > p.tie_cap || nerr_fast > p.err_cap;  // block-uniform
+        if (ntie && !redo_all) {
+            for (uint32_t e = tid; e < ntie; e += blockDim.x) {
+                const uint32_t v = u32p(l.sTie)[e];
+                const uint32_t trd = v >> 16, pos = v & 0xFFFFu;
+                const uint32_t to = trd >= T ? 1u : 0u, tp = trd - to * T;
+                const uint64_t tP = u64p(l.sP)[tp];
+                const Philox4 w = philox4x32_10_rk(pos >> 1, iss_read_stream(to, ISS_K_QUAL) | (u32p(l.sAtt)[tp] << 8), (uint32_t)tP,
+                                                   (uint32_t)(tP >> 32), p.rk);
+                const uint32_t q = quality_exact(p, trd, pos, (pos & 1u) ? w.z : w.x);
+                (imgp(l, to) + rel0 + u32p(l.sRel)[tp] + L + 3u)[pos] = (uint8_t)(q + 33u);
+                if (((pos & 1u) ? w.w : w.y) > u32p(l.sErrThr)[q]) {
+                    const uint32_t slot = atomicAdd(&u32p(l.sCtl)[5], 1u);  // a second list: the first one is being read below
+                    if (slot < p.tie_cap) u32p(l.sTie2)[slot] = v;
+                }
+            }
+        }
+
         // ---- phase 5: substitutions, compacted over the whole tile (error_models/__init__.py:95-109)
-        {
-            const uint32_t nerr_all = u32p(l.sCtl)[0];
-            const uint32_t nerr = nerr_all < p.err_cap ? nerr_all : p.err_cap;
+        if (!redo_all) {
+            const uint32_t nerr = nerr_fast;
             for (uint32_t e = tid; e < nerr; e += blockDim.x) {
                 const uint32_t v = u32p(l.sErr)[e];
                 apply_substitution(p, l, gp0, rel0, v >> 16, v & 0xFFFFu);
             }
-            if (tid == 0 && nerr_all) atomicAdd(p.counters + 1, (unsigned long long)nerr_all);
+            if (ntie) {
+                __syncthreads();  // block-uniform: the tie pass above has finished writing its list
+                const uint32_t n2 = u32p(l.sCtl)[5];
+                for (uint32_t e = tid; e < n2; e += blockDim.x) {
+                    const uint32_t v = u32p(l.sTie2)[e];
+                    apply_substitution(p, l, gp0, rel0, v >> 16, v & 0xFFFFu);
+                }
+                if (tid == 0 && n2) atomicAdd(p.counters + 1, (unsigned long long)n2);
+            }
+            if (tid == 0 && nerr) atomicAdd(p.counters + 1, (unsigned long long)nerr);
+        } else if (valid) {
+            uint8_t *qual = seq + L + 3;
+            const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
+            uint32_t napplied = 0;
+#pragma unroll 1
+            for (uint32_t b = b_begin; b < b_end; ++b) {
+                const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
+#pragma unroll 1
+                for (uint32_t h = 0; h < 2; ++h) {
+                    const uint32_t pos = 2u * b + h;
+                    if (pos >= L) break;
+                    const uint32_t q = quality_exact(p, rd, pos, h ? w.z : w.x);
+                    qual[pos] = (uint8_t)(q + 33u);
+                    if ((h ? w.w : w.y) > u32p(l.sErrThr)[q]) { apply_substitution(p, l, gp0, rel0, rd, pos); ++napplied; }
+                }
+            }
+            if (napplied) atomicAdd(p.counters + 1, (unsigned long long)napplied);
         }
         // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -738,41 +796,29 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 // ---- host-visible launch helpers --------------------------------------------------------------------
 size_t iss_tile_smem_bytes(const Lay &l) { return l.total; }
 
-#define ISS_FOR_EACH_KERNEL(X) X(256, 4, 1) X(512, 2, 1) X(256, 4, 2) X(512, 2, 2)
-
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
-#define X(T_, B_, Q_)                                                                                                        \
-    if (cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<T_, B_, Q_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); e != cudaSuccess) return e;
-    ISS_FOR_EACH_KERNEL(X)
-#undef X
-    return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
 }
 
 cudaError_t iss_kernel_carveout(int percent) {  // shared-memory share of the SM's unified L1/shared array
-#define X(T_, B_, Q_)                                                                                                        \
-    if (cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<T_, B_, Q_>, cudaFuncAttributePreferredSharedMemoryCarveout, percent); e != cudaSuccess) return e;
-    ISS_FOR_EACH_KERNEL(X)
-#undef X
-    return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
 }
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
-    const bool big = threads > 256, deep = p.q_stage_shift == 2;
-    if (big && deep) iss_generate_kernel<512, 2, 2><<<grid, threads, smem, stream>>>(p);
-    else if (big) iss_generate_kernel<512, 2, 1><<<grid, threads, smem, stream>>>(p);
-    else if (deep) iss_generate_kernel<256, 4, 2><<<grid, threads, smem, stream>>>(p);
-    else iss_generate_kernel<256, 4, 1><<<grid, threads, smem, stream>>>(p);
+    if (threads > 256) iss_generate_kernel<512, 2><<<grid, threads, smem, stream>>>(p);
+    else iss_generate_kernel<256, 4><<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_stage_shift, size_t smem, int *blocks_per_sm) {
+cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, size_t smem, int *blocks_per_sm) {
     const int threads = (int)((2u << split_shift) * T);
-    const bool big = threads > 256, deep = q_stage_shift == 2;
-    if (big && deep) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2>, threads, smem);
-    if (big) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 1>, threads, smem);
-    if (deep) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 2>, threads, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 1>, threads, smem);
+    if (threads > 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4>, threads, smem);
 }
 
 cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {

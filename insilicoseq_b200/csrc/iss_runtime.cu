@@ -22,6 +22,7 @@
 #include "iss_device.cuh"
 #include "iss_kernels.h"
 #include "iss_deflate.h"
+#include "iss_hostmem.h"
 
 namespace {
 
@@ -47,12 +48,14 @@ int fail(int code, const std::string &msg) {
 constexpr uint64_t kGenomeMagic = 0x31474e4547535349ull;  // "ISSGENG1"
 constexpr uint64_t kModelMagic = 0x314c444f4d535349ull;   // "ISSMODL1"
 constexpr size_t kMaxSmem = 232448;                        // 227 KB opt-in per CTA on sm_100
+constexpr uint32_t kTieCap = 64;                           // exact-pass queue per tile (~ 11 ties expected per 64-pair tile at L = 150)
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 struct Slot {
     uint8_t *d_out[2] = {nullptr, nullptr};
     uint8_t *h_out[2] = {nullptr, nullptr};
+    IssHostBuf h_buf[2];
     DevSegment *d_segs = nullptr;
     DevSegment *h_segs = nullptr;
     cudaStream_t stream = nullptr;
@@ -109,13 +112,14 @@ struct iss_ctx {
     uint64_t cur_item = 0, cur_off = 0;  // planner cursor
     uint64_t batch_pairs = 0, slot_cap = 0, max_rec = 0;
     uint32_t n_slots = 0, max_segs = 0;
-    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 768, grid = 0, split_shift = 1;
-    uint32_t q_stage_shift = 1, q_dist = 1, q_stage_cap = 0;  // quality-row pipeline: ring depth 2^shift, prefetch distance, bytes per stage
+    uint32_t tile_pairs = 64, img_cap = 0, err_cap = 512, grid = 0, split_shift = 1;
+    uint32_t q_stage_cap = 0;  // quality-row pipeline: bytes per stage
     Lay lay{};
     size_t smem = 0;
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
     bool trace = getenv("ISS_TRACE") != nullptr;
+    int ring_alloc = ISS_HOSTMEM_NUMA;  // ISS_RING_ALLOC=pinned|numa|wc
     double gz_ratio[2] = {0.4, 0.4};            // compressed / plain bytes per stream: a first guess, then the last returned batch
     bool active = false, exhausted = false;
     unsigned long long *d_counters = nullptr;
@@ -139,8 +143,9 @@ void free_slots(iss_ctx *c) {
     for (auto &s : c->slots) {
         if (s.d_out[0]) cudaFree(s.d_out[0]);
         if (s.d_out[1]) cudaFree(s.d_out[1]);
-        if (s.h_out[0]) cudaFreeHost(s.h_out[0]);
-        if (s.h_out[1]) cudaFreeHost(s.h_out[1]);
+        iss_host_free(&s.h_buf[0]);
+        iss_host_free(&s.h_buf[1]);
+        s.h_out[0] = s.h_out[1] = nullptr;
         if (s.d_segs) cudaFree(s.d_segs);
         if (s.h_segs) cudaFreeHost(s.h_segs);
         for (int k = 0; k < 2; ++k) {
@@ -284,18 +289,17 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.key = batch_key;
     philox_round_keys(batch_key, p.rk);
     p.lay = c->lay;
-    p.q_stage_shift = c->q_stage_shift;
-    p.q_dist = c->q_dist;
     p.q_stage_cap = c->q_stage_cap;
     for (uint32_t o = 0; o < 2; ++o) {
-        p.q_pos_stride[o] = h.q16_nb[o] * h.q16_rs;
-        p.q_stage_bytes[o] = 2u * p.q_pos_stride[o];
-        for (uint32_t b = 0; b < 4; ++b) p.q_row_off[o][b] = h.q16_cbin[o][b] * h.q16_rs;
+        p.q_pos_stride[o] = h.q16_ps[o];
+        p.q_stage_bytes[o] = 2u * h.q16_ps[o];
+        for (uint32_t b = 0; b < 4; ++b) p.q_row_off[o][b] = h.q16_cbin[o][b] * ISS_Q16_ROW_BYTES;
     }
     p.out1 = s.d_out[0];
     p.out2 = s.d_out[1];
     p.img_cap = c->img_cap;
     p.err_cap = c->err_cap;
+    p.tie_cap = kTieCap;
     p.amplicon = c->opts.sequence_type == ISS_SEQ_AMPLICON;
     p.gc_bias = c->opts.gc_bias;
     p.nchunk = (L + 15u) / 16u;
@@ -412,6 +416,7 @@ extern "C" {
 
 int iss_abi_version(void) { return ISS_ABI_VERSION; }
 const char *iss_last_error(void) { return g_err.c_str(); }
+void iss_set_last_error(const char *msg) { g_err = msg ? msg : ""; }  // for the other translation units of the library
 
 int iss_device_count(int *count) {
     CU(cudaGetDeviceCount(count));
@@ -436,6 +441,9 @@ int iss_ctx_create(int device, iss_ctx **out) {
     iss_ctx *c = new iss_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->stats.ring_numa_node = -1;
+    if (const char *e = getenv("ISS_RING_ALLOC"))
+        c->ring_alloc = !strcmp(e, "wc") ? ISS_HOSTMEM_WC : (!strcmp(e, "pinned") ? ISS_HOSTMEM_PINNED : ISS_HOSTMEM_NUMA);
     const int rc = [&]() -> int {
         CU(iss_kernel_configure(kMaxSmem));
         CU(iss_gz_init_device());
@@ -592,27 +600,19 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
     h.grp_begin[4] = h.n_grp = (uint32_t)grps.size();
     uint64_t off = align_up(sizeof(ModelHeader), 16);
     auto place = [&](uint64_t bytes) { uint64_t at = off; off = align_up(off + std::max<uint64_t>(bytes, 16), 16); return at; };
-    // 16-bit quality rows (layout: iss_kernels.cu).  Only populated bins get rows; G groups of 8 cover the live
-    // thresholds of every row plus one pad entry, so the last splitter of a row is always 0xFFFF.
+    // 16-bit quality rows (layout: iss_kernels.cu).  Only populated bins get rows.
     const bool kde = m->qual_mode == ISS_QUAL_KDE;
-    uint32_t q_groups = 1;
     if (kde) {
-        uint32_t max_live = 0;
         for (uint32_t o = 0; o < 2; ++o)
             for (uint32_t b = 0; b < 4; ++b) {
                 if (!m->bin_valid[o * 4 + b]) continue;
                 for (uint64_t pos = 0; pos < L; ++pos) {
                     const uint32_t *src = m->qual_thr + ((uint64_t)(o * 4 + b) * L + pos) * ISS_QROW;
-                    uint32_t live = 0;
-                    for (int j = 0; j < ISS_QROW; ++j) {
-                        if (j && src[j] < src[j - 1]) return fail(ISS_E_ARG, "qual_thr rows must be sorted");
-                        if (src[j] != 0xFFFFFFFFu) live = (uint32_t)j + 1;
-                    }
-                    max_live = std::max(max_live, live);
+                    for (int j = 1; j < ISS_QROW; ++j)
+                        if (src[j] < src[j - 1]) return fail(ISS_E_ARG, "qual_thr rows must be sorted");
+                    if (src[ISS_QROW - 1] != 0xFFFFFFFFu) return fail(ISS_E_ARG, "qual_thr rows need at least one 0xFFFFFFFF pad entry");
                 }
             }
-        if (max_live >= ISS_QROW) return fail(ISS_E_ARG, "qual_thr rows need at least one 0xFFFFFFFF pad entry");
-        q_groups = (max_live + 1 + 7) / 8;
         for (uint32_t o = 0; o < 2; ++o) {
             uint32_t nb = 0;
             for (uint32_t b = 0; b < 4; ++b) {
@@ -620,14 +620,13 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
                 if (m->bin_valid[o * 4 + b]) ++nb;
             }
             h.q16_nb[o] = std::max(nb, 1u);
+            h.q16_ps[o] = (uint32_t)align_up((uint64_t)h.q16_nb[o] * ISS_Q16_ROW_BYTES, 16);
         }
     }
-    h.q16_groups = q_groups;
-    h.q16_rs = 16u * ((1u + q_groups) | 1u);  // an odd number of 16-byte units: the rows of a position start in different banks
     h.frag_thr_off = place(8ull * m->n_frag);
     h.insert_thr_off = place(4ull * m->n_insert);
     h.qual_exact_off = place(kde ? 2ull * 4 * L * ISS_QROW * 4 : 0);
-    for (uint32_t o = 0; o < 2; ++o) h.q16_off[o] = place(kde ? (uint64_t)(L + 1) * h.q16_nb[o] * h.q16_rs : 0);
+    for (uint32_t o = 0; o < 2; ++o) h.q16_off[o] = place(kde ? (uint64_t)(L + 1) * h.q16_ps[o] : 0);
     h.subst_n_off = place(2ull * L * 4);
     h.subst_thr_off = place(2ull * L * 4 * ISS_MAX_ALT * 8);
     h.subst_alt_off = place(2ull * L * 4 * ISS_MAX_ALT);
@@ -647,15 +646,16 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
         put(h.qual_exact_off, m->qual_thr, 2ull * 4 * L * ISS_QROW * 4);
         for (uint32_t o = 0; o < 2; ++o) {
             uint8_t *base = blob.data() + h.q16_off[o];
-            memset(base, 0xFF, (size_t)(L + 1) * h.q16_nb[o] * h.q16_rs);  // pad rows / the pad position behind an odd L never count
+            memset(base, 0xFF, (size_t)(L + 1) * h.q16_ps[o]);  // pad entries / the pad position behind an odd L never count
             for (uint32_t b = 0; b < 4; ++b) {
                 if (!m->bin_valid[o * 4 + b]) continue;
                 for (uint64_t pos = 0; pos < L; ++pos) {
                     const uint32_t *src = m->qual_thr + ((uint64_t)(o * 4 + b) * L + pos) * ISS_QROW;
-                    uint16_t *row = reinterpret_cast<uint16_t *>(base + (pos * h.q16_nb[o] + h.q16_cbin[o][b]) * h.q16_rs);
-                    for (uint32_t k = 0; k < 7; ++k) row[k] = k < q_groups ? (uint16_t)(src[8 * k + 7] >> 16) : (uint16_t)0xFFFFu;
-                    row[7] = 0xFFFFu;
-                    for (uint32_t j = 0; j < 8 * q_groups; ++j) row[8 + j] = (uint16_t)(src[j] >> 16);
+                    uint8_t *row = base + pos * h.q16_ps[o] + (size_t)h.q16_cbin[o][b] * ISS_Q16_ROW_BYTES;  // 4-byte aligned
+                    for (uint32_t j = 0; j < ISS_QROW; ++j) {
+                        const uint16_t e = (uint16_t)(src[j] >> 16);
+                        memcpy(row + 2 * j, &e, 2);
+                    }
                 }
             }
         }
@@ -710,60 +710,73 @@ int iss_comm_init_all(iss_ctx **ctxs, int n) {
 
 int iss_ctx_bcast_all(iss_ctx **ctxs, int n, int root) {
     if (!ctxs || n < 1 || root < 0) return fail(ISS_E_ARG, "bad arguments");
-    for (int i = 0; i < n; ++i)
+    // every check that can fail happens BEFORE the first collective: a rank that returned early would leave its peers
+    // blocked inside ncclBroadcast
+    for (int i = 0; i < n; ++i) {
         if (!ctxs[i] || !ctxs[i]->comm) return fail(ISS_E_STATE, "communicator not initialised");
-    // 1. sizes
+        if (ctxs[i]->active) return fail(ISS_E_STATE, "generation in progress");
+        if (root >= ctxs[i]->nranks) return fail(ISS_E_ARG, "root is not a rank of the communicator");
+        if (ctxs[i]->rank == root) {
+            if (!ctxs[i]->have_genome || !ctxs[i]->have_model) return fail(ISS_E_STATE, "root has no genome/model");
+        }
+    }
     std::vector<uint64_t *> d_sizes(n, nullptr);
-    for (int i = 0; i < n; ++i) {
-        iss_ctx *c = ctxs[i];
-        CU(cudaSetDevice(c->device));
-        CU(cudaMalloc(&d_sizes[i], 16));
-        const bool is_root = (c->rank == root);
-        if (is_root) {
-            if (!c->have_genome || !c->have_model) return fail(ISS_E_STATE, "root has no genome/model");
-            uint64_t sz[2] = {c->genome_bytes, c->model_bytes};
-            CU(cudaMemcpy(d_sizes[i], sz, 16, cudaMemcpyHostToDevice));
+    auto free_sizes = [&] {
+        for (int i = 0; i < n; ++i)
+            if (d_sizes[i]) { cudaSetDevice(ctxs[i]->device); cudaFree(d_sizes[i]); d_sizes[i] = nullptr; }
+    };
+    const int rc = [&]() -> int {
+        // 1. sizes
+        for (int i = 0; i < n; ++i) {
+            iss_ctx *c = ctxs[i];
+            CU(cudaSetDevice(c->device));
+            CU(cudaMalloc(&d_sizes[i], 16));
+            if (c->rank == root) {
+                uint64_t sz[2] = {c->genome_bytes, c->model_bytes};
+                CU(cudaMemcpy(d_sizes[i], sz, 16, cudaMemcpyHostToDevice));
+            }
         }
-    }
-    NC(ncclGroupStart());
-    for (int i = 0; i < n; ++i) {
-        CU(cudaSetDevice(ctxs[i]->device));
-        NC(ncclBroadcast(d_sizes[i], d_sizes[i], 16, ncclUint8, root, ctxs[i]->comm, 0));
-    }
-    NC(ncclGroupEnd());
-    for (int i = 0; i < n; ++i) {
-        iss_ctx *c = ctxs[i];
-        CU(cudaSetDevice(c->device));
-        CU(cudaStreamSynchronize(0));
-        uint64_t sz[2];
-        CU(cudaMemcpy(sz, d_sizes[i], 16, cudaMemcpyDeviceToHost));
-        CU(cudaFree(d_sizes[i]));
-        const bool is_root = (c->rank == root);
-        if (!is_root) {
-            if (c->d_genome) { cudaFree(c->d_genome); c->d_genome = nullptr; }
-            if (c->d_model) { cudaFree(c->d_model); c->d_model = nullptr; }
-            CU(cudaMalloc(&c->d_genome, sz[0]));
-            CU(cudaMalloc(&c->d_model, sz[1]));
-            c->genome_bytes = sz[0];
-            c->model_bytes = sz[1];
+        NC(ncclGroupStart());
+        for (int i = 0; i < n; ++i) {
+            CU(cudaSetDevice(ctxs[i]->device));
+            NC(ncclBroadcast(d_sizes[i], d_sizes[i], 16, ncclUint8, root, ctxs[i]->comm, 0));
         }
-    }
-    // 2. blobs
-    NC(ncclGroupStart());
-    for (int i = 0; i < n; ++i) {
-        iss_ctx *c = ctxs[i];
-        CU(cudaSetDevice(c->device));
-        NC(ncclBroadcast(c->d_genome, c->d_genome, c->genome_bytes, ncclUint8, root, c->comm, 0));
-        NC(ncclBroadcast(c->d_model, c->d_model, c->model_bytes, ncclUint8, root, c->comm, 0));
-    }
-    NC(ncclGroupEnd());
-    for (int i = 0; i < n; ++i) {
-        iss_ctx *c = ctxs[i];
-        CU(cudaSetDevice(c->device));
-        CU(cudaStreamSynchronize(0));
-        if (int rc = rebuild_views(c)) return rc;
-    }
-    return ISS_OK;
+        NC(ncclGroupEnd());
+        for (int i = 0; i < n; ++i) {
+            iss_ctx *c = ctxs[i];
+            CU(cudaSetDevice(c->device));
+            CU(cudaStreamSynchronize(0));
+            uint64_t sz[2];
+            CU(cudaMemcpy(sz, d_sizes[i], 16, cudaMemcpyDeviceToHost));
+            if (c->rank != root) {
+                if (c->d_genome) { cudaFree(c->d_genome); c->d_genome = nullptr; }
+                if (c->d_model) { cudaFree(c->d_model); c->d_model = nullptr; }
+                c->have_genome = c->have_model = false;
+                CU(cudaMalloc(&c->d_genome, sz[0]));
+                CU(cudaMalloc(&c->d_model, sz[1]));
+                c->genome_bytes = sz[0];
+                c->model_bytes = sz[1];
+            }
+        }
+        // 2. blobs
+        NC(ncclGroupStart());
+        for (int i = 0; i < n; ++i) {
+            iss_ctx *c = ctxs[i];
+            CU(cudaSetDevice(c->device));
+            NC(ncclBroadcast(c->d_genome, c->d_genome, c->genome_bytes, ncclUint8, root, c->comm, 0));
+            NC(ncclBroadcast(c->d_model, c->d_model, c->model_bytes, ncclUint8, root, c->comm, 0));
+        }
+        NC(ncclGroupEnd());
+        for (int i = 0; i < n; ++i) {
+            iss_ctx *c = ctxs[i];
+            CU(cudaSetDevice(c->device));
+            CU(cudaStreamSynchronize(0));
+            if (int r = rebuild_views(c)) return r;
+        }
+        return ISS_OK;
+    }();
+    free_sizes();
+    return rc;
 }
 
 int iss_ctx_bcast(iss_ctx *c, int root) { return iss_ctx_bcast_all(&c, 1, root); }
@@ -807,17 +820,12 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     }
     uint32_t img_cap = 0;
     size_t smem = 0;
-    c->err_cap = 768;
+    c->err_cap = 512;
     // quality-row pipeline geometry: one stage = the 16-bit rows of 2 positions for the populated bins of an orientation
     const bool kde = c->mh.qual_mode == ISS_QUAL_KDE;
-    uint32_t q_shift = 1, q_dist = 1;
-    if (const char *e = getenv("ISS_QSTAGES")) {  // A/B switch for benchmarks: ring depth 2 or 4
-        if (atoi(e) == 4) q_shift = 2;
-    }
-    if (const char *e = getenv("ISS_QDIST")) q_dist = (uint32_t)std::max(1, std::min(atoi(e), (1 << q_shift) - 1));
-    const uint32_t q_cap = kde ? 2u * std::max(c->mh.q16_nb[0], c->mh.q16_nb[1]) * c->mh.q16_rs : 0u;
+    const uint32_t q_cap = kde ? 2u * std::max(c->mh.q16_ps[0], c->mh.q16_ps[1]) : 0u;
     auto layout = [&](uint32_t T_, uint32_t split) {
-        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, 2u << split, kde ? (1u << q_shift) : 0u, q_cap);
+        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, kTieCap, 2u << split, q_cap);
     };
     Lay lay{};
     for (;; T >>= 1) {
@@ -830,20 +838,18 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     if (4ull * c->err_cap < L) return fail(ISS_E_ARG, "read length too long for the indel replay scratch");
     int bps = 0;
     uint32_t split_shift = 1;
-    CU(iss_occupancy(T, split_shift, q_shift, smem, &bps));
+    CU(iss_occupancy(T, split_shift, smem, &bps));
     if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
     if (bps <= 2 && T == 64) {  // long reads: the images leave room for <= 2 CTAs/SM -> 4 threads per read keep 32 warps/SM
         int bps4 = 0;
         const Lay lay4 = layout(T, 2);
         if (lay4.total <= kMaxSmem) {
-            CU(iss_occupancy(T, 2, q_shift, lay4.total, &bps4));
+            CU(iss_occupancy(T, 2, lay4.total, &bps4));
             if (bps4 >= bps) { split_shift = 2; bps = bps4; lay = lay4; smem = lay4.total; }
         }
     }
     c->split_shift = split_shift;
     c->lay = lay;
-    c->q_stage_shift = q_shift;
-    c->q_dist = q_dist;
     c->q_stage_cap = q_cap;
     if (const char *e = getenv("ISS_BPS")) {  // A/B switch for benchmarks: fewer CTAs per SM (with ISS_CARVEOUT: more L1)
         const int cap = atoi(e);
@@ -853,7 +859,11 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     const uint32_t grid = (uint32_t)(c->sm_count * bps);
     const uint64_t slot_cap = align_up(batch_pairs * max_rec + 64, 256);
     const uint32_t max_segs = 1u << 16;
-    const bool realloc = c->slots.size() != o.n_slots || (o.compress && (c->slots.empty() || !c->slots[0].d_gz_out[0])) || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
+    // --store_mutations: room for every event a batch can produce at all -- per read at most L substitutions, 4 (L - 1)
+    // insertions and L - 1 deletions -- capped at 1 GB per slot (256 events per pair at the default batch size); a model
+    // that still overflows the cap gets ISS_E_DEVICE.
+    const uint64_t event_cap = c->mh.store_mutations ? std::min<uint64_t>(2ull * batch_pairs * (6ull * L), (1ull << 30) / sizeof(uint4)) + 1024 : 0;
+    const bool realloc = c->slots.size() != o.n_slots || (o.compress && (c->slots.empty() || !c->slots[0].d_gz_out[0])) || (c->mh.store_mutations && (c->slots.empty() || !c->slots[0].d_events || c->slots[0].event_cap < event_cap)) || c->slot_cap < slot_cap || c->max_segs != max_segs ||
                          (bool)c->opts.device_only != (c->slots.size() && c->slots[0].h_out[0] == nullptr);
     if (realloc) {
         free_slots(c);
@@ -862,11 +872,15 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             CU(cudaMalloc(&s.d_out[0], slot_cap));
             CU(cudaMalloc(&s.d_out[1], slot_cap));
             if (!o.device_only) {
-                CU(cudaMallocHost(&s.h_out[0], slot_cap));
-                CU(cudaMallocHost(&s.h_out[1], slot_cap));
+                for (int k = 0; k < 2; ++k) {
+                    CU((cudaError_t)iss_host_alloc(&s.h_buf[k], slot_cap, c->ring_alloc, c->device));
+                    s.h_out[k] = s.h_buf[k].ptr;
+                }
+                c->stats.ring_numa_node = s.h_buf[0].node;
+                c->stats.ring_alloc_mode = (uint32_t)s.h_buf[0].mode;
             }
             if (c->mh.store_mutations) {
-                s.event_cap = 32ull * batch_pairs + 1024;
+                s.event_cap = event_cap;
                 CU(cudaMalloc(&s.d_events, sizeof(uint4) * s.event_cap));
                 CU(cudaMalloc(&s.d_evcount, sizeof(unsigned long long)));
                 CU(cudaMallocHost(&s.h_evcount, sizeof(unsigned long long)));
@@ -911,7 +925,11 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     c->active = true;
     // prime the ring
     for (uint32_t si = 0; si < c->n_slots && !c->exhausted; ++si)
-        if (int rc = launch_batch(c, si)) return rc;
+        if (int rc = launch_batch(c, si)) {
+            const std::string msg = g_err;
+            iss_ctx_abort(c);  // a failed submit leaves a usable context
+            return fail(rc, msg);
+        }
     return ISS_OK;
 }
 
@@ -1004,6 +1022,22 @@ int iss_ctx_release(iss_ctx *c, const iss_batch *b) {
     if (b->slot >= c->slots.size() || c->slots[b->slot].state != 2) return fail(ISS_E_STATE, "batch is not held");
     c->slots[b->slot].state = 0;
     if (c->active && !c->exhausted) return launch_batch(c, b->slot);
+    return ISS_OK;
+}
+
+int iss_ctx_abort(iss_ctx *c) {
+    if (!c) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    for (auto &s : c->slots)
+        if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaGetLastError();
+    for (auto &s : c->slots) s.state = 0;
+    c->items.clear();
+    c->cur_item = c->cur_off = 0;
+    c->next_launch = c->next_return = 0;
+    c->active = false;
+    c->exhausted = false;
+    if (c->d_counters) CU(cudaMemset(c->d_counters + 2, 0, sizeof(unsigned long long)));
     return ISS_OK;
 }
 

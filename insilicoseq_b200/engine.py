@@ -8,6 +8,7 @@
 """
 import ctypes
 import logging
+import os
 
 import numpy as np
 
@@ -52,6 +53,7 @@ class Engine(object):
         self.read_length = None
         self.record_names = []
         self.record_lengths = []
+        self._records = {}  # id(record object) -> (device index, the object itself: the strong reference keeps the id unique)
         self.logger = logging.getLogger(__name__)
 
     # -- lifecycle ------------------------------------------------------------------------------------
@@ -95,6 +97,28 @@ class Engine(object):
         _lib.check(self._lib.iss_ctx_set_genome(self._h, arr, len(recs)))
         self.record_names = [n.decode() for _, n in keep]
         self.record_lengths = [len(b) for b, _ in keep]
+        self._records = {}
+
+    def register_records(self, records):
+        """Upload record objects (anything with .id and .seq) and remember each one's device index INSIDE the engine:
+        caller-owned records are not modified, and the same record may be registered with several engines."""
+        records = list(records)
+        self.set_genome([(r.id, r.seq) for r in records])
+        self._records = {id(r): (k, r) for k, r in enumerate(records)}
+        return records
+
+    def adopt_records(self, other):
+        """Share another engine's record map (the genome arrived by ncclBroadcast, same indices)."""
+        self._records = dict(other._records)
+
+    def record_index(self, record):
+        """Device index of a record passed to register_records (an int is taken as the index itself)."""
+        if isinstance(record, (int, np.integer)):
+            return int(record)
+        hit = self._records.get(id(record))
+        if hit is None or hit[1] is not record:
+            raise KeyError("record %r was not registered with this engine" % getattr(record, "id", record))
+        return hit[0]
 
     def set_model(self, model):
         tables = model.device_tables()
@@ -140,9 +164,8 @@ class Engine(object):
             e.record_lengths = list(src.record_lengths)
 
     # -- generation -------------------------------------------------------------------------------------
-    def submit(self, items, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0, device_only=False,
-               tma_gather=False, compress=False):
-        """items: iterable of dicts/tuples (record, cpu_number, n_pairs, i0, item_base, key)."""
+    @staticmethod
+    def _c_items(items):
         items = list(items)
         arr = (_lib.IssWorkItem * max(len(items), 1))()
         for k, it in enumerate(items):
@@ -153,14 +176,53 @@ class Engine(object):
             arr[k].i0 = i0
             arr[k].item_base = base
             arr[k].key = key & MASK64
+        return arr, len(items)
+
+    @staticmethod
+    def _c_opts(sequence_type, gc_bias, batch_pairs, n_slots, device_only, tma_gather, compress):
         st = {"metagenomics": 0, "amplicon": 1}
         if sequence_type not in st:
             # generator.py:139 raises RuntimeError for the forward read of an unknown sequence type
             raise RuntimeError("sequence type '%s' is not supported" % sequence_type)
-        opts = _lib.IssGenOpts(st[sequence_type], int(bool(gc_bias)), int(batch_pairs), int(n_slots), int(bool(device_only)),
+        return _lib.IssGenOpts(st[sequence_type], int(bool(gc_bias)), int(batch_pairs), int(n_slots), int(bool(device_only)),
                                int(bool(tma_gather)), int(bool(compress)))
+
+    def submit(self, items, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0, device_only=False,
+               tma_gather=False, compress=False):
+        """items: iterable of tuples (record, cpu_number, n_pairs, i0, item_base, key)."""
+        arr, n = self._c_items(items)
+        opts = self._c_opts(sequence_type, gc_bias, batch_pairs, n_slots, device_only, tma_gather, compress)
         self._device_only = bool(device_only)
-        _lib.check(self._lib.iss_ctx_submit(self._h, arr, len(items), ctypes.byref(opts)))
+        _lib.check(self._lib.iss_ctx_submit(self._h, arr, n, ctypes.byref(opts)))
+
+    def abort(self):
+        """Drop the rest of the current submit (waits for the batches in flight); the engine stays usable."""
+        _lib.check(self._lib.iss_ctx_abort(self._h))
+
+    def write_files(self, items, path_r1, path_r2, path_vcf=None, offset_r1=0, offset_r2=0, append=False, truncate=False,
+                    writer_threads=0, sequence_type="metagenomics", gc_bias=False, batch_pairs=0, n_slots=0,
+                    compress=False):
+        """Generate `items` and write the FASTQ (and VCF) bytes to files with the library's native writer threads:
+        every batch goes from its pinned ring slot to the file by pwrite(2); no Python object holds read bytes and the
+        GIL is released for the whole call.  append=False places this call's bytes at [offset_r1, ...) / [offset_r2, ...)
+        so several workers can fill ONE final file at disjoint, precomputed offsets (`fastq_bytes`).  A path of None
+        discards that stream after the copy to the host.  Returns the iss_write_stats fields as a dict."""
+        arr, n = self._c_items(items)
+        opts = self._c_opts(sequence_type, gc_bias, batch_pairs, n_slots, False, False, compress)
+        enc = lambda q: None if q is None else os.fsencode(q)  # noqa: E731
+        sink = _lib.IssFileSink(enc(path_r1), enc(path_r2), enc(path_vcf), int(offset_r1), int(offset_r2),
+                                int(bool(append)), int(bool(truncate)), int(writer_threads), 0)
+        st = _lib.IssWriteStats()
+        _lib.check(self._lib.iss_ctx_write_files(self._h, arr, n, ctypes.byref(opts), ctypes.byref(sink), ctypes.byref(st)))
+        return {k: getattr(st, k) for k, _ in _lib.IssWriteStats._fields_}
+
+    def fastq_bytes(self, items):
+        """Bytes of one FASTQ stream (R1 == R2) that `items` produce: the closed form the planner uses on the device."""
+        total = 0
+        for rec, cpu, n, i0, _base, _key in items:
+            total += int(self._lib.iss_fastq_bytes(len(self.record_names[rec].encode()), int(cpu), int(self.read_length),
+                                                   int(i0), int(i0) + int(n)))
+        return total
 
     def batches(self):
         b = _lib.IssBatch()

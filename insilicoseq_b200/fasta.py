@@ -6,7 +6,7 @@ whitespace removed, case preserved.  Sequences are kept as bytes (they go straig
 class Record(object):
     """The slice of Bio.SeqRecord the generator touches: .id, .description, .seq (bytes here), len()."""
 
-    __slots__ = ("id", "description", "seq", "gpu_index")
+    __slots__ = ("id", "description", "seq")
 
     def __init__(self, seq, id="", description=""):
         if isinstance(seq, str):
@@ -14,7 +14,6 @@ class Record(object):
         self.seq = seq
         self.id = id
         self.description = description
-        self.gpu_index = None
 
     def __len__(self):
         return len(self.seq)

@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-from . import abundance, error_models, fasta, util
+from . import _lib, abundance, error_models, fasta, util
 from .engine import Engine, worker_items
 
 
@@ -201,29 +201,46 @@ def generate_work_divider(fasta_file, readcount_dic, abundance_dic, n_reads, cov
 
 
 def register_records(engine, records):
-    """Upload records to the engine (once) and remember each record's device index."""
-    records = list(records)
-    engine.set_genome([(r.id, r.seq) for r in records])
-    for k, r in enumerate(records):
-        r.gpu_index = k
-    return records
+    """Upload records to the engine (once).  The record -> device index map lives inside the engine
+    (Engine.record_index); the caller's record objects are not touched."""
+    return engine.register_records(records)
 
 
-def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence_type, gc_bias, engine=None, compress=False):
+def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence_type, gc_bias, engine=None, compress=False,
+                    sink=None, stop=None):
     """Drop-in for iss/generator.py:223-251: writes {worker_prefix}_R1.fastq, _R2.fastq and .vcf for one work chunk.
 
-    work: list of (record, n_pairs, mode).  `engine` is an Engine that already holds the genome (records carry
-    .gpu_index) and the model; when omitted a private engine on GPU 0 is created for the call.  `compress=True` writes
-    {worker_prefix}_R1.fastq.gz / _R2.fastq.gz instead: gzip members produced on the GPU (`--compress`)."""
+    work: list of (record, n_pairs, mode).  `engine` is an Engine that already holds the genome and the model; when
+    omitted a private engine on GPU 0 is created for the call.  `compress=True` writes {worker_prefix}_R1.fastq.gz /
+    _R2.fastq.gz instead: gzip members produced on the GPU (`--compress`).  The bytes are written by the library's
+    native writer threads straight from the pinned ring (Engine.write_files): the reference's SeqIO.write loop
+    (generator.py:64-66) has no Python counterpart here.
+
+    sink (optional): dict(path_r1, path_r2, offset_r1, offset_r2) -- write this chunk's FASTQ at those offsets of the
+    FINAL files instead of {worker_prefix}_R1/_R2 temp files (plain text only: the sizes are closed-form), which removes
+    the parent's concatenation pass (iss/app.py:123-133).  The VCF always goes to {worker_prefix}.vcf.
+    stop (optional): threading.Event checked before the chunk starts (cooperative cancellation from the CLI)."""
     logger = logging.getLogger(__name__)
-    try:
-        ext = ".fastq.gz" if compress else ".fastq"
-        forward_handle = open(f"{worker_prefix}_R1{ext}", "wb")
-        reverse_handle = open(f"{worker_prefix}_R2{ext}", "wb")
-        mutation_handle = open(f"{worker_prefix}.vcf", "wb")
+    ext = ".fastq.gz" if compress else ".fastq"
+    vcf_path = f"{worker_prefix}.vcf"
+    if sink is None:
+        paths = (f"{worker_prefix}_R1{ext}", f"{worker_prefix}_R2{ext}")
+        offsets = (0, 0)
+    else:
+        if compress:
+            raise ValueError("final-offset writes need plain FASTQ (compressed sizes are not known in advance)")
+        paths = (sink["path_r1"], sink["path_r2"])
+        offsets = (int(sink["offset_r1"]), int(sink["offset_r2"]))
+    try:  # the reference opens its three files before anything else and exits on failure (generator.py:226-232)
+        for q in (paths if sink is None else ()) + (vcf_path,):
+            open(q, "wb").close()
     except PermissionError as e:
         logger.error("Failed to write temporary output file(s): %s" % e)
         sys.exit(1)
+    if sequence_type not in ("metagenomics", "amplicon"):
+        raise RuntimeError(f"sequence type '{sequence_type}' is not supported")
+    if stop is not None and stop.is_set():
+        return None
     own = engine is None
     if own:
         engine = Engine(0)
@@ -233,23 +250,24 @@ def worker_iterator(work, error_model, cpu_number, worker_prefix, seed, sequence
             if id(rec) not in seen:
                 seen.add(id(rec))
                 uniq.append(rec)
-        register_records(engine, uniq)
+        engine.register_records(uniq)
         engine.set_model(error_model)
     if seed is None:  # the reference leaves its RNGs unseeded: any stream will do
         seed = random.SystemRandom().getrandbits(63)
     try:
-        with forward_handle, reverse_handle, mutation_handle:
-            if sequence_type not in ("metagenomics", "amplicon"):
-                raise RuntimeError(f"sequence type '{sequence_type}' is not supported")
-            for rec, n_pairs, _ in work:
-                logger.debug("Cpu #%s: Generating %s read pairs" % (cpu_number, n_pairs))
-            items = worker_items([(rec.gpu_index, n) for rec, n, _ in work], cpu_number, seed, engine.record_lengths,
-                                 engine.read_length, logger=logger, record_names=engine.record_names)
-            for batch in engine.generate(items, sequence_type=sequence_type, gc_bias=gc_bias, compress=compress):
-                forward_handle.write(memoryview(batch.r1))
-                reverse_handle.write(memoryview(batch.r2))
-                if batch.vcf is not None:
-                    mutation_handle.write(memoryview(batch.vcf))
+        for rec, n_pairs, _ in work:
+            logger.debug("Cpu #%s: Generating %s read pairs" % (cpu_number, n_pairs))
+        items = worker_items([(engine.record_index(rec), n) for rec, n, _ in work], cpu_number, seed, engine.record_lengths,
+                             engine.read_length, logger=logger, record_names=engine.record_names)
+        try:
+            return engine.write_files(items, paths[0], paths[1], vcf_path, offset_r1=offsets[0], offset_r2=offsets[1],
+                                      append=False, truncate=False, sequence_type=sequence_type, gc_bias=gc_bias,
+                                      compress=compress)
+        except _lib.NativeError as e:
+            if e.code == _lib.ISS_E_IO:  # same convention as the reference for I/O trouble: log, exit(1)
+                logger.error("Failed to write temporary output file(s): %s" % e)
+                sys.exit(1)
+            raise
     finally:
         if own:
             engine.close()
@@ -271,20 +289,20 @@ class Read(object):
         return "@%s\n%s\n+\n%s\n" % (self.id, self.seq, "".join(chr(q + 33) for q in self.letter_annotations["phred_quality"]))
 
 
-_private_engines = {}
+_private_engines = []  # [(record, error_model, device, engine)]: strong references, compared by identity
 
 
 def _engine_for(record, error_model, device=0):
     """One cached engine per (record, model) pair for the single-pair API below."""
-    key = (id(record), id(error_model), device)
-    eng = _private_engines.get(key)
-    if eng is None:
-        if len(_private_engines) >= 4:
-            _private_engines.pop(next(iter(_private_engines))).close()
-        eng = Engine(device)
-        register_records(eng, [record])
-        eng.set_model(error_model)
-        _private_engines[key] = eng
+    for rec, em, dev, eng in _private_engines:
+        if rec is record and em is error_model and dev == device:
+            return eng
+    if len(_private_engines) >= 4:
+        _private_engines.pop(0)[3].close()
+    eng = Engine(device)
+    eng.register_records([record])
+    eng.set_model(error_model)
+    _private_engines.append((record, error_model, device, eng))
     return eng
 
 
@@ -306,7 +324,7 @@ def simulate_read(record, error_model, i, cpu_number, sequence_type, seed=0, ite
 
     assert int(error_model.read_length) < len(record.seq)
     eng = engine or _engine_for(record, error_model)
-    item = (record.gpu_index, int(cpu_number), 1, int(i), int(item_base), philox_key(seed, cpu_number))
+    item = (eng.record_index(record), int(cpu_number), 1, int(i), int(item_base), philox_key(seed, cpu_number))
     out = None
     for batch in eng.generate([item], sequence_type=sequence_type):
         out = _parse_pair(batch.r1, batch.r2)
@@ -330,7 +348,7 @@ def simulate_reads(record, error_model, n_pairs, cpu_number, forward_handle, rev
         logger.warning("Skipping %s. You will have less reads than specified" % record.id)
         return
     eng = engine or _engine_for(record, error_model)
-    item = (record.gpu_index, int(cpu_number), int(n_pairs), 0, int(item_base), philox_key(seed, cpu_number))
+    item = (eng.record_index(record), int(cpu_number), int(n_pairs), 0, int(item_base), philox_key(seed, cpu_number))
 
     def put(handle, view):
         data = bytes(view)

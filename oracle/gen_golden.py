@@ -82,6 +82,80 @@ def write_full_model(path, base_npz, seed):
         np.savez_compressed(fh, **out)
 
 
+def write_tie_model(path, base_npz, seed):
+    """Quality CDF rows whose 32-bit thresholds collide in their top 16 bits: every row is a few clusters of CDF values
+    2**-26 .. 2**-19 apart (plus plateaus of equal values), so a draw whose top 16 bits hit a cluster must be resolved by the
+    exact 32-bit compare, several entries deep.  The kernel searches quality rows on 16 bits first (iss_kernels.cu)."""
+    d = np.load(base_npz, allow_pickle=True)
+    L = int(d["read_length"])
+    rng = np.random.RandomState(seed)
+    out = {k: d[k] for k in d.files}
+    for orient in ("forward", "reverse"):
+        hist = np.empty(4, dtype=object)
+        for b in range(4):
+            rows = []
+            for _pos in range(L):
+                centers = np.sort(rng.rand(6))
+                vals = []
+                for c in centers:
+                    k = int(rng.randint(3, 9))
+                    step = 2.0 ** -int(rng.randint(19, 27))
+                    base = np.floor(c * 65536) / 65536 + rng.randint(0, 200) * 2.0 ** -32
+                    inc = np.cumsum(rng.randint(0, 3, size=k)) * step  # zeros -> equal neighbours (plateaus)
+                    vals.extend(base + inc)
+                vals = np.sort(np.clip(np.array(vals), 0.0, 1.0))[:40]
+                row = np.concatenate([vals, np.ones(41 - len(vals))])
+                rows.append(row.astype(np.float64))
+            hist[b] = rows
+        out["quality_hist_" + orient] = hist
+        out["mean_count_" + orient] = np.array([5, 20, 40, 35], dtype=np.int64)
+    with open(path, "wb") as fh:
+        np.savez_compressed(fh, **out)
+
+
+def write_flat_quality_model(path, base_npz, levels, lo=0):
+    """Every quality row is the CDF of a uniform distribution over `levels` phred values lo .. lo + levels - 1.
+    levels=60: 60 distinct 16-bit prefixes per row, so long reads overflow the kernel's tie queue now and then;
+    lo=2, levels=3: phred 2-4, i.e. about every other base a substitution -- the substitution list of a tile overflows and
+    the kernel's exact pass takes over."""
+    d = np.load(base_npz, allow_pickle=True)
+    L = int(d["read_length"])
+    out = {k: d[k] for k in d.files}
+    row = np.concatenate([np.zeros(lo), np.arange(1, levels + 1) / float(levels)])
+    row = np.concatenate([row, np.ones(max(0, 41 - len(row)))])
+    for orient in ("forward", "reverse"):
+        hist = np.empty(4, dtype=object)
+        for b in range(4):
+            hist[b] = [row.copy() for _ in range(L)]
+        out["quality_hist_" + orient] = hist
+        out["mean_count_" + orient] = np.array([1, 2, 3, 4], dtype=np.int64)
+    with open(path, "wb") as fh:
+        np.savez_compressed(fh, **out)
+
+
+def write_long_model(path, base_npz, reps):
+    """The per-position arrays of a bundled profile repeated `reps` times: a read length beyond ~860, where a record no
+    longer fits a 64-pair tile and the kernel falls back to 32-pair tiles."""
+    d = np.load(base_npz, allow_pickle=True)
+    L = int(d["read_length"])
+    out = {k: d[k] for k in d.files}
+    out["read_length"] = np.int64(L * reps)
+    for orient in ("forward", "reverse"):
+        q = d["quality_hist_" + orient]
+        hist = np.empty(len(q), dtype=object)
+        for b in range(len(q)):
+            hist[b] = list(q[b]) * reps if len(q[b]) else []
+        out["quality_hist_" + orient] = hist
+        for key in ("subst_choices_", "ins_", "del_"):
+            arr = d[key + orient]
+            rep = np.empty(len(arr) * reps, dtype=object)
+            for k in range(len(rep)):
+                rep[k] = arr[k % len(arr)]
+            out[key + orient] = rep
+    with open(path, "wb") as fh:
+        np.savez_compressed(fh, **out)
+
+
 def sha(b):
     return hashlib.sha256(b).hexdigest()
 
@@ -97,6 +171,11 @@ def build_cases():
     oracle.truncate_profile(os.path.join(MODELS, "stress20.npz"), os.path.join(MODELS, "stress3.npz"), 3)
     for n in (2, 16, 17):  # around the 16-base chunk of the gather and the smallest length the indel loop accepts
         oracle.truncate_profile(os.path.join(MODELS, "stress20.npz"), os.path.join(MODELS, "stress%d.npz" % n), n)
+
+    write_tie_model(os.path.join(MODELS, "ties20.npz"), os.path.join(MODELS, "ecoli.npz"), 11)
+    write_long_model(os.path.join(MODELS, "novaseq_x6.npz"), os.path.join(REF_PROFILES, "NovaSeq"), 6)
+    write_flat_quality_model(os.path.join(MODELS, "flat60_x6.npz"), os.path.join(MODELS, "novaseq_x6.npz"), 60)
+    write_flat_quality_model(os.path.join(MODELS, "lowq20.npz"), os.path.join(MODELS, "ecoli.npz"), 3, lo=2)
 
     cases = []
 
@@ -154,6 +233,12 @@ def build_cases():
         cases.append(dict(name="read_length_%d" % n, model="models/stress%d.npz" % n, seed=100 + n, cpu=1, store_mutations=(n == 17),
                           records=[rec("q%d" % n, 200 + n, 150 + n, frac_lower=0.1, n_runs=1, iupac="N"), rec("pure%d" % n, 90, 160 + n)],
                           work=[[0, 90], [1, 70]], inline=True))
+    cases.append(dict(name="quality_ties_16bit", model="models/ties20.npz", seed=606, cpu=0,
+                      records=[rec("tie_rec", 3000, 170)], work=[[0, 2500]], inline=False))
+    cases.append(dict(name="long_reads_906", model="models/novaseq_x6.npz", seed=907, cpu=2,
+                      records=[rec("long_a", 9000, 171), rec("long_b", 2100, 172)], work=[[0, 70], [1, 31]], inline=False))
+    cases.append(dict(name="low_quality_overflow", model="models/lowq20.npz", seed=808, cpu=1, store_mutations=True,
+                      records=[rec("lq", 2000, 173)], work=[[0, 400]], inline=False))
     cases.append(dict(name="long_names_cpu_digits", model="profile:NovaSeq", seed=4242, cpu=40950,
                       records=[rec("NZ_" + "contig.with.a.long.name|" * 3 + "end", 2600, 144), rec("x", 1900, 145)],
                       work=[[0, 33], [1, 70]], inline=True))

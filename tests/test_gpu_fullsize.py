@@ -89,7 +89,7 @@ def test_metagenome_many_records_matches_oracle():
         generator.register_records(e, recs)
         e.set_model(model)
         for cpu, work in enumerate(chunks[:cpus]):
-            items = eng_mod.worker_items([(r.gpu_index, n) for r, n, _ in work], cpu, 7, e.record_lengths, e.read_length)
+            items = eng_mod.worker_items([(e.record_index(r), n) for r, n, _ in work], cpu, 7, e.record_lengths, e.read_length)
             got1 = b"".join(b.r1.tobytes() for b in e.generate(items, batch_pairs=5000))
             exp1, _ = oracle.run_worker(om, [(r.id, r.seq, n) for r, n, _ in work], cpu, 7)
             assert hashlib.sha256(got1).digest() == hashlib.sha256(exp1).digest()

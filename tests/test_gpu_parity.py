@@ -77,7 +77,11 @@ def test_batch_size_invariance(name, batch_pairs):
 
 
 @pytest.mark.parametrize("spec,npairs", [("models/miseq_150.npz", 20000), ("profile:MiSeq", 6000),
-                                        ("profile:HiSeq", 20000), ("models/stress20.npz", 30000)])
+                                        ("profile:HiSeq", 20000), ("models/stress20.npz", 30000),
+                                        ("models/ties20.npz", 120000),     # thresholds colliding in their top 16 bits
+                                        ("models/novaseq_x6.npz", 1500),   # L = 906: 32-pair tiles
+                                        ("models/flat60_x6.npz", 1500),    # 60 distinct prefixes x 58 k draws per tile: tie queue overflows
+                                        ("models/lowq20.npz", 30000)])     # phred 2-4: substitution list overflows, exact pass
 def test_against_oracle_at_scale(spec, npairs):
     """Sizes the C oracle finishes in seconds; byte-identical streams."""
     case = dict(model=spec, seed=20260924, cpu=5, records=[dict(id="scale_a", synth_seed=7, length=150000),
@@ -92,6 +96,89 @@ def test_against_oracle_at_scale(spec, npairs):
     assert first_diff(r2, o2) is None
     if spec in ("profile:MiSeq", "models/stress20.npz"):
         assert stats["slow_reads"] > 0  # the sequential indel replay really ran
+
+
+@pytest.mark.parametrize("name", ["miseq150_bench_model", "stress_indels_dense", "hiseq_multi_short", "quality_ties_16bit",
+                                  "nextseq_large_digest", "read_length_2"])
+def test_128_pair_tiles(name, monkeypatch):
+    """ISS_TILE=128: 512-thread CTAs, four warps per position stream (four arrivals per `empty` barrier of the quality-row ring)."""
+    monkeypatch.setenv("ISS_TILE", "128")
+    case, exp = fixtures.load_case(name)
+    r1, r2, _ = run_product(case, batch_pairs=300)
+    assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
+    assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
+
+
+@pytest.mark.parametrize("stages,dist", [("4", "1"), ("4", "3")])
+def test_quality_row_ring_depths(stages, dist, monkeypatch):
+    """The quality-row ring with 4 stages and prefetch distance 1 / 3 (default: 2 stages, distance 1)."""
+    monkeypatch.setenv("ISS_QSTAGES", stages)
+    monkeypatch.setenv("ISS_QDIST", dist)
+    for name in ("miseq150_bench_model", "long_reads_906", "read_length_3"):
+        case, exp = fixtures.load_case(name)
+        r1, r2, _ = run_product(case, batch_pairs=500)
+        assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
+        assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
+
+
+def test_native_file_writer(tmp_path):
+    """Engine.write_files (iss_ctx_write_files): the FASTQ / VCF bytes land in files through the library's pwrite threads,
+    at given offsets of a shared final file (two workers, plain text) or appended (gzip members)."""
+    import gzip
+
+    from insilicoseq_b200 import engine as eng_mod
+    from insilicoseq_b200 import error_models
+
+    case, exp = fixtures.load_case("ecoli_kde_vcf")
+    recs = fixtures.materialise_records(case)
+    with eng_mod.Engine(0) as e:
+        e.set_genome([(n, s.encode()) for n, s in recs])
+        e.set_model(error_models.KDErrorModel(fixtures.model_path(case["model"]), store_mutations=True))
+        work = case["work"]
+        items0 = eng_mod.worker_items(work, case["cpu"], case["seed"], e.record_lengths, e.read_length)
+        items1 = eng_mod.worker_items(work, case["cpu"] + 1, case["seed"], e.record_lengths, e.read_length)
+        n0, n1 = e.fastq_bytes(items0), e.fastq_bytes(items1)
+        assert n0 == len(exp["R1"])
+        f1, f2, v = str(tmp_path / "final_R1.fastq"), str(tmp_path / "final_R2.fastq"), str(tmp_path / "w.vcf")
+        for f in (f1, f2):
+            with open(f, "wb") as fh:
+                fh.truncate(n0 + n1)
+        st1 = e.write_files(items1, f1, f2, None, offset_r1=n0, offset_r2=n0, batch_pairs=17)  # second worker first
+        st0 = e.write_files(items0, f1, f2, v, offset_r1=0, offset_r2=0, batch_pairs=23)
+        assert st0["bytes_r1"] == n0 and st1["bytes_r1"] == n1 and st0["n_pairs"] == sum(n for _, n in work)
+        got1, got2 = open(f1, "rb").read(), open(f2, "rb").read()
+        assert got1[:n0] == exp["R1"] and got2[:n0] == exp["R2"]
+        again = b"".join(b.r1.tobytes() for b in e.generate(items1))
+        assert got1[n0:] == again
+        assert open(v, "rb").read() == exp["vcf"]
+        # appended gzip members
+        z1, z2 = str(tmp_path / "a_R1.fastq.gz"), str(tmp_path / "a_R2.fastq.gz")
+        e.write_files(items0, z1, z2, None, append=True, truncate=True, compress=True, batch_pairs=31)
+        e.write_files(items1, z1, z2, None, append=True, compress=True, batch_pairs=31)
+        assert gzip.decompress(open(z1, "rb").read()) == got1 and gzip.decompress(open(z2, "rb").read()) == got2
+        # a path that cannot be opened: ISS_E_IO, and the engine stays usable
+        from insilicoseq_b200 import _lib
+
+        with pytest.raises(_lib.NativeError) as err:
+            e.write_files(items0, str(tmp_path / "no_such_dir" / "x"), f2)
+        assert err.value.code == _lib.ISS_E_IO
+        assert b"".join(b.r1.tobytes() for b in e.generate(items0)) == exp["R1"]
+
+
+def test_abort_leaves_a_usable_context():
+    """iss_ctx_abort drops a half-consumed submit; the next submit starts from a clean ring."""
+    from insilicoseq_b200 import engine as eng_mod
+    from insilicoseq_b200 import error_models
+
+    case, exp = fixtures.load_case("novaseq_single")
+    recs = fixtures.materialise_records(case)
+    with eng_mod.Engine(0) as e:
+        e.set_genome([(n, s.encode()) for n, s in recs])
+        e.set_model(error_models.KDErrorModel(fixtures.model_path(case["model"])))
+        items = eng_mod.worker_items(case["work"], case["cpu"], case["seed"], e.record_lengths, e.read_length)
+        e.submit(items, batch_pairs=5)
+        e.abort()
+        assert b"".join(b.r1.tobytes() for b in e.generate(items, batch_pairs=7)) == exp["R1"]
 
 
 def test_error_conventions_at_the_c_abi():

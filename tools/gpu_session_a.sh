@@ -7,7 +7,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
 ( timeout 120 python __graft_entry__.py smoke ) > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.txt
-( timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.txt
+( timeout 1200 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.txt
 tail -5 $OUT/pytest_gpu.log | tee -a $OUT/summary.txt
 ( timeout 600 python bench.py --steps 5 --warmup 3 ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err; echo "bench rc=$?" | tee -a $OUT/summary.txt
 python - <<PY | tee -a $OUT/summary.txt
@@ -18,18 +18,7 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
-for cfg in "4 1" "4 2" "4 3"; do
-  set -- $cfg
-  ( ISS_QSTAGES=$1 ISS_QDIST=$2 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/bench_q$1_d$2.json 2>> $OUT/bench_ab.err
-  python - <<PY | tee -a $OUT/summary.txt
-import json
-try:
-    d=json.loads(open("$OUT/bench_q$1_d$2.json").read().strip().splitlines()[-1])
-    print("stages $1 dist $2: value %.4g launch_ms %.3f" % (d["value"], d["roofline"]["avg_launch_ms"]))
-except Exception as e:
-    print("ab parse failed", e)
-PY
-done
+( timeout 120 python tools/d2h_probe.py --seconds 0.7 --out $OUT/d2h_probe_n1.json ) > $OUT/d2h_probe_n1.log 2>&1; echo "probe rc=$?" | tee -a $OUT/summary.txt
 ( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline ) > $OUT/ncu_list.log 2>&1
 ( timeout 900 ncu --set full --clock-control none --import-source on -k regex:iss_generate_kernel -s 6 -c 1 -o $OUT/gen_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/gen_full.ncu-rep --page details > $OUT/ncu_details.txt 2>&1
