@@ -10,6 +10,8 @@
 
 #define ISS_QROW 64
 #define ISS_MAX_ALT 4
+#define ISS_SLOW_SLOTS 16
+#define ISS_SURV_CAP 64  // queued indel-site survivors per tile before the scan falls back to a second walk
 #define ISS_Q16_ROW_BYTES 132  // a 16-bit quality row: ISS_QROW u16 entries + 4 bytes, so that the rows of a position start in different banks
 
 // ---------------------------------------------------------------------------------------------
@@ -208,9 +210,11 @@ struct Lay {
     uint32_t sErr;     // u32[err_cap]
     uint32_t sErrThr;  // u32[64]
     uint32_t sTie;     // u32[tie_cap] positions whose 16-bit quality search met a tie (read << 16 | position)
-    uint32_t sTie2;    // u32[tie_cap] those of them that turned out to be substitution errors
-    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 2 gather-mbarrier parity, 3 bytes of the tile's last record, 4 nTie, 5 nTie2;
-                       //         +24: mbarrier of the TMA genome gather
+    uint32_t sSurv;    // u32[ISS_SURV_CAP] indel sites whose draw passed, to be checked against the base under them
+                       //         (read << 24 | site bits << 16 | position)
+    uint32_t sCtl;     // u32[8]: 0 nErr, 1 nSlow, 2 gather-mbarrier parity, 3 bytes of the tile's last record, 4 nTie, 6 nSurv;
+                       //         +28: (unused); the mbarrier of the TMA genome gather has its own 8 bytes behind (sGbar)
+    uint32_t sGbar;    // u64 mbarrier of the TMA genome gather
     uint32_t sBar;     // u64[n_streams][2 stages][2]: {full, empty} mbarriers of the quality-row pipeline
     uint32_t sQst;     // [n_streams][2 stages][q_stage_cap] staged 16-bit quality rows (2 positions per stage)
     uint32_t total;    // bytes of dynamic shared memory
@@ -239,8 +243,9 @@ __host__ __device__ inline Lay iss_make_layout(uint32_t T, uint32_t img_cap, uin
     l.sErr = q; q += 4u * err_cap;
     l.sErrThr = q; q += 4u * ISS_QROW;
     l.sTie = q; q += 4u * tie_cap;
-    l.sTie2 = q; q += 4u * tie_cap;
+    l.sSurv = q; q += 4u * ISS_SURV_CAP;
     l.sCtl = q; q += 32u;
+    l.sGbar = q; q += 16u;
     l.sBar = q; q += 16u * n_streams * q_stages;
     l.sQst = q; q += n_streams * q_stages * q_stage_cap;
     l.total = q;
@@ -288,9 +293,9 @@ struct GenParams {
     uint32_t chunk_magic;     // ceil(2^32 / nchunk) for idx / nchunk (unused when nchunk == 1: the value would be 2^32)
     uint32_t nchunk;          // ceil(L / 16)
     uint8_t *scratch;         // slow-path scratch: gridDim.x * ISS_SLOW_SLOTS * scratch_stride bytes
-    uint32_t scratch_stride;  // >= 5L + 8
+    uint32_t scratch_stride;  // per replayed read: L original bases + 4L stack + L draw masks (+ alignment)
+    uint32_t scratch_mask_off;  // offset of the draw masks inside a slot's scratch (multiple of 4)
     uint32_t gc_thr;          // accept iff w < gc_thr  (ceil(0.90 * 2^32))
-    uint32_t slow_slots;      // reads replayed per round: min(ISS_SLOW_SLOTS, 4 * err_cap / L) (their draw masks alias the substitution list)
     unsigned long long *counters;  // [0] slow reads [1] substitution events [2] error flags
     uint32_t store_mutations;
     uint32_t tma_gather;           // 1: genome windows are staged into shared memory with cp.async.bulk (needs 15 + stage_bytes <= L)
@@ -301,7 +306,6 @@ struct GenParams {
     unsigned long long event_cap;
 };
 
-#define ISS_SLOW_SLOTS 16
 #define ISS_DEVERR_RANGE 1u
 #define ISS_DEVERR_QUALBIN 2u
 #define ISS_DEVERR_CHAR 4u

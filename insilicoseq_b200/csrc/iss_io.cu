@@ -10,6 +10,7 @@
 // Also here: iss_probe_d2h, the measurement behind the choice of ring memory (profiles/r2_d2h_probe.*).
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <nvtx3/nvToolsExt.h>
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -140,6 +141,7 @@ int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_ite
             rc = iss_ctx_next(ctx, &b, &have);
             if (rc != ISS_OK || !have) break;
             const double w0 = now_ms();
+            nvtxRangePushA("iss:write_batch");
             const uint8_t *src[2] = {b.r1, b.r2};
             const uint64_t len[2] = {b.nbytes, b.nbytes2};
             for (int k = 0; k < 2; ++k) {
@@ -157,6 +159,7 @@ int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_ite
                 st.bytes_vcf += b.vcf_bytes;
             }
             const int e = pool.wait();  // the slot may be refilled once it is released
+            nvtxRangePop();
             if (e && !io_err) io_err = e;
             st.write_ms += now_ms() - w0;
             st.bytes_r1 += b.nbytes;

@@ -65,21 +65,28 @@ __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_
 // the search stops at: e[count] == w16 (~ 41 / 65536 of the draws) defers the position to the exact pass (phase 4b), which
 // evaluates it on the 32-bit row -- nothing is called from the hot loop.
 // row_off: offset of the read's staged row from iss_smem
-// row: shared-window address of the read's staged row (smem_addr(iss_smem) + offset)
-__device__ __forceinline__ uint32_t q16_search(uint32_t row, uint32_t w16, bool &tie) {
-    uint32_t a = row;
+// rowA / rowB: shared-window addresses of the read's staged rows at two positions (smem_addr(iss_smem) + offset).  The
+// two lower-bound searches are independent chains of 7 dependent LDS; stepping them together halves what a warp waits.
+__device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t &qA, uint32_t &qB,
+                                            bool &tieA, bool &tieB) {
+    uint32_t a = rowA, b = rowB;
 #define ISS_Q16_STEP(S)                                                                                              \
     {                                                                                                                \
-        uint32_t e;                                                                                                  \
-        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(e) : "r"(a));                                       \
-        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(a) : "r"(w16), "r"(e)); \
+        uint32_t ea, eb;                                                                                             \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ea) : "r"(a));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(eb) : "r"(b));                                      \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(a) : "r"(wA), "r"(ea)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(b) : "r"(wB), "r"(eb)); \
     }
     ISS_Q16_STEP(32) ISS_Q16_STEP(16) ISS_Q16_STEP(8) ISS_Q16_STEP(4) ISS_Q16_STEP(2) ISS_Q16_STEP(1)
 #undef ISS_Q16_STEP
-    uint32_t e;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(a));
-    tie = e == w16;
-    return (a - row) >> 1;
+    uint32_t ea, eb;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ea) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(eb) : "r"(b));
+    tieA = ea == wA;
+    tieB = eb == wB;
+    qA = (a - rowA) >> 1;
+    qB = (b - rowB) >> 1;
 }
 
 // queue (read, position) for the exact pass; a full queue makes the whole tile take it (ctl word 5)
@@ -105,6 +112,27 @@ __device__ __noinline__ uint32_t quality_exact(const GenParams &p, uint32_t rd, 
     for (uint32_t s = 32; s >= 1; s >>= 1)
         if (wq > __ldg(row + c + s - 1u)) c += s;  // row[63] == 0xFFFFFFFF: c <= 63
     return c;
+}
+
+// 8 two-bit codes (16 bits) -> 8 nibbles: the selectors of two PRMTs into "ACTG"
+__device__ __forceinline__ uint32_t spread_codes(uint32_t h) {
+    uint32_t x = (h | (h << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    return (x | (x << 2)) & 0x33333333u;
+}
+// the four bytes of v to shared-window addresses a + kOff .. a + kOff + 3 (no alignment assumed)
+template <int kOff>
+__device__ __forceinline__ void sts_word_bytes(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v), "n"(kOff) : "memory");
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v >> 8), "n"(kOff + 1) : "memory");
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v >> 16), "n"(kOff + 2) : "memory");
+    asm volatile("st.shared.u8 [%0+%2], %1;" ::"r"(a), "r"(v >> 24), "n"(kOff + 3) : "memory");
+}
+template <int kOff>
+__device__ __forceinline__ void sts_word_bytes_n(uint32_t a, uint32_t v, uint32_t n) {  // only bytes with index < n
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if ((uint32_t)(kOff + t) < n) asm volatile("st.shared.u8 [%0], %1;" ::"r"(a + kOff + t), "r"(v >> (8 * t)) : "memory");
 }
 
 __device__ __forceinline__ uint32_t genome_ascii(const DevGenome &g, uint32_t enc, uint64_t abs_pos) {
@@ -281,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
     const Lay &l = p.lay;
     if (tid < ISS_QROW) u32p(l.sErrThr)[tid] = p.err_thr[tid];
     const uint32_t smem0 = smem_addr(iss_smem);
-    const uint32_t mbar = smem0 + l.sCtl + 24u;                 // 8-byte mbarrier behind the control words
+    const uint32_t mbar = smem0 + l.sGbar;                      // mbarrier of the TMA genome gather
     if (tid == 0) {
         u32p(l.sCtl)[2] = 0;
         if (p.tma_gather) mbar_init(mbar, 2u * T);  // every (pair, orientation) thread arrives once per tile
@@ -340,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         //      before the barrier that ends the phase.
         if (tid == 0) {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // returns at once when nothing is pending
-            u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0; u32p(l.sCtl)[4] = 0; u32p(l.sCtl)[5] = 0;
+            u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0; u32p(l.sCtl)[4] = 0; u32p(l.sCtl)[6] = 0;
             u32p(l.sCtl)[2] ^= 1u;  // phase parity of the gather mbarrier for this tile (1, 0, 1, ... ; read as parity ^ 1)
         }
         if (tid < 2u * T) u32p(l.sFlag)[tid] = 0;
@@ -505,11 +533,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         w1 = __ldg(p.g.packed + wi + 1);
                     }
                     uint32_t w = __funnelshift_r(w0, w1, sh);
-                    if (ro) w ^= 0xAAAAAAAAu;  // complement every base: code ^ 2
-#pragma unroll
-                    for (uint32_t m = 0; m < 16; ++m) {
-                        const uint32_t k = ro ? (16u * j + 15u - m) : (16u * j + m);
-                        if (k < L) seq[k] = (uint8_t)code_to_ascii((w >> (2u * m)) & 3u);
+                    if (ro) {  // reverse complement of the 16 bases: complement = code ^ 2, then the 2-bit fields in reverse order
+                        w = __brev(w ^ 0xAAAAAAAAu);
+                        w = ((w & 0xAAAAAAAAu) >> 1) | ((w & 0x55555555u) << 1);
+                    }
+                    // base m of w -> position 16 j + m of the read, for both strands.  2-bit codes -> PRMT selector nibbles
+                    // (8 bases per 32-bit selector pair) -> four ASCII words -> byte stores (the line has no alignment).
+                    const uint32_t s0 = spread_codes(w & 0xFFFFu), s1 = spread_codes(w >> 16);
+                    const uint32_t W0 = __byte_perm(0x47544341u, 0u, s0), W1 = __byte_perm(0x47544341u, 0u, s0 >> 16);
+                    const uint32_t W2 = __byte_perm(0x47544341u, 0u, s1), W3 = __byte_perm(0x47544341u, 0u, s1 >> 16);
+                    const uint32_t dst = smem0 + l.img[ro] + so + 16u * j;  // shared-window address of position 16 j
+                    const uint32_t n = L - 16u * j;                        // bases of this chunk that belong to the read (>= 1)
+                    if (n >= 16u) {
+                        sts_word_bytes<0>(dst, W0); sts_word_bytes<4>(dst, W1); sts_word_bytes<8>(dst, W2); sts_word_bytes<12>(dst, W3);
+                    } else {
+                        sts_word_bytes_n<0>(dst, W0, n); sts_word_bytes_n<4>(dst, W1, n); sts_word_bytes_n<8>(dst, W2, n); sts_word_bytes_n<12>(dst, W3, n);
                     }
                 } else {
 #pragma unroll 4
@@ -523,84 +561,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 }
             }
         }
-        __syncthreads();
+        if (p.tma_gather) __syncthreads();  // block-uniform: the staged windows live in the quality lines that phase 4 writes
 
         // ---- phase 3: indel scan in the no-event world (error_models/__init__.py:187-224).  The pair's combined list
-        //      of non-zero positions (forward then reverse) is cut in four equal parts, one per thread of the pair.
+        //      of non-zero positions (forward then reverse) is cut in equal parts, one per thread of the pair.  Whether a
+        //      site that passes its draw really fires depends on the base under it, which another thread may still be
+        //      gathering: such survivors (rare) are queued and resolved behind the barrier that ends this phase.
         const uint64_t P = valid ? u64p(l.sP)[pair] : 0;
         const uint32_t Plo = (uint32_t)P, Phi = (uint32_t)(P >> 32);
         const uint32_t att8 = valid ? (u32p(l.sAtt)[pair] << 8) : 0;
         const uint32_t seq_off = rel0 + (valid ? u32p(l.sRel)[pair] : 0);
         uint8_t *seq = imgp(l, o) + seq_off;
+        const uint32_t g_begin = (q4 * p.n_grp) >> (p.split_shift + 1u), g_end = ((q4 + 1u) * p.n_grp) >> (p.split_shift + 1u);
         if (valid && p.n_grp) {
-            const uint32_t g_begin = (q4 * p.n_grp) >> (p.split_shift + 1u), g_end = ((q4 + 1u) * p.n_grp) >> (p.split_shift + 1u);
-            uint32_t fired = 0;  // bit so set when read orientation so has an event
             for (uint32_t g = g_begin; g < g_end; ++g) {
                 const uint32_t li = (g >= p.grp_begin[1] ? 1u : 0u) + (g >= p.grp_begin[2] ? 1u : 0u) + (g >= p.grp_begin[3] ? 1u : 0u);
                 const uint32_t so = li >> 1, kind = li & 1u;
                 const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
                 const Philox4 w = philox4x32_10_rk(g - p.grp_begin[li], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
                 if ((w.x <= t.x) | (w.y <= t.y) | (w.z <= t.z) | (w.w <= t.w)) {  // rare: some site may fire
-                    const uint8_t *sq = imgp(l, so) + seq_off;
 #pragma unroll 1
                     for (uint32_t r = 0; r < 4; ++r) {
                         const uint32_t meta = pick(mt, r);
                         const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
                         if (!bits) continue;
-                        const uint32_t c = sq[meta & 0xFFFFu];
-                        if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
-                        if ((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) fired |= 1u << so;
+                        const uint32_t slot = atomicAdd(&u32p(l.sCtl)[6], 1u);
+                        if (slot < ISS_SURV_CAP) u32p(l.sSurv)[slot] = ((so * T + pair) << 24) | (bits << 16) | (meta & 0xFFFFu);
                     }
                 }
-            }
-            for (uint32_t so = 0; so < 2; ++so)
-                if (((fired >> so) & 1u) && atomicExch(&u32p(l.sFlag)[so * T + pair], 1u) == 0u)
-                    u32p(l.sSlow)[atomicAdd(&u32p(l.sCtl)[1], 1u)] = so * T + pair;
-        }
-        __syncthreads();
-        {
-            const uint32_t nslow = u32p(l.sCtl)[1];
-            if (nslow) {  // block-uniform; rare for the bundled models, 15 % of the pairs for a dense fitted model
-                // phase 3b: all indel draws of the queued reads, in parallel.  A draw is addressed by (read, position, lane)
-                // and does not depend on the evolving sequence -- only WHICH deletion threshold applies depends on the
-                // current base -- so the mask holds the insertion lanes that fire and, per base, whether a deletion
-                // fires.  The masks live in the (still unused) substitution list.
-                uint32_t *masks32 = u32p(l.sErr);
-                uint8_t *masks = reinterpret_cast<uint8_t *>(masks32);
-                const uint32_t n_o0 = p.grp_begin[2] - p.grp_begin[0], n_o1 = p.grp_begin[4] - p.grp_begin[2];
-                const uint32_t ngrp = (n_o0 > n_o1) ? n_o0 : n_o1;  // groups of 4 sites (one Philox block each) per read
-                for (uint32_t base = 0; base < nslow; base += p.slow_slots) {
-                    const uint32_t nround = (nslow - base < p.slow_slots) ? (nslow - base) : p.slow_slots;
-                    for (uint32_t i = tid; i < ((nround * L + 3u) >> 2); i += blockDim.x) masks32[i] = 0;
-                    __syncthreads();
-                    for (uint32_t idx = tid; idx < nround * ngrp; idx += blockDim.x) {
-                        const uint32_t sidx = idx / ngrp, gq = idx - sidx * ngrp;
-                        const uint32_t srd = u32p(l.sSlow)[base + sidx];
-                        const uint32_t so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
-                        const uint32_t g = p.grp_begin[2u * so] + gq;
-                        if (g >= p.grp_begin[2u * so + 2u]) continue;
-                        const uint32_t kind = g >= p.grp_begin[2u * so + 1u] ? 1u : 0u;
-                        const uint64_t sP = u64p(l.sP)[sp_];
-                        const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
-                        const Philox4 w = philox4x32_10_rk(g - p.grp_begin[2u * so + kind], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | (u32p(l.sAtt)[sp_] << 8),
-                                                           (uint32_t)sP, (uint32_t)(sP >> 32), p.rk);
-#pragma unroll 1
-                        for (uint32_t r = 0; r < 4; ++r) {
-                            const uint32_t meta = pick(mt, r);
-                            const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
-                            if (bits) {
-                                const uint32_t bi = sidx * L + (meta & 0xFFFFu);
-                                atomicOr(&masks32[bi >> 2], bits << (8u * (bi & 3u)));
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    if (tid < nround)
-                        replay_indels(p, l, gp0, rel0, u32p(l.sSlow)[base + tid],
-                                      p.scratch + ((size_t)blockIdx.x * ISS_SLOW_SLOTS + tid) * p.scratch_stride, masks + tid * L);
-                    __syncthreads();
-                }
-                if (tid == 0) atomicAdd(p.counters + 0, (unsigned long long)nslow);
             }
         }
 
@@ -621,9 +609,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         const uint32_t pos = 2u * b;
                         const uint32_t r0 = row0 + stg * p.q_stage_cap;
                         const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
-                        bool tie;
-                        const uint32_t q0 = q16_search(r0, w.x >> 16, tie);
-                        if (tie) {
+                        bool tie0, tie1;
+                        uint32_t q0, q1;  // the row behind an odd L is all pad: q1 = 0 there, and not used
+                        q16_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
+                        if (tie0) {
                             defer_position(l, p.tie_cap, rd, pos);
                         } else {
                             qual[pos] = (uint8_t)(q0 + 33u);
@@ -633,8 +622,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                             }
                         }
                         if (pos + 1u < L) {
-                            const uint32_t q1 = q16_search(r0 + p.q_pos_stride[o], w.z >> 16, tie);
-                            if (tie) {
+                            if (tie1) {
                                 defer_position(l, p.tie_cap, rd, pos + 1u);
                             } else {
                                 qual[pos + 1u] = (uint8_t)(q1 + 33u);
@@ -684,6 +672,98 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         }
         __syncthreads();
 
+        // ---- phase 3b: which reads have an indel event?  (block-uniform; no survivor at all in most tiles of the bundled
+        //      models).  A survivor fires if the base under it is unambiguous and -- for a deletion -- is one of the bases
+        //      whose threshold its draw passed.  An overflowing queue (dense, fitted or adversarial tables) falls back to
+        //      every thread re-walking its groups with the gathered bases in place.
+        {
+            const uint32_t nsurv = u32p(l.sCtl)[6];
+            if (nsurv) {
+                if (nsurv <= ISS_SURV_CAP) {
+                    for (uint32_t e = tid; e < nsurv; e += blockDim.x) {
+                        const uint32_t v = u32p(l.sSurv)[e];
+                        const uint32_t srd = v >> 24, bits = (v >> 16) & 0xFFu, so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
+                        const uint32_t c = (imgp(l, so) + rel0 + u32p(l.sRel)[sp_])[v & 0xFFFFu];
+                        if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
+                        if (((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) && atomicExch(&u32p(l.sFlag)[srd], 1u) == 0u)
+                            u32p(l.sSlow)[atomicAdd(&u32p(l.sCtl)[1], 1u)] = srd;
+                    }
+                } else if (valid) {
+                    uint32_t fired = 0;  // bit so set when read orientation so has an event
+                    for (uint32_t g = g_begin; g < g_end; ++g) {
+                        const uint32_t li = (g >= p.grp_begin[1] ? 1u : 0u) + (g >= p.grp_begin[2] ? 1u : 0u) + (g >= p.grp_begin[3] ? 1u : 0u);
+                        const uint32_t so = li >> 1, kind = li & 1u;
+                        const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
+                        const Philox4 w = philox4x32_10_rk(g - p.grp_begin[li], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
+                        if ((w.x <= t.x) | (w.y <= t.y) | (w.z <= t.z) | (w.w <= t.w)) {
+                            const uint8_t *sq = imgp(l, so) + seq_off;
+#pragma unroll 1
+                            for (uint32_t r = 0; r < 4; ++r) {
+                                const uint32_t meta = pick(mt, r);
+                                const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
+                                if (!bits) continue;
+                                const uint32_t c = sq[meta & 0xFFFFu];
+                                if (!is_acgt(c)) continue;
+                                if ((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) fired |= 1u << so;
+                            }
+                        }
+                    }
+                    for (uint32_t so = 0; so < 2; ++so)
+                        if (((fired >> so) & 1u) && atomicExch(&u32p(l.sFlag)[so * T + pair], 1u) == 0u)
+                            u32p(l.sSlow)[atomicAdd(&u32p(l.sCtl)[1], 1u)] = so * T + pair;
+                }
+                __syncthreads();
+                const uint32_t nslow = u32p(l.sCtl)[1];
+                if (nslow) {
+                    // phase 3c: all indel draws of the queued reads, in parallel.  A draw is addressed by (read, position, lane)
+                    // and does not depend on the evolving sequence -- only WHICH deletion threshold applies depends on the
+                    // current base -- so the mask holds the insertion lanes that fire and, per base, whether a deletion
+                    // fires.  The masks live in the slot's scratch (global memory, behind the replay's own buffers).
+                    const uint32_t n_o0 = p.grp_begin[2] - p.grp_begin[0], n_o1 = p.grp_begin[4] - p.grp_begin[2];
+                    const uint32_t ngrp = (n_o0 > n_o1) ? n_o0 : n_o1;  // groups of 4 sites (one Philox block each) per read
+                    const uint32_t mask_words = (L + 3u) >> 2;
+                    for (uint32_t base = 0; base < nslow; base += ISS_SLOW_SLOTS) {
+                        const uint32_t nround = (nslow - base < ISS_SLOW_SLOTS) ? (nslow - base) : ISS_SLOW_SLOTS;
+                        uint8_t *cta_scratch = p.scratch + (size_t)blockIdx.x * ISS_SLOW_SLOTS * p.scratch_stride;
+                        for (uint32_t i = tid; i < nround * mask_words; i += blockDim.x) {
+                            const uint32_t sidx = i / mask_words;
+                            reinterpret_cast<uint32_t *>(cta_scratch + (size_t)sidx * p.scratch_stride + p.scratch_mask_off)[i - sidx * mask_words] = 0;
+                        }
+                        __syncthreads();
+                        for (uint32_t idx = tid; idx < nround * ngrp; idx += blockDim.x) {
+                            const uint32_t sidx = idx / ngrp, gq = idx - sidx * ngrp;
+                            const uint32_t srd = u32p(l.sSlow)[base + sidx];
+                            const uint32_t so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
+                            const uint32_t g = p.grp_begin[2u * so] + gq;
+                            if (g >= p.grp_begin[2u * so + 2u]) continue;
+                            const uint32_t kind = g >= p.grp_begin[2u * so + 1u] ? 1u : 0u;
+                            const uint64_t sP = u64p(l.sP)[sp_];
+                            const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
+                            const Philox4 w = philox4x32_10_rk(g - p.grp_begin[2u * so + kind], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | (u32p(l.sAtt)[sp_] << 8),
+                                                               (uint32_t)sP, (uint32_t)(sP >> 32), p.rk);
+                            uint32_t *masks32 = reinterpret_cast<uint32_t *>(cta_scratch + (size_t)sidx * p.scratch_stride + p.scratch_mask_off);
+#pragma unroll 1
+                            for (uint32_t r = 0; r < 4; ++r) {
+                                const uint32_t meta = pick(mt, r);
+                                const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
+                                if (bits) {
+                                    const uint32_t bi = meta & 0xFFFFu;
+                                    atomicOr(&masks32[bi >> 2], bits << (8u * (bi & 3u)));
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        if (tid < nround) {
+                            uint8_t *slot = cta_scratch + (size_t)tid * p.scratch_stride;
+                            replay_indels(p, l, gp0, rel0, u32p(l.sSlow)[base + tid], slot, slot + p.scratch_mask_off);
+                        }
+                        __syncthreads();
+                    }
+                    if (tid == 0) atomicAdd(p.counters + 0, (unsigned long long)nslow);
+                }
+            }
+        }
+
         // ---- phase 4b: the exact pass.  Positions whose 16-bit search met a tie are evaluated on the 32-bit row: the draw is
         //      recomputed (a Philox word is a pure function of its address), the phred written, the error test made.  If the
         //      queue or the substitution list overflowed (models far outside the bundled ones: ~ every base an error), every
@@ -701,9 +781,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                                                    (uint32_t)(tP >> 32), p.rk);
                 const uint32_t q = quality_exact(p, trd, pos, (pos & 1u) ? w.z : w.x);
                 (imgp(l, to) + rel0 + u32p(l.sRel)[tp] + L + 3u)[pos] = (uint8_t)(q + 33u);
-                if (((pos & 1u) ? w.w : w.y) > u32p(l.sErrThr)[q]) {
-                    const uint32_t slot = atomicAdd(&u32p(l.sCtl)[5], 1u);  // a second list: the first one is being read below
-                    if (slot < p.tie_cap) u32p(l.sTie2)[slot] = v;
+                if (((pos & 1u) ? w.w : w.y) > u32p(l.sErrThr)[q]) {  // a handful per tile: applied in place, no second list
+                    apply_substitution(p, l, gp0, rel0, trd, pos);
+                    atomicAdd(p.counters + 1, 1ull);
                 }
             }
         }
@@ -714,15 +794,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             for (uint32_t e = tid; e < nerr; e += blockDim.x) {
                 const uint32_t v = u32p(l.sErr)[e];
                 apply_substitution(p, l, gp0, rel0, v >> 16, v & 0xFFFFu);
-            }
-            if (ntie) {
-                __syncthreads();  // block-uniform: the tie pass above has finished writing its list
-                const uint32_t n2 = u32p(l.sCtl)[5];
-                for (uint32_t e = tid; e < n2; e += blockDim.x) {
-                    const uint32_t v = u32p(l.sTie2)[e];
-                    apply_substitution(p, l, gp0, rel0, v >> 16, v & 0xFFFFu);
-                }
-                if (tid == 0 && n2) atomicAdd(p.counters + 1, (unsigned long long)n2);
             }
             if (tid == 0 && nerr) atomicAdd(p.counters + 1, (unsigned long long)nerr);
         } else if (valid) {

@@ -9,6 +9,7 @@
 //                     one process driving several GPUs); no communication afterwards
 #include <cuda_runtime.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in Nsight Systems / ncu --nvtx timelines, cost ~nothing otherwise
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,6 +26,11 @@
 #include "iss_hostmem.h"
 
 namespace {
+
+struct NvtxRange {  // RAII range: "iss:plan+launch", "iss:wait_batch", "iss:vcf"
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_err;
 
@@ -233,6 +239,7 @@ uint32_t record_fixed_len(uint32_t L, uint32_t name_len, uint32_t cpu) {
 
 // Plan and launch the next batch into slot `si`.  Returns ISS_OK; sets c->exhausted when no work is left.
 int launch_batch(iss_ctx *c, uint32_t si) {
+    NvtxRange nvtx("iss:plan+launch");
     Slot &s = c->slots[si];
     const uint32_t L = c->mh.L;
     uint64_t pairs = 0, bytes = 0;
@@ -305,8 +312,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.nchunk = (L + 15u) / 16u;
     p.chunk_magic = (uint32_t)((0x100000000ull + p.nchunk - 1) / p.nchunk);
     p.scratch = s.d_scratch;
-    p.scratch_stride = (uint32_t)align_up(5ull * L + 8, 16);
-    p.slow_slots = std::max<uint32_t>(1u, std::min<uint32_t>(ISS_SLOW_SLOTS, 4u * c->err_cap / L));  // L > 4 * err_cap is refused at submit
+    p.scratch_mask_off = (uint32_t)align_up(5ull * L + 8, 16);
+    p.scratch_stride = p.scratch_mask_off + (uint32_t)align_up(L, 16);
     p.gc_thr = 3865470567u;  // ceil(0.90 * 2^32): u < 0.90  <=>  w < gc_thr   (generator.py:88)
     p.counters = c->d_counters;
     p.store_mutations = c->mh.store_mutations;
@@ -368,6 +375,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
 // write_mutations (iss/generator.py:598-620): "{id}\t{position+1}\t.\t{ref}\t{alt}\t{quality}\t\t\n", in the order the
 // reference appends them: forward indels, forward substitutions, reverse indels, reverse substitutions, pair by pair.
 int format_vcf(iss_ctx *c, Slot &s) {
+    NvtxRange nvtx("iss:vcf");
     const unsigned long long n = *s.h_evcount;
     s.vcf.clear();
     if (n == 0) return ISS_OK;
@@ -835,7 +843,6 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         if (smem <= kMaxSmem) break;
         if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
     }
-    if (4ull * c->err_cap < L) return fail(ISS_E_ARG, "read length too long for the indel replay scratch");
     int bps = 0;
     uint32_t split_shift = 1;
     CU(iss_occupancy(T, split_shift, smem, &bps));
@@ -907,7 +914,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         c->max_segs = max_segs;
     }
     for (auto &s : c->slots) s.state = 0;
-    const uint64_t scratch = (uint64_t)grid * ISS_SLOW_SLOTS * align_up(5ull * L + 8, 16);
+    const uint64_t scratch = (uint64_t)grid * ISS_SLOW_SLOTS * (align_up(5ull * L + 8, 16) + align_up(L, 16));
     for (auto &s : c->slots) {
         if (scratch > s.scratch_bytes) {
             if (s.d_scratch) cudaFree(s.d_scratch);
@@ -958,7 +965,10 @@ int iss_ctx_next(iss_ctx *c, iss_batch *b, int *have) {
     const uint32_t si = (uint32_t)(c->next_return % c->n_slots);
     Slot &s = c->slots[si];
     if (s.state != 1 || s.batch_index != c->next_return) return fail(ISS_E_STATE, "internal: ring out of order");
-    CU(cudaEventSynchronize(s.ev_done));
+    {
+        NvtxRange nvtx("iss:wait_batch");
+        CU(cudaEventSynchronize(s.ev_done));
+    }
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1));
     if (c->trace && c->marks[0]) {  // ISS_TRACE=1: device timeline of the batch relative to mark 0 (ms)

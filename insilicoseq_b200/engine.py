@@ -121,7 +121,11 @@ class Engine(object):
         return hit[0]
 
     def set_model(self, model):
-        tables = model.device_tables()
+        """model: an ErrorModel of this package, or a reference-side instance (iss.error_models.*) -- lowered from its
+        attributes by error_models.lower, which refuses classes that override the hot-path methods."""
+        from . import error_models
+
+        tables = error_models.lower(model)
         cm = tables.c_struct()
         _lib.check(self._lib.iss_ctx_set_model(self._h, ctypes.byref(cm)))
         self.read_length = int(model.read_length)

@@ -8,7 +8,11 @@ attributes can be handed to the engine: `device_tables()` turns the f64 probabil
 integer thresholds on 32-bit Philox words (include/iss_b200.h), after which the device path has no
 floating point.  The per-read methods of the reference (introduce_indels, gen_phred_scores,
 mut_sequence ...) are what the CUDA kernels implement for whole batches; they are not re-offered as
-per-record Python loops (there is no CPU path in this package).
+per-record Python loops (there is no CPU path in this package).  What the engine runs is therefore
+fixed by the model's DATA: `lower(model)` accepts an instance of this package's classes or of the
+reference's own (iss.error_models.kde.KDErrorModel, ...basic.BasicErrorModel, ...perfect.PerfectErrorModel
+-- no class swap needed) and REFUSES a model whose class overrides one of the hot-path methods with
+code the GPU cannot know about (`check_plugin_surface`), instead of silently ignoring the override.
 
 Lowering, with w a 32-bit word and u = w * 2**-32 (scaling an f64 by 2**32 is exact):
     searchsorted(cdf, u, 'left')  = #{j : cdf[j] <  u} = #{j : w >  floor(cdf[j] * 2**32)}
@@ -127,6 +131,151 @@ class DeviceTables:
         return m
 
 
+HOT_PATH_METHODS = ("gen_phred_scores", "random_insert_size", "introduce_error_scores", "mut_sequence", "introduce_indels",
+                    "adjust_seq_length")  # iss/error_models/__init__.py:52,69,114,158, kde.py:52,88
+_KNOWN_MODULES = ("insilicoseq_b200.error_models", "iss.error_models", "iss.error_models.kde", "iss.error_models.basic",
+                  "iss.error_models.perfect")
+_FAMILY_OF_CLASS = {"KDErrorModel": "kde", "BasicErrorModel": "basic", "PerfectErrorModel": "perfect"}
+
+
+def check_plugin_surface(model):
+    """The engine replaces the reference's per-read methods with CUDA kernels driven by the model's tables.  A class
+    (or instance) that overrides one of them with its own Python code would be ignored -- refuse it instead."""
+    for name in HOT_PATH_METHODS:
+        if name in vars(model):
+            raise TypeError("%s.%s is overridden on the instance: the B200 engine implements the reference's %s on the GPU from "
+                            "the model's tables and cannot call Python code per read" % (type(model).__name__, name, name))
+        for cls in type(model).__mro__:
+            if name in vars(cls):
+                if cls.__module__ not in _KNOWN_MODULES:
+                    raise TypeError("%s.%s overrides %s: the B200 engine implements the reference's samplers on the GPU from the "
+                                    "model's tables and cannot call Python code per read; express the change in the tables "
+                                    "(quality_forward/reverse, subst_choices_*, ins_*/del_*, i_size_cdf) instead"
+                                    % (cls.__module__, cls.__qualname__, name))
+                break
+
+
+def sampling_family(model):
+    """'kde' | 'basic' | 'perfect': which of the reference's three samplers the model's methods denote."""
+    for cls in type(model).__mro__:
+        if cls.__module__ in _KNOWN_MODULES and cls.__name__ in _FAMILY_OF_CLASS:
+            return _FAMILY_OF_CLASS[cls.__name__]
+    if hasattr(model, "i_size_cdf") and hasattr(model, "mean_forward"):
+        return "kde"  # a conforming attribute set on some other class (SURVEY.md 8b: the plugin surface is the attributes)
+    raise TypeError("cannot tell which sampler %s stands for: derive from KDErrorModel / BasicErrorModel / PerfectErrorModel "
+                    "or provide the KDE attribute set (i_size_cdf, mean_forward, ...)" % type(model).__name__)
+
+
+def lower(model):
+    """DeviceTables of any conforming model object -- this package's classes or the reference's own instances."""
+    check_plugin_surface(model)
+    family = sampling_family(model)
+    L = int(model.read_length)
+    t = DeviceTables()
+    t.scalars.update(read_length=L, store_mutations=int(bool(getattr(model, "store_mutations", False))),
+                     n_insert=0, fixed_insert=0, frag_mode=0, n_frag=0, frag_lo=0, const_phred=0, n_basic=0,
+                     qual_mode=0)
+    # fragment length (generator.py:121-126)
+    frag_thr = np.zeros(0, dtype=np.uint64)
+    if getattr(model, "fragment_length", None) is not None and getattr(model, "fragment_sd", None) is not None:
+        lo, frag_thr = fragment_table(model.fragment_length, model.fragment_sd)
+        t.scalars.update(frag_mode=1, n_frag=len(frag_thr), frag_lo=lo)
+    t.arrays["frag_thr"] = frag_thr
+    t.arrays["err_thr"] = thr_greater(phred_to_prob_table(QROW))
+    {"kde": _lower_quality_kde, "basic": _lower_quality_basic, "perfect": _lower_quality_perfect}[family](model, t)
+    # substitutions (error_models/__init__.py:83-97): nucl_choices[position][base] = (alts, probs)
+    subs = (model.subst_choices_for, model.subst_choices_rev)
+    subst_n = np.zeros((2, L, 4), dtype=np.uint8)
+    subst_thr = np.full((2, L, 4, MAX_ALT), 1 << 32, dtype=np.uint64)
+    subst_alt = np.full((2, L, 4, MAX_ALT), ord("N"), dtype=np.uint8)
+    for o in range(2):
+        for pos in range(L):
+            entry = subs[o][pos]
+            for c, base in enumerate(BASES):
+                alts, probs = entry[base]
+                na = len(alts)
+                if not 1 <= na <= MAX_ALT:
+                    raise ValueError("substitution table with %d alternatives" % na)
+                subst_n[o, pos, c] = na
+                subst_thr[o, pos, c, :na] = thr_right(choice_cdf(probs))
+                subst_alt[o, pos, c, :na] = [ord(str(a)) for a in alts]
+    t.arrays.update(subst_n=subst_n, subst_thr=subst_thr, subst_alt=subst_alt)
+    # indels (error_models/__init__.py:176-210): dict base -> probability, insertion lanes in dict order
+    ins = (model.ins_for, model.ins_rev)
+    dels = (model.del_for, model.del_rev)
+    ins_thr = np.zeros((2, L, 4), dtype=np.uint32)
+    ins_nz = np.zeros((2, L), dtype=np.uint8)
+    ins_base = np.full((2, L, 4), ord("A"), dtype=np.uint8)
+    del_thr = np.zeros((2, L, 4), dtype=np.uint32)
+    del_nz = np.zeros((2, L), dtype=np.uint8)
+    for o in range(2):
+        for pos in range(L):
+            lanes = list(ins[o][pos].items())
+            if len(lanes) > 4:
+                raise ValueError("insertion table with more than 4 lanes")
+            d, nz = thr_bernoulli([p for _, p in lanes])
+            for lane, (base, _) in enumerate(lanes):
+                ins_thr[o, pos, lane] = d[lane]
+                ins_base[o, pos, lane] = ord(str(base))
+                ins_nz[o, pos] |= int(nz[lane]) << lane
+            d, nz = thr_bernoulli([dels[o][pos][b] for b in BASES])
+            del_thr[o, pos] = d
+            for c in range(4):
+                del_nz[o, pos] |= int(nz[c]) << c
+    t.arrays.update(ins_thr=ins_thr, ins_nz=ins_nz, ins_base=ins_base, del_thr=del_thr, del_nz=del_nz)
+    for k in ("insert_thr", "bin_thr", "bin_valid", "qual_thr", "basic_thr", "basic_val"):
+        t.arrays.setdefault(k, np.zeros(0, dtype=np.uint32))
+    return t
+
+
+def _lower_quality_kde(model, t):
+    """kde.py:52-98: insert size = CDF index, quality bin by np.random.choice, per-position searchsorted."""
+    L = int(model.read_length)
+    ic = np.asarray(model.i_size_cdf, dtype=np.float64)
+    if (np.diff(ic) < 0).any():
+        raise ValueError("insert size CDF is not sorted")
+    t.arrays["insert_thr"] = thr_left(ic)
+    t.scalars.update(qual_mode=0, n_insert=len(ic))
+    bin_thr = np.zeros((2, 4), dtype=np.uint64)
+    bin_valid = np.zeros((2, 4), dtype=np.uint8)
+    qual_thr = np.full((2, 4, L, QROW), 0xFFFFFFFF, dtype=np.uint32)
+    for o, (mean, quals) in enumerate(((model.mean_forward, model.quality_forward),
+                                       (model.mean_reverse, model.quality_reverse))):
+        if len(mean) != 4:
+            raise ValueError("expected 4 mean-quality bins")
+        norm_mean = mean / sum(mean)  # kde.py:72
+        bin_thr[o] = thr_right(choice_cdf(norm_mean))  # np.random.choice(range(4), p=norm_mean), kde.py:74
+        for b in range(4):
+            rows = quals[b]
+            if len(rows) >= L:
+                arr = np.asarray(list(rows[:L]), dtype=np.float64)
+                if arr.shape[1] > QROW:
+                    raise ValueError("quality CDF rows longer than %d" % QROW)
+                if (np.diff(arr, axis=1) < 0).any():
+                    raise ValueError("quality CDF row is not sorted")
+                qual_thr[o, b, :, : arr.shape[1]] = thr_left(arr)
+                bin_valid[o, b] = 1
+            elif norm_mean[b] > 0:
+                # the reference would build a short phred list and fail inside SeqRecord (kde.py:80-86)
+                raise ValueError("quality bin %d has probability %g but only %d CDF rows" % (b, norm_mean[b], len(rows)))
+    t.arrays.update(bin_thr=bin_thr, bin_valid=bin_valid, qual_thr=qual_thr)
+
+
+def _lower_quality_basic(model, t):
+    """basic.py:41-58: phred ~ normal around quality_forward by inversion on the integer table, constant insert size."""
+    thr, val = basic_phred_table(model.quality_forward)
+    if val.min() < 0 or val.max() >= QROW:
+        raise ValueError("phred table out of range")
+    t.arrays["basic_thr"] = thr
+    t.arrays["basic_val"] = val.astype(np.uint8)
+    t.scalars.update(qual_mode=2, n_basic=len(thr), n_insert=0, fixed_insert=int(model.insert_size))
+
+
+def _lower_quality_perfect(model, t):
+    """perfect.py:36-52: constant phred, constant insert size."""
+    t.scalars.update(qual_mode=1, const_phred=int(model.quality_forward), n_insert=0, fixed_insert=int(model.insert_size))
+
+
 class ErrorModel(object):
     """Base class: the attribute contract + lowering to device tables."""
 
@@ -154,67 +303,8 @@ class ErrorModel(object):
             self.logger.debug("Loaded ErrorProfile: %s" % npz_path)
         return error_profile
 
-    # -- lowering -----------------------------------------------------------------------------------
-    def _lower_quality(self, t):
-        raise NotImplementedError
-
     def device_tables(self):
-        L = int(self.read_length)
-        t = DeviceTables()
-        t.scalars.update(read_length=L, store_mutations=int(bool(getattr(self, "store_mutations", False))),
-                         n_insert=0, fixed_insert=0, frag_mode=0, n_frag=0, frag_lo=0, const_phred=0, n_basic=0,
-                         qual_mode=0)
-        # fragment length (generator.py:121-126)
-        frag_thr = np.zeros(0, dtype=np.uint64)
-        if self.fragment_length is not None and self.fragment_sd is not None:
-            lo, frag_thr = fragment_table(self.fragment_length, self.fragment_sd)
-            t.scalars.update(frag_mode=1, n_frag=len(frag_thr), frag_lo=lo)
-        t.arrays["frag_thr"] = frag_thr
-        t.arrays["err_thr"] = thr_greater(phred_to_prob_table(QROW))
-        self._lower_quality(t)
-        # substitutions (error_models/__init__.py:83-97): nucl_choices[position][base] = (alts, probs)
-        subs = (self.subst_choices_for, self.subst_choices_rev)
-        subst_n = np.zeros((2, L, 4), dtype=np.uint8)
-        subst_thr = np.full((2, L, 4, MAX_ALT), 1 << 32, dtype=np.uint64)
-        subst_alt = np.full((2, L, 4, MAX_ALT), ord("N"), dtype=np.uint8)
-        for o in range(2):
-            for pos in range(L):
-                entry = subs[o][pos]
-                for c, base in enumerate(BASES):
-                    alts, probs = entry[base]
-                    na = len(alts)
-                    if not 1 <= na <= MAX_ALT:
-                        raise ValueError("substitution table with %d alternatives" % na)
-                    subst_n[o, pos, c] = na
-                    subst_thr[o, pos, c, :na] = thr_right(choice_cdf(probs))
-                    subst_alt[o, pos, c, :na] = [ord(str(a)) for a in alts]
-        t.arrays.update(subst_n=subst_n, subst_thr=subst_thr, subst_alt=subst_alt)
-        # indels (error_models/__init__.py:176-210): dict base -> probability, insertion lanes in dict order
-        ins = (self.ins_for, self.ins_rev)
-        dels = (self.del_for, self.del_rev)
-        ins_thr = np.zeros((2, L, 4), dtype=np.uint32)
-        ins_nz = np.zeros((2, L), dtype=np.uint8)
-        ins_base = np.full((2, L, 4), ord("A"), dtype=np.uint8)
-        del_thr = np.zeros((2, L, 4), dtype=np.uint32)
-        del_nz = np.zeros((2, L), dtype=np.uint8)
-        for o in range(2):
-            for pos in range(L):
-                lanes = list(ins[o][pos].items())
-                if len(lanes) > 4:
-                    raise ValueError("insertion table with more than 4 lanes")
-                d, nz = thr_bernoulli([p for _, p in lanes])
-                for lane, (base, _) in enumerate(lanes):
-                    ins_thr[o, pos, lane] = d[lane]
-                    ins_base[o, pos, lane] = ord(str(base))
-                    ins_nz[o, pos] |= int(nz[lane]) << lane
-                d, nz = thr_bernoulli([dels[o][pos][b] for b in BASES])
-                del_thr[o, pos] = d
-                for c in range(4):
-                    del_nz[o, pos] |= int(nz[c]) << c
-        t.arrays.update(ins_thr=ins_thr, ins_nz=ins_nz, ins_base=ins_base, del_thr=del_thr, del_nz=del_nz)
-        for k in ("insert_thr", "bin_thr", "bin_valid", "qual_thr", "basic_thr", "basic_val"):
-            t.arrays.setdefault(k, np.zeros(0, dtype=np.uint32))
-        return t
+        return lower(self)
 
 
 class KDErrorModel(ErrorModel):
@@ -257,37 +347,6 @@ class KDErrorModel(ErrorModel):
         for attr in ("subst_choices_for", "subst_choices_rev", "ins_for", "ins_rev", "del_for", "del_rev"):
             setattr(self, attr, getattr(self, attr)[:n])
         return self
-
-    def _lower_quality(self, t):
-        L = int(self.read_length)
-        ic = np.asarray(self.i_size_cdf, dtype=np.float64)
-        if (np.diff(ic) < 0).any():
-            raise ValueError("insert size CDF is not sorted")
-        t.arrays["insert_thr"] = thr_left(ic)
-        t.scalars.update(qual_mode=0, n_insert=len(ic))
-        bin_thr = np.zeros((2, 4), dtype=np.uint64)
-        bin_valid = np.zeros((2, 4), dtype=np.uint8)
-        qual_thr = np.full((2, 4, L, QROW), 0xFFFFFFFF, dtype=np.uint32)
-        for o, (mean, quals) in enumerate(((self.mean_forward, self.quality_forward),
-                                           (self.mean_reverse, self.quality_reverse))):
-            if len(mean) != 4:
-                raise ValueError("expected 4 mean-quality bins")
-            norm_mean = mean / sum(mean)  # kde.py:72
-            bin_thr[o] = thr_right(choice_cdf(norm_mean))  # np.random.choice(range(4), p=norm_mean), kde.py:74
-            for b in range(4):
-                rows = quals[b]
-                if len(rows) >= L:
-                    arr = np.asarray(list(rows[:L]), dtype=np.float64)
-                    if arr.shape[1] > QROW:
-                        raise ValueError("quality CDF rows longer than %d" % QROW)
-                    if (np.diff(arr, axis=1) < 0).any():
-                        raise ValueError("quality CDF row is not sorted")
-                    qual_thr[o, b, :, : arr.shape[1]] = thr_left(arr)
-                    bin_valid[o, b] = 1
-                elif norm_mean[b] > 0:
-                    # the reference would build a short phred list and fail inside SeqRecord (kde.py:80-86)
-                    raise ValueError("quality bin %d has probability %g but only %d CDF rows" % (b, norm_mean[b], len(rows)))
-        t.arrays.update(bin_thr=bin_thr, bin_valid=bin_valid, qual_thr=qual_thr)
 
 
 def basic_phred_table(mean_quality, sd=0.01, cap=0.9999):
@@ -342,14 +401,6 @@ class BasicErrorModel(ErrorModel):
             {"A": 0.0, "T": 0.0, "C": 0.0, "G": 0.0} for _ in range(125)
         ]
 
-    def _lower_quality(self, t):
-        thr, val = basic_phred_table(self.quality_forward)
-        if val.min() < 0 or val.max() >= QROW:
-            raise ValueError("phred table out of range")
-        t.arrays["basic_thr"] = thr
-        t.arrays["basic_val"] = val.astype(np.uint8)
-        t.scalars.update(qual_mode=2, n_basic=len(thr), n_insert=0, fixed_insert=int(self.insert_size))
-
 
 class PerfectErrorModel(ErrorModel):
     """perfect.py:7-52 -- Q40 everywhere, identity 'substitutions', no indels."""
@@ -374,10 +425,6 @@ class PerfectErrorModel(ErrorModel):
         self.ins_for = self.ins_rev = self.del_for = self.del_rev = [
             {"A": 0.0, "T": 0.0, "C": 0.0, "G": 0.0} for _ in range(self.read_length)
         ]
-
-    def _lower_quality(self, t):
-        t.scalars.update(qual_mode=1, const_phred=int(self.quality_forward), n_insert=0,
-                         fixed_insert=int(self.insert_size))
 
 
 PRECOMPUTED = {  # iss/generator.py:377-387

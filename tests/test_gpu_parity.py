@@ -35,7 +35,8 @@ def test_golden_fixture(name):
     assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
     assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
     if case.get("store_mutations"):
-        assert first_diff(stats["vcf"], exp["vcf"]) is None
+        if exp["vcf"] is not None:  # the larger cases keep only the digest
+            assert first_diff(stats["vcf"], exp["vcf"]) is None
         assert hashlib.sha256(stats["vcf"]).hexdigest() == case["sha256"]["vcf"]
 
 

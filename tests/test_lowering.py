@@ -173,3 +173,69 @@ def test_lowering_rejects_what_the_reference_could_not_sample():
     lane = list(m.ins_for[2].keys()).index("G")
     assert (t["ins_nz"][0, 2] >> lane) & 1 and t["ins_thr"][0, 2, lane] == 0xFFFFFFFF
     assert not (t["del_nz"][0, 0] >> error_models.BASES.index("A")) & 1
+
+
+# ---- plug-in surface ---------------------------------------------------------------------------------
+def _tables_equal(a, b):
+    assert a.scalars == b.scalars
+    assert set(a.arrays) == set(b.arrays)
+    for k in a.arrays:
+        assert np.array_equal(np.asarray(a.arrays[k]), np.asarray(b.arrays[k])), k
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/iss"), reason="needs /root/reference")
+def test_reference_side_model_instances_lower_without_a_class_swap():
+    """error_models.lower takes the reference's OWN model objects (iss.error_models.kde.KDErrorModel, Basic, Perfect):
+    the tables are identical to those of this package's classes built from the same inputs."""
+    import patched_reference as pr
+
+    pr.import_reference()
+    from iss.error_models import basic, kde, perfect
+
+    npz = fixtures.model_path("profile:HiSeq")
+    _tables_equal(error_models.lower(kde.KDErrorModel(npz, 400, 30, True)), error_models.lower(error_models.KDErrorModel(npz, 400, 30, True)))
+    _tables_equal(error_models.lower(basic.BasicErrorModel(None, None, True)), error_models.lower(error_models.BasicErrorModel(None, None, True)))
+    _tables_equal(error_models.lower(perfect.PerfectErrorModel()), error_models.lower(error_models.PerfectErrorModel()))
+    assert error_models.sampling_family(kde.KDErrorModel(npz)) == "kde"
+
+
+def test_models_that_override_a_hot_path_method_are_refused():
+    """A subclass that replaces gen_phred_scores / mut_sequence / ... with Python code cannot run on the GPU: lowering must
+    say so instead of silently ignoring the override.  Attribute-only plug-ins stay welcome."""
+    npz = fixtures.model_path("profile:HiSeq")
+
+    class Louder(error_models.KDErrorModel):
+        def gen_phred_scores(self, cdfs, orientation):  # what a third-party plug-in of the reference might do
+            return [40] * int(self.read_length)
+
+    with pytest.raises(TypeError, match="gen_phred_scores"):
+        error_models.lower(Louder(npz))
+
+    class Shorter(error_models.KDErrorModel):
+        def random_insert_size(self):
+            return 10
+
+    with pytest.raises(TypeError, match="random_insert_size"):
+        Shorter(npz).device_tables()
+    m = error_models.KDErrorModel(npz)
+    m.mut_sequence = lambda record, orientation: record  # instance-level override
+    with pytest.raises(TypeError, match="mut_sequence"):
+        error_models.lower(m)
+
+    class TablesOnly(error_models.KDErrorModel):  # changes data, not code: fine
+        def __init__(self, path):
+            super().__init__(path)
+            self.i_size_cdf = np.linspace(0.0, 1.0, 500)
+
+    t = error_models.lower(TablesOnly(npz))
+    assert t.scalars["n_insert"] == 500
+
+    class Duck(object):  # not derived from anything: the KDE attribute set alone decides
+        pass
+
+    src = error_models.KDErrorModel(npz)
+    d = Duck()
+    for k, v in vars(src).items():
+        setattr(d, k, v)
+    _tables_equal(error_models.lower(d), error_models.lower(src))

@@ -18,9 +18,7 @@ subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "insilicoseq_b20
 KFILE = os.environ.get("ISS_KERNEL_FILE", "iss_kernels")
 cub = [f for f in os.listdir(tmp) if f.startswith(KFILE + ".") and f.endswith(".cubin")][0]
 sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.split("\n")
-SYM = os.environ.get("ISS_KERNEL_SYM", "_Z19iss_generate_kernelILi%sELi%sELi%sE" % (
-    os.environ.get("ISS_KERNEL_THREADS", "256"), "4" if os.environ.get("ISS_KERNEL_THREADS", "256") == "256" else "2",
-    os.environ.get("ISS_KERNEL_QSHIFT", "1")))
+SYM = os.environ.get("ISS_KERNEL_SYM", "_Z19iss_generate_kernelILi%sE" % os.environ.get("ISS_KERNEL_THREADS", "256"))
 start = [i for i, l in enumerate(sass) if l.startswith(".text." + SYM)][0]
 ins, cur, inl = [], None, None
 for l in sass[start + 1:]:
