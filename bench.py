@@ -609,12 +609,17 @@ def files_leg(cfg, eng, eng_mod, generator, items, my_pairs, rank, world, barrie
     d = tempfile.mkdtemp(prefix="iss_files_r%d_" % rank, dir=target)
     prefix = os.path.join(d, "w")
     try:
-        def run(null=False):
+        wt = max(2, min(16, usable_cores()))
+
+        def run(null=False, gz=False):
             t = time.perf_counter()
             if null:
                 st = eng.write_files(sub, None, None, None)
+            elif gz:
+                st = eng.write_files(sub, prefix + "_R1.fastq.gz", prefix + "_R2.fastq.gz", None, append=True, truncate=True,
+                                     compress=True, writer_threads=wt)
             else:
-                st = eng.write_files(sub, prefix + "_R1.fastq", prefix + "_R2.fastq", prefix + ".vcf", truncate=True)
+                st = eng.write_files(sub, prefix + "_R1.fastq", prefix + "_R2.fastq", prefix + ".vcf", truncate=True, writer_threads=wt)
             return time.perf_counter() - t, st
 
         run()
@@ -632,14 +637,23 @@ def files_leg(cfg, eng, eng_mod, generator, items, my_pairs, rank, world, barrie
             run(null=True)
         dt_null = reduce_max(time.perf_counter() - t0)
         barrier()
+        run(gz=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, tot_gz = run(gz=True)
+        dt_gz = reduce_max(time.perf_counter() - t0)
+        barrier()
         pairs = reduce_sum(sample)
         nbytes = reduce_sum(tot["bytes_r1"] + tot["bytes_r2"])
         return {"value": pairs * steps / dt, "unit": "pairs/s", "clock": "host wall clock, max over ranks",
                 "target": "tmpfs %s" % target if target == "/dev/shm" else target, "pairs_per_step": int(pairs),
                 "bytes_per_step": int(nbytes), "GBps_written": nbytes * steps / dt / 1e9, "files_ok": bool(ok),
-                "discard_value": pairs * steps / dt_null,
+                "discard_value": pairs * steps / dt_null, "gzip_value": pairs * steps / dt_gz,
+                "gzip_bytes_per_step": int(reduce_sum(tot_gz["bytes_r1"] + tot_gz["bytes_r2"])), "writer_threads": wt,
                 "note": "Engine.write_files (what generator.worker_iterator calls): native pwrite threads from the pinned ring; "
-                        "discard_value = same call with no output paths (copy to the host, no file system)"}
+                        "discard_value = same call with no output paths (copy to the host, no file system); gzip_value = --compress members "
+                        "appended to .fastq.gz files"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

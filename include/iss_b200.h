@@ -192,7 +192,7 @@ typedef struct {
     uint64_t offset_r2;
     uint32_t append;          /* 1: write at the end of the file (compressed streams: sizes are not known in advance) */
     uint32_t truncate;        /* 1: O_TRUNC on open (a worker's private file, like the reference's open(..., "w")) */
-    uint32_t writer_threads;  /* pwrite threads; 0 = default (4) */
+    uint32_t writer_threads;  /* pwrite threads; 0 = default (8) */
     uint32_t reserved;
 } iss_file_sink;
 

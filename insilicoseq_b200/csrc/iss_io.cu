@@ -129,8 +129,8 @@ int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_ite
     auto close_all = [&] { for (int k = 0; k < 3; ++k) if (fd[k] >= 0) close(fd[k]); };
     int rc = iss_ctx_submit(ctx, items, n_items, opts);
     if (rc != ISS_OK) { close_all(); return rc; }
-    const unsigned nthreads = sink->writer_threads ? sink->writer_threads : 4u;
-    const uint64_t piece = 8ull << 20;
+    const unsigned nthreads = sink->writer_threads ? sink->writer_threads : 8u;
+    const uint64_t piece = 4ull << 20;
     int io_err = 0;
     {
         WriterPool pool(nthreads);

@@ -236,57 +236,96 @@ __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay
     seq[pos] = (uint8_t)alt;
 }
 
-// ---- sequential replay of introduce_indels + adjust_seq_length for one read ---------------------------
+// ---- replay of introduce_indels + adjust_seq_length for one read, by one warp -------------------------------
 // Reference list semantics (error_models/__init__.py:187-226) restated as a stream:
 //   seq = out[0..nucl) ++ [cur] ++ future,   future = LIFO of inserted bases on top of the unread original.
 //   insertion at index nucl+1  == push on the LIFO (a later lane lands in front of an earlier one)
 //   pop(nucl)                  == drop cur; the next element takes index nucl WITHOUT being examined
 //   IndexError at seq[nucl]    == the stream is exhausted: nothing further is drawn
-__device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rel0, uint32_t rd, uint8_t *scratch,
-                              const uint8_t *mask /* shared: per position, bits 0-3 insertion lanes that fire, 4-7 deletion fires for base b */) {
-    const uint32_t T = p.tile_pairs, L = p.L;
+// Every draw of the read was made in parallel beforehand (phase 3c): mask[pos] holds the insertion lanes that fire at loop
+// position pos (bits 0-3) and, per base, whether a deletion fires (bits 4-7).  Where the mask is zero and the LIFO is empty
+// the loop just moves one original base to the output, so the warp alternates between
+//   (a) finding the next position with a non-zero mask (ballot over 32 mask bytes at a time),
+//   (b) copying the run of original bases in front of it, 32 bases per step, and
+//   (c) lane 0 stepping the reference's loop through that position and on while the LIFO holds bases.
+// Cost is proportional to the number of events, not to L: what used to be one thread walking all L positions through
+// global memory (~0.3 us per step) is a few warp-wide steps per event.
+__device__ __noinline__ void replay_indels_warp(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rel0, uint32_t rd, uint8_t *scratch,
+                                   const uint8_t *mask, uint32_t lane) {
+    const uint32_t T = p.tile_pairs, L = p.L, FULL = 0xFFFFFFFFu;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
     uint8_t *seq = imgp(l, o) + rel0 + u32p(l.sRel)[pair];
-    uint8_t *orig = scratch;
-    uint8_t *stk = scratch + L;
-    for (uint32_t k = 0; k < L; ++k) orig[k] = seq[k];
-    const uint64_t P = u64p(l.sP)[pair];
-    uint32_t sp = 0, k = 0, outlen = 0;
-    for (uint32_t nucl = 0; nucl + 1 < L; ++nucl) {
-        uint32_t cur;
-        if (sp) cur = stk[--sp]; else if (k < L) cur = orig[k++]; else break;
-        if (!is_acgt(cur)) { seq[outlen++] = (uint8_t)cur; continue; }
-        const uint32_t tb = o * L + nucl;
-        const uint32_t mk = mask[nucl];  // every draw of this read was made in parallel (phase 3b)
-        if (mk & 15u) {
-            for (uint32_t lane = 0; lane < 4; ++lane)
-                if ((mk >> lane) & 1u) {
-                    const uint32_t ib = p.m.ins_base[tb * 4 + lane];
-                    stk[sp++] = (uint8_t)ib;
-                    if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, lane, cur, cur, ib, 255u);
+    uint8_t *orig = scratch;       // [L]  the read before indels
+    uint8_t *stk = scratch + L;    // [4L] LIFO of inserted bases (lane 0 only)
+    for (uint32_t i = lane; i < L; i += 32u) orig[i] = seq[i];
+    __syncwarp();
+    uint32_t nucl = 0, k = 0, sp = 0;  // loop position == bytes written so far; next unread original base; LIFO depth
+    bool broke = false;                // the reference's loop ended on an IndexError
+    while (nucl + 1u < L && !broke) {
+        // (a) next loop position >= nucl whose mask is non-zero (L - 1 = none); with bases on the LIFO: right here
+        uint32_t e = nucl;
+        if (sp == 0) {
+            e = L - 1u;
+            for (uint32_t base = nucl; base + 1u < L; base += 32u) {
+                const uint32_t pos = base + lane;
+                const uint32_t m = pos + 1u < L ? mask[pos] : 0u;
+                const uint32_t bal = __ballot_sync(FULL, m != 0u);
+                if (bal) { e = base + (uint32_t)__ffs((int)bal) - 1u; break; }
+            }
+            // (b) the run in front of it comes straight from the original read
+            const uint32_t want = e - nucl, have = L - k, run = want < have ? want : have;
+            for (uint32_t i = lane; i < run; i += 32u) seq[nucl + i] = orig[k + i];
+            nucl += run;
+            k += run;
+            if (run < want) { broke = true; break; }  // original exhausted before the loop ended
+            if (nucl + 1u >= L) break;
+        }
+        // (c) the reference's loop body, position by position, while something can happen
+        if (lane == 0) {
+            do {
+                uint32_t cur;
+                if (sp) cur = stk[--sp]; else if (k < L) cur = orig[k++]; else { broke = true; break; }
+                if (!is_acgt(cur)) { seq[nucl++] = (uint8_t)cur; continue; }  // ambiguous bases draw nothing (:190-192)
+                const uint32_t tb = o * L + nucl;
+                const uint32_t mk = mask[nucl];
+                if (mk & 15u) {
+                    for (uint32_t ln = 0; ln < 4; ++ln)
+                        if ((mk >> ln) & 1u) {
+                            const uint32_t ib = p.m.ins_base[tb * 4 + ln];
+                            stk[sp++] = (uint8_t)ib;
+                            if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, ln, cur, cur, ib, 255u);
+                        }
                 }
+                if ((mk >> (4u + base_code(cur))) & 1u) {
+                    uint32_t x;
+                    if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else { broke = true; break; }  // "ref" is read after the pop: IndexError -> no record
+                    if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, 4u, x, (uint32_t)'.', 0u, 255u);
+                    seq[nucl++] = (uint8_t)x;
+                } else {
+                    seq[nucl++] = (uint8_t)cur;
+                }
+            } while (nucl + 1u < L && (sp != 0u || mask[nucl] != 0u));
         }
-        const bool del = (mk >> (4u + base_code(cur))) & 1u;
-        if (del) {
-            uint32_t x;
-            if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;  // "ref" is read after the pop: IndexError -> no record
-            if (p.store_mutations) emit_event(p, gp0 + pair, o, 0u, nucl, 4u, x, (uint32_t)'.', 0u, 255u);
-            seq[outlen++] = (uint8_t)x;
-        } else {
-            seq[outlen++] = (uint8_t)cur;
-        }
+        nucl = __shfl_sync(FULL, nucl, 0);
+        k = __shfl_sync(FULL, k, 0);
+        sp = __shfl_sync(FULL, sp, 0);
+        broke = __shfl_sync(FULL, broke ? 1u : 0u, 0) != 0u;
     }
-    while (outlen < L) {  // the part of the list behind the loop position, truncated to L (:136-139)
-        uint32_t x;
-        if (sp) x = stk[--sp]; else if (k < L) x = orig[k++]; else break;
-        seq[outlen++] = (uint8_t)x;
+    // the part of the list behind the loop position, truncated to L (:136-139): LIFO first, then original bases
+    uint32_t outlen = nucl;
+    if (lane == 0)
+        while (outlen < L && sp) seq[outlen++] = stk[--sp];
+    outlen = __shfl_sync(FULL, outlen, 0);
+    {
+        const uint32_t want = L - outlen, have = L - k, run = want < have ? want : have;
+        for (uint32_t i = lane; i < run; i += 32u) seq[outlen + i] = orig[k + i];
+        outlen += run;
     }
     if (outlen < L) {  // extension from the reference sequence (:141-155)
         const uint32_t enc = u32p(l.sEnc)[pair];
         const uint64_t win = u64p(l.sWin)[rd], reclen = u64p(l.sRecLen)[pair];
         const uint64_t rec_abs = u64p(l.sWabs)[rd] - win;  // absolute index of the record's first base
-        uint32_t e = 0;
-        while (outlen < L) {
+        for (uint32_t e = lane; outlen + e < L; e += 32u) {
             uint32_t ch;
             if (o == 0) {
                 const uint64_t g = win + L + e;  // read_end + i
@@ -295,10 +334,10 @@ __device__ void replay_indels(const GenParams &p, const Lay &l, uint64_t gp0, ui
                 if (win < (uint64_t)e + 1u) ch = (uint32_t)'A';  // read_start - 1 - i < 0
                 else ch = complement_ascii(genome_ascii(p.g, enc, rec_abs + (win - 1u - e)));
             }
-            seq[outlen++] = (uint8_t)ch;
-            ++e;
+            seq[outlen + e] = (uint8_t)ch;
         }
     }
+    __syncwarp();
 }
 
 }  // namespace
@@ -753,9 +792,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                             }
                         }
                         __syncthreads();
-                        if (tid < nround) {
-                            uint8_t *slot = cta_scratch + (size_t)tid * p.scratch_stride;
-                            replay_indels(p, l, gp0, rel0, u32p(l.sSlow)[base + tid], slot, slot + p.scratch_mask_off);
+                        for (uint32_t sidx = tid >> 5; sidx < nround; sidx += blockDim.x >> 5) {  // one warp per read
+                            uint8_t *slot = cta_scratch + (size_t)sidx * p.scratch_stride;
+                            replay_indels_warp(p, l, gp0, rel0, u32p(l.sSlow)[base + sidx], slot, slot + p.scratch_mask_off, tid & 31u);
                         }
                         __syncthreads();
                     }

@@ -23,6 +23,7 @@
 #include "iss_device.cuh"
 #include "iss_kernels.h"
 #include "iss_deflate.h"
+#include "iss_genome.h"
 #include "iss_hostmem.h"
 
 namespace {
@@ -222,15 +223,6 @@ int rebuild_views(iss_ctx *c) {
         c->stats.model_bytes_device = c->model_bytes;
     }
     return ISS_OK;
-}
-
-// util.rev_comp's dictionary (iss/util.py:57-88): ACGT + YRWSKMNBVDH in either case
-bool in_alphabet(uint8_t ch) {
-    const uint32_t u = (uint32_t)(ch & 0xDF) - 65u;
-    // A B C D G H K M N R S T V W Y
-    const uint32_t mask = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3) | (1u << 6) | (1u << 7) | (1u << 10) | (1u << 12) |
-                          (1u << 13) | (1u << 17) | (1u << 18) | (1u << 19) | (1u << 21) | (1u << 22) | (1u << 24);
-    return u < 26u && ((mask >> u) & 1u) && (ch >= 'A');
 }
 
 uint32_t record_fixed_len(uint32_t L, uint32_t name_len, uint32_t cpu) {
@@ -485,74 +477,114 @@ int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
     if (!c || (!records && n)) return fail(ISS_E_ARG, "null argument");
     if (int rc = set_device(c)) return rc;
     if (c->active) return fail(ISS_E_STATE, "generation in progress");
-    // classify + size
-    std::vector<uint32_t> enc(n);
-    uint64_t names_bytes = 0, packed_bases = 64, ascii_bytes = 64;
-    std::vector<DevRecord> dr(n);
+    NvtxRange nvtx("iss:set_genome");
+    // 1. the records' bytes to a staging buffer in HBM (16-byte aligned starts); classification and packing happen there
+    std::vector<IssStagedRecord> st(n);
+    std::vector<uint64_t> unit_begin(n + 1, 0);
+    uint64_t stage_bytes = 0, names_bytes = 0;
     for (uint32_t r = 0; r < n; ++r) {
-        const iss_record &rec = records[r];
-        bool pure = true;
-        for (uint64_t k = 0; k < rec.len; ++k) {
-            const uint8_t ch = rec.seq[k];
-            if (ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T') continue;
-            pure = false;
-            if (!in_alphabet(ch)) {
+        if (!records[r].seq && records[r].len) return fail(ISS_E_ARG, "record with a null sequence");
+        st[r].stage_off = stage_bytes;
+        st[r].len = records[r].len;
+        st[r].data_off = 0; st[r].enc = 0; st[r].pad = 0;
+        stage_bytes = align_up(stage_bytes + records[r].len, 16);
+        unit_begin[r + 1] = unit_begin[r] + (records[r].len + 15) / 16;
+        names_bytes += records[r].name_len;
+    }
+    const uint64_t n_units = unit_begin[n];
+    uint8_t *d_stage = nullptr;
+    IssStagedRecord *d_recs = nullptr;
+    uint64_t *d_units = nullptr;
+    uint32_t *d_flags = nullptr;
+    unsigned long long *d_bad = nullptr;
+    uint8_t *d_blob = nullptr;
+    auto cleanup = [&] {
+        if (d_stage) cudaFree(d_stage);
+        if (d_recs) cudaFree(d_recs);
+        if (d_units) cudaFree(d_units);
+        if (d_flags) cudaFree(d_flags);
+        if (d_bad) cudaFree(d_bad);
+    };
+    uint64_t total = 0;
+    const int rc = [&]() -> int {
+        CU(cudaMalloc(&d_stage, stage_bytes + 32));
+        CU(cudaMemsetAsync(d_stage + (stage_bytes & ~(uint64_t)15), 0, 32, 0));
+        for (uint32_t r = 0; r < n; ++r)
+            if (records[r].len) CU(cudaMemcpyAsync(d_stage + st[r].stage_off, records[r].seq, records[r].len, cudaMemcpyHostToDevice, 0));
+        CU(cudaMalloc(&d_recs, sizeof(IssStagedRecord) * std::max<uint32_t>(n, 1)));
+        CU(cudaMalloc(&d_units, sizeof(uint64_t) * (n + 1)));
+        CU(cudaMalloc(&d_flags, sizeof(uint32_t) * std::max<uint32_t>(n, 1)));
+        CU(cudaMalloc(&d_bad, sizeof(unsigned long long) * std::max<uint32_t>(n, 1)));
+        CU(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * std::max<uint32_t>(n, 1), 0));
+        CU(cudaMemsetAsync(d_bad, 0xFF, sizeof(unsigned long long) * std::max<uint32_t>(n, 1), 0));
+        if (n) CU(cudaMemcpyAsync(d_recs, st.data(), sizeof(IssStagedRecord) * n, cudaMemcpyHostToDevice, 0));
+        CU(cudaMemcpyAsync(d_units, unit_begin.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, 0));
+        // 2. classify on the device
+        CU(iss_genome_classify(d_stage, d_recs, d_units, n, n_units, d_flags, d_bad, c->sm_count, 0));
+        std::vector<uint32_t> flags(n);
+        std::vector<unsigned long long> bad(n);
+        if (n) {
+            CU(cudaMemcpy(flags.data(), d_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(bad.data(), d_bad, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+        }
+        for (uint32_t r = 0; r < n; ++r)
+            if (bad[r] != ~0ull) {
                 char buf[160];
-                snprintf(buf, sizeof buf, "record %u: character 0x%02x at position %llu is outside the reference's alphabet", r, ch,
-                         (unsigned long long)k);
+                snprintf(buf, sizeof buf, "record %u: character 0x%02x at position %llu is outside the reference's alphabet", r,
+                         (unsigned)records[r].seq[bad[r]], bad[r]);
                 return fail(ISS_E_CHAR, buf);
             }
+        // 3. layout of the blob
+        uint64_t packed_bases = 64, ascii_bytes = 64, name_off = 0;
+        std::vector<DevRecord> dr(n);
+        for (uint32_t r = 0; r < n; ++r) {
+            const bool pure = !(flags[r] & 1u);
+            dr[r].len = records[r].len;
+            dr[r].enc = pure ? ISS_ENC_2BIT : ISS_ENC_ASCII;
+            dr[r].name_off = (uint32_t)name_off;
+            dr[r].name_len = records[r].name_len;
+            dr[r].pad = 0;
+            name_off += records[r].name_len;
+            if (pure) { dr[r].data_off = packed_bases; packed_bases = align_up(packed_bases + records[r].len, 64); }
+            else { dr[r].data_off = ascii_bytes; ascii_bytes = align_up(ascii_bytes + records[r].len, 16); }
+            st[r].data_off = dr[r].data_off;
+            st[r].enc = dr[r].enc;
         }
-        enc[r] = pure ? ISS_ENC_2BIT : ISS_ENC_ASCII;
-        dr[r].len = rec.len;
-        dr[r].enc = enc[r];
-        dr[r].name_off = (uint32_t)names_bytes;
-        dr[r].name_len = rec.name_len;
-        dr[r].pad = 0;
-        names_bytes += rec.name_len;
-        if (pure) { dr[r].data_off = packed_bases; packed_bases = align_up(packed_bases + rec.len, 64); }
-        else { dr[r].data_off = ascii_bytes; ascii_bytes = align_up(ascii_bytes + rec.len, 16); }
+        packed_bases += 128;  // tail pad: windows may be read up to 31 bases past a record
+        ascii_bytes += 64;
+        GenomeHeader gh{};
+        gh.magic = kGenomeMagic;
+        gh.n_records = n;
+        uint64_t off = align_up(sizeof(GenomeHeader), 16);
+        gh.recs_off = off; off = align_up(off + sizeof(DevRecord) * (uint64_t)n, 16);
+        gh.names_off = off; gh.names_bytes = names_bytes; off = align_up(off + names_bytes, 64);
+        gh.packed_off = off; gh.packed_bytes = packed_bases / 4; off = align_up(off + gh.packed_bytes, 64);
+        gh.ascii_off = off; gh.ascii_bytes = ascii_bytes; off = align_up(off + ascii_bytes, 64);
+        gh.total_bytes = off;
+        total = off;
+        std::vector<uint8_t> head(gh.packed_off, 0);  // header + record table + names: the only part built on the host
+        memcpy(head.data(), &gh, sizeof gh);
+        if (n) memcpy(head.data() + gh.recs_off, dr.data(), sizeof(DevRecord) * (size_t)n);
+        for (uint32_t r = 0; r < n; ++r) memcpy(head.data() + gh.names_off + dr[r].name_off, records[r].name, records[r].name_len);
+        CU(cudaMalloc(&d_blob, off));
+        CU(cudaMemsetAsync(d_blob, 0, off, 0));
+        CU(cudaMemcpyAsync(d_blob, head.data(), head.size(), cudaMemcpyHostToDevice, 0));
+        if (n) CU(cudaMemcpyAsync(d_recs, st.data(), sizeof(IssStagedRecord) * n, cudaMemcpyHostToDevice, 0));
+        // 4. pack on the device
+        CU(iss_genome_pack(d_stage, d_recs, d_units, n, n_units, reinterpret_cast<uint32_t *>(d_blob + gh.packed_off), d_blob + gh.ascii_off,
+                           c->sm_count, 0));
+        CU(cudaStreamSynchronize(0));
+        return ISS_OK;
+    }();
+    cleanup();
+    if (rc != ISS_OK) {
+        if (d_blob) cudaFree(d_blob);
+        return rc;
     }
-    packed_bases += 128;  // tail pad: windows may be read up to 31 bases past a record
-    ascii_bytes += 64;
-    GenomeHeader gh{};
-    gh.magic = kGenomeMagic;
-    gh.n_records = n;
-    uint64_t off = align_up(sizeof(GenomeHeader), 16);
-    gh.recs_off = off; off = align_up(off + sizeof(DevRecord) * (uint64_t)n, 16);
-    gh.names_off = off; gh.names_bytes = names_bytes; off = align_up(off + names_bytes, 64);
-    gh.packed_off = off; gh.packed_bytes = packed_bases / 4; off = align_up(off + gh.packed_bytes, 64);
-    gh.ascii_off = off; gh.ascii_bytes = ascii_bytes; off = align_up(off + ascii_bytes, 64);
-    gh.total_bytes = off;
-    std::vector<uint8_t> blob(off, 0);
-    memcpy(blob.data(), &gh, sizeof gh);
-    if (n) memcpy(blob.data() + gh.recs_off, dr.data(), sizeof(DevRecord) * (size_t)n);
-    uint32_t *packed = reinterpret_cast<uint32_t *>(blob.data() + gh.packed_off);
-    for (uint32_t r = 0; r < n; ++r) {
-        const iss_record &rec = records[r];
-        memcpy(blob.data() + gh.names_off + dr[r].name_off, rec.name, rec.name_len);
-        if (enc[r] == ISS_ENC_2BIT) {
-            const uint64_t b0 = dr[r].data_off;  // multiple of 64
-            uint32_t *w = packed + (b0 >> 4);
-            const uint64_t full = rec.len / 16;
-            for (uint64_t q = 0; q < full; ++q) {
-                const uint8_t *sp = rec.seq + q * 16;
-                uint32_t v = 0;
-                for (int m = 0; m < 16; ++m) v |= (uint32_t)((sp[m] >> 1) & 3u) << (2 * m);
-                w[q] = v;
-            }
-            uint32_t v = 0;
-            for (uint64_t k = full * 16; k < rec.len; ++k) v |= (uint32_t)((rec.seq[k] >> 1) & 3u) << (2 * (k & 15));
-            if (rec.len & 15) w[full] = v;
-        } else {
-            memcpy(blob.data() + gh.ascii_off + dr[r].data_off, rec.seq, rec.len);
-        }
-    }
-    if (c->d_genome) { cudaFree(c->d_genome); c->d_genome = nullptr; }
-    CU(cudaMalloc(&c->d_genome, off));
-    CU(cudaMemcpy(c->d_genome, blob.data(), off, cudaMemcpyHostToDevice));
-    c->genome_bytes = off;
-    c->stats.h2d_bytes += off;
+    if (c->d_genome) cudaFree(c->d_genome);
+    c->d_genome = d_blob;
+    c->genome_bytes = total;
+    c->stats.h2d_bytes += stage_bytes;
     return rebuild_views(c);
 }
 

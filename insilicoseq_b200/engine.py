@@ -81,6 +81,8 @@ class Engine(object):
         recs = []
         keep = []
         for name, seq in records:
+            if not isinstance(seq, (str, bytes, bytearray, memoryview, np.ndarray)):
+                seq = str(seq)  # e.g. Bio.Seq.Seq of a reference-side SeqRecord
             if isinstance(seq, str):
                 seq = seq.encode("ascii")
             if isinstance(name, str):
