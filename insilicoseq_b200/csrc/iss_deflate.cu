@@ -2,15 +2,19 @@
 //
 // The FASTQ text of a batch already sits in HBM; compressing it there is the only way the end-to-end rate can exceed
 // what PCIe can carry as plain text.  Format: a gzip file is a sequence of members (RFC 1952); every 64 KB chunk of
-// a stream becomes one member holding ONE dynamic-Huffman DEFLATE block (RFC 1951) of literals only (no LZ77):
+// a stream becomes one member holding ONE dynamic-Huffman DEFLATE block (RFC 1951): literals, plus one LZ77 match per
+// FASTQ record -- the name line "@name_i_cpu/1" against the previous record's (distance = that record's length; the
+// lines differ in their last digits only), found by pattern ("\n@" not preceded by "\n+") and verified byte by byte,
+// so any input stays valid, and never reaching back across a member boundary:
 //
-//   10 B gzip header | BFINAL=1 BTYPE=10 HLIT=0 HDIST=0 HCLEN=15 | 19 x 3 bit code-length-code lengths (0..15 -> 4 bits,
-//   16/17/18 unused) | 257 literal/EOB lengths + 1 distance length, 4 bits each | the literals | EOB | pad | CRC32 | ISIZE
+//   10 B gzip header | BFINAL=1 BTYPE=10 HLIT=29 HDIST=29 HCLEN=15 | 19 x 3 bit code-length-code lengths (0..15 -> 4 bits,
+//   16/17/18 unused) | 286 literal/length + 30 distance code lengths, 4 bits each | tokens | EOB | pad | CRC32 | ISIZE
 //
-// so the block header has a fixed size (1106 bits) and every symbol's bit position follows from a prefix sum.
-// Per call (= one FASTQ stream of one batch): byte histogram of a <= 4 MB sample -> ONE Huffman code, lengths limited to
-// 15 bits (two-queue merge + zlib's overflow repair, always a complete code; every byte value keeps a code) ->
-// canonical codes + block header.  Then one CTA per chunk: bit count per 128-byte slice -> prefix sum -> bit packing
+// so the block header has a fixed size (1338 bits) and every token's bit position follows from a prefix sum.
+// Per call (= one FASTQ stream of one batch): byte histogram of a <= 4 MB sample + the match statistics of the first
+// 16 KB -> ONE literal/length code and ONE distance code, lengths limited to 15 bits (two-queue merge + zlib's overflow
+// repair, always complete codes; every symbol keeps a code) -> canonical codes + block header.  Then one CTA per chunk:
+// name-line matches planned per 128-byte slice -> bit count per slice -> prefix sum -> bit packing
 // into shared memory -> CRC-32 from per-slice raw CRCs (slicing-by-4) advanced by x^(8 * bytes_after) (GF(2)
 // multiply, zlib's crc32_combine arithmetic) -> member written at its final offset, found by a decoupled look-back over
 // the member sizes (no staging copy).  Incompressible chunks fall back to stored blocks.
@@ -27,7 +31,40 @@ constexpr uint32_t kOutWords = 12288;  // 48 KB of packed bits per chunk in shar
 constexpr uint32_t kThreads = 512;     // threads of iss_deflate_kernel
 constexpr uint32_t kSlice = kChunk / kThreads;  // bytes per thread: 128
 constexpr uint32_t kPiece = 16384;     // granule of the histogram sample
-constexpr uint32_t kHeaderBits = 17 + 19 * 3 + 258 * 4;  // 1106
+constexpr uint32_t kLitLen = 286, kDist = 30;  // symbols of the two alphabets (HLIT = 29, HDIST = 29)
+constexpr uint32_t kHeaderBits = 17 + 19 * 3 + (kLitLen + kDist) * 4;  // 1338
+constexpr uint32_t kHdrWords = (kHeaderBits + 31) / 32;                // 42
+constexpr uint32_t kMaxTok = 1024;     // matches per member kept (a 64 KB chunk of 150 bp FASTQ holds ~200 records)
+constexpr uint32_t kSampleLz = 16384;  // bytes of the stream whose matches give the length / distance statistics
+
+// RFC 1951 3.2.5: length codes 257..285 and distance codes 0..29
+__constant__ uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
+                                       4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+__device__ __forceinline__ uint32_t len_code(uint32_t len) {  // 3..258 -> 0..28
+    uint32_t k = 28;
+    while (len < kLenBase[k]) --k;
+    return k;
+}
+__device__ __forceinline__ uint32_t dist_code(uint32_t dist) {  // 1..32768 -> 0..29 (zlib's d_code)
+    if (dist <= 4u) return dist - 1u;
+    const uint32_t d = dist - 1u, hb = 31u - (uint32_t)__clz((int)d);
+    return 2u * hb + ((d >> (hb - 1u)) & 1u);
+}
+// "@..." at x starts a FASTQ record: line start, and the line before is not the "+" separator (a quality line may begin with '@')
+__device__ __forceinline__ bool is_record_start(const uint8_t *__restrict__ b, uint32_t x) {
+    return x >= 3u && b[x] == '@' && b[x - 1u] == '\n' && !(b[x - 2u] == '+' && b[x - 3u] == '\n');
+}
+// common prefix of the name lines at s and q (q < s), newline excluded, as an LZ77 match length (0: no match)
+__device__ __forceinline__ uint32_t name_match(const uint8_t *__restrict__ b, uint32_t n, uint32_t s, uint32_t q) {
+    if (s - q > 32768u) return 0u;
+    uint32_t m = 0;
+    while (s + m < n && m < 258u && b[s + m] == b[q + m] && b[s + m] != '\n') ++m;
+    return m >= 3u ? m : 0u;
+}
 constexpr uint32_t kPoly = 0xedb88320u;
 
 __device__ __forceinline__ uint32_t multmodp(uint32_t a, uint32_t b) {  // a * b mod P over GF(2), reflected (zlib)
@@ -63,8 +100,9 @@ __device__ uint32_t x2nmodp(uint32_t n, uint32_t k) {  // x^(n * 2^k) mod P
 // The code of one iss_gz_compress call, built once from a sample of the stream and shared by all its members
 // (FASTQ of one batch is statistically uniform; any complete prefix code gives a valid member).
 struct GzCode {
-    uint32_t cl[260];   // bit-reversed canonical code | length << 16, symbols 0..255 and 256 = end of block
-    uint32_t hdr[36];   // the kHeaderBits bits of the block header (lengths included)
+    uint32_t cl[288];   // bit-reversed canonical code | length << 16: literals 0..255, 256 = end of block, 257..285 = match lengths
+    uint32_t dl[32];    // the same for the 30 distance codes
+    uint32_t hdr[44];   // the kHeaderBits bits of the block header (lengths included)
 };
 constexpr uint32_t kWorkHist = 0;     // word offsets inside the caller's work area (ISS_GZ_WORK_WORDS u32)
 constexpr uint32_t kWorkTicket = 260;  // next chunk to hand out
@@ -73,16 +111,18 @@ constexpr uint32_t kWorkCode = 264;
 static_assert(kWorkCode + sizeof(GzCode) / 4 <= ISS_GZ_WORK_WORDS, "work area too small");
 
 struct TableSmem {
-    uint32_t out[36];
-    uint32_t freq[260];
-    uint32_t keys[260];
-    uint32_t w[516];      // node weights during the merge, then node depths
+    uint32_t out[44];
+    uint32_t freq[288];
+    uint32_t keys[288];
+    uint32_t w[576];      // node weights during the merge, then node depths
     uint32_t bl[17];      // leaves per code length
     uint32_t first[17];   // first canonical code per length
     uint32_t total, overflow;
-    uint16_t parent[516];
-    uint32_t cl[260];
-    uint8_t lens[260];
+    uint16_t parent[576];
+    uint32_t cl[288];
+    uint8_t lens[288];
+    uint32_t tokf[64];    // sample statistics: [0..28] match-length codes, [32..61] distance codes
+    int32_t start[256];   // sample planning: record start inside each 64-byte slice of the first 16 KB (-1: none)
 };
 
 __device__ __forceinline__ void put_bits(uint32_t *out, uint32_t pos, uint32_t v, uint32_t nbits) {
@@ -193,23 +233,15 @@ __global__ void __launch_bounds__(256) iss_gz_hist_kernel(const uint8_t *__restr
     if (f) atomicAdd(&work[kWorkHist + tid], f);
 }
 
-// ---- 2. one CTA: the Huffman code of the call (every byte value keeps a code: frequency = sample count + 1) ------------
+// ---- 2. one CTA: the two Huffman codes of the call (every symbol keeps a code: frequency = sample count + 1) ------------
 // Lengths are limited to 15 bits the way zlib's gen_bitlen does it: depth capped at 15 while descending, `overflow` =
 // nodes deeper than that, then the repair loop on the per-length counts and lengths re-dealt to the leaves in frequency
 // order (the rarest get the longest codes); always a complete code.
-__global__ void __launch_bounds__(256) iss_gz_table_kernel(uint32_t *__restrict__ work) {
-    __shared__ TableSmem s;
-    const uint32_t tid = threadIdx.x;
-    constexpr uint32_t n = 257, root = 2 * n - 2;
-    if (tid == 0) s.total = s.overflow = 0;
-    if (tid < 36) s.out[tid] = 0;
+// In: s.freq[0..n).  Out: s.lens[0..n), s.cl[0..n) (bit-reversed code | length << 16).  256 threads, n <= 288.
+__device__ void build_code(TableSmem &s, uint32_t n, uint32_t tid) {
+    const uint32_t root = 2 * n - 2;
+    if (tid == 0) s.overflow = 0;
     if (tid < 17) s.bl[tid] = 0;
-    __syncthreads();
-    const uint32_t f0 = work[kWorkHist + tid];
-    atomicAdd(&s.total, f0);
-    s.freq[tid] = f0 + 1u;
-    __syncthreads();
-    if (tid == 0) s.freq[256] = (s.total >> 16) ? (s.total >> 16) : 1u;  // end of block: one per 64 KB member
     __syncthreads();
     // rank sort by (frequency, symbol); frequencies stay below 2^23 (sample <= 4 MB)
     for (uint32_t sym = tid; sym < n; sym += 256) {
@@ -221,18 +253,7 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(uint32_t *__restrict_
     __syncthreads();
     for (uint32_t i = tid; i < n; i += 256) s.w[i] = s.keys[i] >> 9;
     __syncthreads();
-    if (tid == 0) {
-        merge_tree(s, n);
-        // constant part of the block header: BFINAL=1, BTYPE=2, HLIT=0, HDIST=0, HCLEN=15, then the 19 code-length-code
-        // lengths in the order 16,17,18,0,8,7,...: three zeros and sixteen fours
-        uint32_t pos = 0;
-        put_bits(s.out, pos, 1u, 1); pos += 1;
-        put_bits(s.out, pos, 2u, 2); pos += 2;
-        pos += 10;  // HLIT, HDIST = 0
-        put_bits(s.out, pos, 15u, 4); pos += 4;
-        pos += 9;   // lengths of 16, 17, 18 = 0
-        for (int k = 0; k < 16; ++k) { put_bits(s.out, pos, 4u, 3); pos += 3; }
-    }
+    if (tid == 0) merge_tree(s, n);
     __syncthreads();
     // node depths by walking to the root (w[] is free now)
     for (uint32_t i = tid; i < root; i += 256) {
@@ -280,25 +301,104 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(uint32_t *__restrict_
         uint32_t idx = 0;
         for (uint32_t o = 0; o < sym; ++o) idx += (s.lens[o] == l) ? 1u : 0u;
         s.cl[sym] = (__brev(s.first[l] + idx) >> (32u - l)) | (l << 16);
-        // the 257 literal/EOB lengths (+ a zero distance length), each as the 4-bit code of its value (flat code, MSB first)
-        put_bits(s.out, 74u + 4u * sym, __brev(l) >> 28, 4);
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__restrict__ in, uint64_t n_in, uint32_t *__restrict__ work) {
+    __shared__ TableSmem s;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) s.total = 0;
+    if (tid < 44) s.out[tid] = 0;
+    if (tid < 64) s.tokf[tid] = 0;
+    __syncthreads();
+    const uint32_t f0 = work[kWorkHist + tid];
+    atomicAdd(&s.total, f0);
+    s.freq[tid] = f0 + 1u;
+    // match statistics from the first 16 KB of the stream: the record starts of each 64-byte slice, each name line
+    // against the one before it -- the same plan the member kernel makes
+    const uint32_t ns = (uint32_t)(n_in < kSampleLz ? n_in : kSampleLz);
+    {
+        int32_t st = -1;
+        for (uint32_t x = tid * 64u; x < tid * 64u + 64u && x < ns; ++x)
+            if (is_record_start(in, x)) st = (int32_t)x;
+        s.start[tid] = st;
+    }
+    __syncthreads();
+    {
+        int32_t prev = -1;
+        for (int32_t t = (int32_t)tid - 1; t >= 0 && prev < 0; --t) prev = s.start[t];
+        // a slice holds at most a few records of very short reads: the statistics take the last start of each slice only
+        if (s.start[tid] >= 0 && prev >= 0) {
+            const uint32_t m = name_match(in, ns, (uint32_t)s.start[tid], (uint32_t)prev);
+            if (m) {
+                atomicAdd(&s.tokf[len_code(m)], 1u);
+                atomicAdd(&s.tokf[32u + dist_code((uint32_t)(s.start[tid] - prev))], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t scale = ns ? (s.total / ns > 1u ? s.total / ns : 1u) : 1u;  // sampled bytes per byte of the 16 KB window
+    if (tid == 0) s.freq[256] = (s.total >> 16) ? (s.total >> 16) : 1u;  // end of block: one per 64 KB member
+    if (tid < 29) s.freq[257 + tid] = s.tokf[tid] * scale + 1u;
+    __syncthreads();
+    build_code(s, kLitLen, tid);
     GzCode *code = reinterpret_cast<GzCode *>(work + kWorkCode);
-    for (uint32_t sym = tid; sym < 260; sym += 256) code->cl[sym] = sym < n ? s.cl[sym] : 0u;
-    if (tid < 36) code->hdr[tid] = s.out[tid];
+    for (uint32_t sym = tid; sym < 288; sym += 256) code->cl[sym] = sym < kLitLen ? s.cl[sym] : 0u;
+    // the 286 literal/length lengths, each as the 4-bit code of its value (flat code-length code, MSB first)
+    for (uint32_t sym = tid; sym < kLitLen; sym += 256) put_bits(s.out, 74u + 4u * sym, __brev((uint32_t)s.lens[sym]) >> 28, 4);
+    __syncthreads();
+    if (tid < kDist) s.freq[tid] = s.tokf[32u + tid] * scale + 1u;
+    __syncthreads();
+    build_code(s, kDist, tid);
+    if (tid < 32) code->dl[tid] = tid < kDist ? s.cl[tid] : 0u;
+    if (tid < kDist) put_bits(s.out, 74u + 4u * (kLitLen + tid), __brev((uint32_t)s.lens[tid]) >> 28, 4);
+    if (tid == 0) {
+        // constant part of the block header: BFINAL=1, BTYPE=2, HLIT=29, HDIST=29, HCLEN=15, then the 19 code-length-code
+        // lengths in the order 16,17,18,0,8,7,...: three zeros and sixteen fours
+        uint32_t pos = 0;
+        put_bits(s.out, pos, 1u, 1); pos += 1;
+        put_bits(s.out, pos, 2u, 2); pos += 2;
+        put_bits(s.out, pos, 29u, 5); pos += 5;
+        put_bits(s.out, pos, 29u, 5); pos += 5;
+        put_bits(s.out, pos, 15u, 4); pos += 4;
+        pos += 9;   // lengths of 16, 17, 18 = 0
+        for (int k = 0; k < 16; ++k) { put_bits(s.out, pos, 4u, 3); pos += 3; }
+    }
+    __syncthreads();
+    if (tid < 44) code->hdr[tid] = s.out[tid];
 }
 
 // ---- 3. the members: one CTA per 64 KB chunk, 512 threads x 128-byte slices ----------------------------------------------
 struct Smem {
     uint32_t out[kOutWords];
     uint32_t crcT[4][256];
-    uint32_t cl[260];
-    uint32_t misc[64];  // 3 crc accumulator, 4 x^(8*(n % kSlice)), 8.. warp sums
-    uint8_t len8[260];
+    uint32_t cl[288];
+    uint32_t dl[32];
+    uint32_t misc[64];       // 0 ticket, 3 crc accumulator, 4 x^(8*(n % kSlice)), 5/6 member offset, 7 matches, 8.. warp sums
+    uint32_t tok_pos[kMaxTok];   // the member's matches in stream order: start inside the chunk,
+    uint32_t tok_ld[kMaxTok];    //   length | distance << 16 (distance 32768 stored as 0)
+    int32_t last_start[kThreads];  // last record start inside each slice (-1: none)
+    uint16_t tok_off[kThreads + 1];  // matches that start before each slice
+    uint8_t len8[288];
 };
 
 extern __shared__ __align__(16) uint8_t iss_gz_smem[];
+
+namespace {
+// bits of one match: length code + extra, distance code + extra
+__device__ __forceinline__ uint32_t match_bits(const Smem &s, uint32_t len, uint32_t dist) {
+    const uint32_t lc = len_code(len), dc = dist_code(dist);
+    return (s.cl[257u + lc] >> 16) + kLenExtra[lc] + (s.dl[dc] >> 16) + kDistExtra[dc];
+}
+__device__ __forceinline__ void flush_acc(Smem &s, uint64_t &acc, uint32_t &accbits, uint32_t &wi) {
+    if (accbits >= 32u) {
+        atomicOr(&s.out[wi++], (uint32_t)acc);
+        acc >>= 32;
+        accbits -= 32u;
+    }
+}
+}  // namespace
 
 __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t *__restrict__ in, uint64_t n_in, uint8_t *__restrict__ out,
                                                                   unsigned long long *status, uint32_t *__restrict__ work,
@@ -307,11 +407,12 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
     const GzCode *code = reinterpret_cast<const GzCode *>(work + kWorkCode);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (uint32_t i = tid; i < 1024; i += kThreads) s.crcT[i >> 8][i & 255u] = g_gz.crc[i >> 8][i & 255u];
-    for (uint32_t i = tid; i < 260; i += kThreads) {
+    for (uint32_t i = tid; i < 288; i += kThreads) {
         const uint32_t e = code->cl[i];
         s.cl[i] = e;
         s.len8[i] = (uint8_t)(e >> 16);
     }
+    if (tid < 32) s.dl[tid] = code->dl[tid];
     for (;;) {
         __syncthreads();  // previous chunk fully written out; tables loaded
         if (tid == 0) s.misc[0] = atomicAdd(&work[kWorkTicket], 1u);
@@ -321,12 +422,13 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         const uint64_t base = (uint64_t)c * kChunk;
         const uint32_t n = (uint32_t)((n_in - base < kChunk) ? (n_in - base) : kChunk);
         const uint8_t *src = in + base;
-        for (uint32_t i = tid; i < kOutWords; i += kThreads) s.out[i] = i < 36u ? code->hdr[i] : 0u;
+        for (uint32_t i = tid; i < kOutWords; i += kThreads) s.out[i] = i < kHdrWords ? code->hdr[i] : 0u;
         if (tid >= 1 && tid < 64) s.misc[tid] = 0;
-        // 1. my slice (kSlice contiguous bytes, read 16 at a time): bit count + raw CRC (slicing-by-4)
+        // 1. my slice (kSlice contiguous bytes, read 16 at a time): literal bit count + raw CRC (slicing-by-4) + record starts
         const uint32_t lo = tid * kSlice, hi = (lo + kSlice < n) ? lo + kSlice : n;
         const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);  // chunk base and slices are 16-byte aligned
         uint32_t bits = 0, crc = 0;
+        int32_t st0 = -1, st1 = -1;  // the last two record starts of the slice (st0 < st1)
         for (uint32_t i = lo; i < hi; i += 16u) {
             const uint4 v = __ldg(src4 + ((i - lo) >> 4));
             const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
@@ -344,7 +446,64 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                         crc = s.crcT[0][(crc ^ b) & 0xFFu] ^ (crc >> 8);
                     }
                 }
+                const uint32_t z = wd ^ 0x40404040u;  // any '@' in this word?
+                if ((z - 0x01010101u) & ~z & 0x80808080u) {
+                    for (uint32_t j = 0; j < 4u; ++j) {
+                        const uint32_t x = i + 4u * k + j;
+                        if (x < hi && ((wd >> (8u * j)) & 0xFFu) == '@' && is_record_start(src, x)) { st0 = st1; st1 = (int32_t)x; }
+                    }
+                }
             }
+        }
+        s.last_start[tid] = st1;
+        __syncthreads();  // out[] initialised, misc zeroed, record starts visible
+        // 2. name-line matches that start in my slice: each record start against the one before it (inside this member)
+        uint32_t mlen[2] = {0, 0}, mpos[2] = {0, 0}, mdist[2] = {0, 0}, nm = 0;
+        if (st1 >= 0) {
+            int32_t before = -1;  // the last record start in an earlier slice of this member
+            for (int32_t t = (int32_t)tid - 1; t >= 0 && before < 0; --t) before = s.last_start[t];
+            const int32_t first = st0 >= 0 ? st0 : st1;
+            if (before >= 0) {
+                const uint32_t m = name_match(src, n, (uint32_t)first, (uint32_t)before);
+                if (m) { mpos[nm] = (uint32_t)first; mlen[nm] = m; mdist[nm] = (uint32_t)(first - before); ++nm; }
+            }
+            if (st0 >= 0) {  // two starts in this slice (reads of a few dozen bases): the second against the first
+                const uint32_t m = name_match(src, n, (uint32_t)st1, (uint32_t)st0);
+                if (m) { mpos[nm] = (uint32_t)st1; mlen[nm] = m; mdist[nm] = (uint32_t)(st1 - st0); ++nm; }
+            }
+        }
+        // exclusive scan of the match counts -> the member's matches in stream order
+        uint32_t cincl = nm;
+        for (uint32_t d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, cincl, d);
+            if (lane >= d) cincl += v;
+        }
+        if (lane == 31) s.misc[32 + warp] = cincl;
+        __syncthreads();
+        uint32_t cwarp = 0;
+        for (uint32_t w = 0; w < warp; ++w) cwarp += s.misc[32 + w];
+        const uint32_t my_first = cwarp + cincl - nm;  // matches starting before my slice
+        for (uint32_t j = 0; j < nm; ++j)
+            if (my_first + j < kMaxTok) { s.tok_pos[my_first + j] = mpos[j]; s.tok_ld[my_first + j] = mlen[j] | (mdist[j] << 16); }
+        s.tok_off[tid] = (uint16_t)(my_first < kMaxTok ? my_first : kMaxTok);
+        if (tid == kThreads - 1) {
+            const uint32_t tot = my_first + nm;
+            s.tok_off[kThreads] = (uint16_t)(tot < kMaxTok ? tot : kMaxTok);
+        }
+        __syncthreads();
+        // 3. my slice's bits: literals of the bytes no match covers + the matches that start here
+        const uint32_t t_begin = s.tok_off[tid], t_end = s.tok_off[tid + 1];
+        uint32_t cov_end = lo;  // bytes [lo, cov_end) belong to a match that started in an earlier slice
+        if (t_begin > 0) {
+            const uint32_t e = s.tok_pos[t_begin - 1] + (s.tok_ld[t_begin - 1] & 0xFFFFu);
+            if (e > lo) cov_end = e < hi ? e : hi;
+        }
+        for (uint32_t x = lo; x < cov_end; ++x) bits -= s.len8[src[x]];
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t ps = s.tok_pos[t], ld = s.tok_ld[t], len = ld & 0xFFFFu, dist = (ld >> 16) ? (ld >> 16) : 32768u;
+            const uint32_t e = ps + len < hi ? ps + len : hi;
+            for (uint32_t x = ps; x < e; ++x) bits -= s.len8[src[x]];
+            bits += match_bits(s, len, dist);
         }
         // block-wide exclusive scan of `bits`
         uint32_t incl = bits;
@@ -352,7 +511,6 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += v;
         }
-        __syncthreads();  // out[] initialised, misc zeroed
         if (lane == 31) s.misc[8 + warp] = incl;
         if (tid == 0) s.misc[4] = x2nmodp(n % kSlice, 3);
         __syncthreads();
@@ -372,23 +530,49 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             const uint64_t excl = look_back(status, c, 18u + nbytes, lane);
             if (lane == 0) { s.misc[5] = (uint32_t)excl; s.misc[6] = (uint32_t)(excl >> 32); }
         }
-        // 2. pack my literals
+        // 4. pack my tokens
         if (!too_big) {
             uint64_t acc = 0;
             uint32_t accbits = pos & 31u, wi = pos >> 5;
+            uint32_t t = t_begin;
+            uint32_t next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
+            uint32_t skip_to = cov_end;  // bytes below this position are covered by a match
             for (uint32_t i = lo; i < hi; i += 16u) {
                 const uint4 v = __ldg(src4 + ((i - lo) >> 4));
                 const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+                if (skip_to <= i && next_tok >= i + 16u) {  // 16 plain literals
 #pragma unroll
-                for (uint32_t k = 0; k < 16; ++k) {
-                    if (i + k < hi) {
-                        const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
-                        acc |= (uint64_t)(e & 0xFFFFu) << accbits;
-                        accbits += e >> 16;
-                        if (accbits >= 32u) {
-                            atomicOr(&s.out[wi++], (uint32_t)acc);
-                            acc >>= 32;
-                            accbits -= 32u;
+                    for (uint32_t k = 0; k < 16; ++k) {
+                        if (i + k < hi) {
+                            const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
+                            acc |= (uint64_t)(e & 0xFFFFu) << accbits;
+                            accbits += e >> 16;
+                            flush_acc(s, acc, accbits, wi);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (uint32_t k = 0; k < 16 && i + k < hi; ++k) {
+                        const uint32_t x = i + k;
+                        if (x < skip_to) continue;
+                        if (x == next_tok) {
+                            const uint32_t ld = s.tok_ld[t], len = ld & 0xFFFFu, dist = (ld >> 16) ? (ld >> 16) : 32768u;
+                            const uint32_t lc = len_code(len), dc = dist_code(dist);
+                            const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
+                            acc |= (uint64_t)((le & 0xFFFFu) | ((len - kLenBase[lc]) << (le >> 16))) << accbits;
+                            accbits += (le >> 16) + kLenExtra[lc];
+                            flush_acc(s, acc, accbits, wi);
+                            acc |= (uint64_t)((de & 0xFFFFu) | ((dist - kDistBase[dc]) << (de >> 16))) << accbits;
+                            accbits += (de >> 16) + kDistExtra[dc];
+                            flush_acc(s, acc, accbits, wi);
+                            skip_to = x + len;
+                            ++t;
+                            next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
+                        } else {
+                            const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
+                            acc |= (uint64_t)(e & 0xFFFFu) << accbits;
+                            accbits += e >> 16;
+                            flush_acc(s, acc, accbits, wi);
                         }
                     }
                 }
@@ -396,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             if (accbits) atomicOr(&s.out[wi], (uint32_t)acc);
             if (tid == 0) put_bits(s.out, kHeaderBits + total, eob & 0xFFFFu, eob >> 16);
         }
-        // 3. CRC-32 of the chunk: raw slice CRCs advanced over the bytes that follow them, XOR-reduced
+        // 5. CRC-32 of the chunk: raw slice CRCs advanced over the bytes that follow them, XOR-reduced
         uint32_t part = 0;
         if (hi > lo) {
             const uint32_t after = n - hi;  // = (after / kSlice) * kSlice + (n % kSlice) for every slice but the last
@@ -407,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         for (uint32_t d = 16; d; d >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, d);
         if (lane == 0) atomicXor(&s.misc[3], part);
         __syncthreads();
-        // 4. the member at its final place: header, deflate bytes, CRC32, ISIZE
+        // 6. the member at its final place: header, deflate bytes, CRC32, ISIZE
         const uint64_t off = (uint64_t)s.misc[5] | ((uint64_t)s.misc[6] << 32);
         if (off >= kFail) {
             if (tid == 0 && c + 1u == n_chunks) status[n_chunks] = ~0ull;
@@ -498,7 +682,7 @@ cudaError_t iss_gz_compress(const uint8_t *d_in, uint64_t n_in, uint64_t *d_stat
     const uint32_t piece_stride = (uint32_t)((n_pieces + 255) / 256);
     const uint32_t n_sampled = (uint32_t)((n_pieces + piece_stride - 1) / piece_stride);
     iss_gz_hist_kernel<<<n_sampled < (uint32_t)sm_count ? n_sampled : (uint32_t)sm_count, 256, 0, stream>>>(d_in, n_in, piece_stride, d_work);
-    iss_gz_table_kernel<<<1, 256, 0, stream>>>(d_work);
+    iss_gz_table_kernel<<<1, 256, 0, stream>>>(d_in, n_in, d_work);
     const uint32_t grid = nc < (uint32_t)(sm_count * 3) ? nc : (uint32_t)(sm_count * 3);
     iss_deflate_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(d_in, n_in, d_out, reinterpret_cast<unsigned long long *>(d_status), d_work, nc);
     return cudaGetLastError();

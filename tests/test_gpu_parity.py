@@ -305,6 +305,47 @@ def test_gpu_gzip_roundtrip_arbitrary_bytes():
     assert ratio > 2.0, ratio  # Huffman-only: ~2.4x on L=301 MiSeq text, ~3x on 150 bp reads (gzip -6: ~3.8x)
 
 
+def test_gpu_gzip_name_line_matches():
+    """The LZ77 part of the GPU gzip: one match per FASTQ record, its name line against the previous record's.  Cases that
+    stress the parallel planning: reads so short that a 128-byte slice holds several records, names longer than a slice
+    and longer than the 258-byte match limit, quality lines that begin with '@', records 40 KB apart (beyond the 32 KB
+    window), "\n@" patterns in arbitrary bytes, and streams whose members end inside a name line."""
+    import gzip
+
+    from insilicoseq_b200.engine import Engine
+
+    rng = np.random.RandomState(5)
+
+    def fastq(n, L, name, qual0=None):
+        out = []
+        for i in range(n):
+            seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L))
+            q = bytes(rng.randint(33, 75, L).astype(np.uint8))
+            if qual0 is not None:
+                q = qual0 + q[1:]
+            out.append(b"@%s_%d_0/1\n%s\n+\n%s\n" % (name, i, seq, q))
+        return b"".join(out)
+
+    samples = [fastq(30000, 8, b"s"), fastq(20000, 20, b"contig_7"), fastq(3000, 150, b"x" * 140), fastq(1500, 150, b"n" * 300),
+               fastq(4000, 150, b"syn5M", qual0=b"@"), fastq(40, 20000, b"far_apart"), fastq(5000, 151, b"NZ_CP0123.1|plasmid"),
+               b"\n@".join(rng.bytes(200) for _ in range(3000)), (b"@a\nAC\n+\n@@\n" * 30000)[3:]]
+    with Engine(0) as e:
+        for data in samples:
+            z = e.gzip(data)
+            assert gzip.decompress(z) == data, len(data)
+        # the benchmark's text: MiSeq model at 150 positions.  Literals alone reach 2.82 on it; the name match must show
+        from insilicoseq_b200 import engine as eng_mod
+        from insilicoseq_b200 import error_models
+
+        e.set_genome([("syn5M", fixtures.synth_genome(3, 400000).encode())])
+        e.set_model(error_models.KDErrorModel(fixtures.model_path("models/miseq_150.npz")))
+        items = eng_mod.worker_items([(0, 30000)], 0, 42, e.record_lengths, e.read_length)
+        plain = b"".join(b.r1.tobytes() for b in e.generate(items))
+        z = b"".join(b.r1.tobytes() for b in e.generate(items, compress=True))
+        assert gzip.decompress(z) == plain
+        assert len(plain) / len(z) > 2.95, len(plain) / len(z)
+
+
 def test_compressed_batches_decompress_to_the_plain_output():
     import gzip
 
