@@ -211,7 +211,7 @@ __device__ __forceinline__ void emit_event(const GenParams &p, uint64_t gpair, u
 __device__ __forceinline__ void apply_substitution(const GenParams &p, const Lay &l, uint64_t gp0, uint32_t rel0, uint32_t rd, uint32_t pos) {
     const uint32_t T = p.tile_pairs, L = p.L;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
-    uint8_t *seq = imgp(l, o) + rel0 + u32p(l.sRel)[pair];
+    uint8_t *seq = imgp(l, o) + (uint32_t)(rel0 + u32p(l.sRel)[pair]);  // the sum wraps in 32 bits by construction
     const uint32_t c = seq[pos];
     if (!is_acgt(c)) return;  // "RYWSMKHBVDN" are never substituted (__init__.py:94)
     const uint32_t code = base_code(c);
@@ -254,7 +254,7 @@ __device__ __noinline__ void replay_indels_warp(const GenParams &p, const Lay &l
                                    const uint8_t *mask, uint32_t lane) {
     const uint32_t T = p.tile_pairs, L = p.L, FULL = 0xFFFFFFFFu;
     const uint32_t o = rd >= T ? 1u : 0u, pair = rd - o * T;
-    uint8_t *seq = imgp(l, o) + rel0 + u32p(l.sRel)[pair];
+    uint8_t *seq = imgp(l, o) + (uint32_t)(rel0 + u32p(l.sRel)[pair]);  // the sum wraps in 32 bits by construction
     uint8_t *orig = scratch;       // [L]  the read before indels
     uint8_t *stk = scratch + L;    // [4L] LIFO of inserted bases (lane 0 only)
     for (uint32_t i = lane; i < L; i += 32u) orig[i] = seq[i];
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         // ---- phase 2a: record skeleton, one thread per read:  "@{name}_{i}_{cpu}/{1|2}\n" ... "\n+\n" ... "\n"
         if (valid && half == 0) {
             const DevSegment *sg = p.segs + u32p(l.sSeg)[pair];
-            uint8_t *img = imgp(l, o) + rel0 + (uint32_t)u64p(l.sOff)[pair];
+            uint8_t *img = imgp(l, o) + (uint32_t)(rel0 + (uint32_t)u64p(l.sOff)[pair]);  // wraps in 32 bits by construction
             const uint64_t i = u64p(l.sP)[pair] - sg->item_base;
             const DevRecord *rec = p.g.recs + sg->rec;
             uint32_t w = 0;
@@ -722,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                     for (uint32_t e = tid; e < nsurv; e += blockDim.x) {
                         const uint32_t v = u32p(l.sSurv)[e];
                         const uint32_t srd = v >> 24, bits = (v >> 16) & 0xFFu, so = srd >= T ? 1u : 0u, sp_ = srd - so * T;
-                        const uint32_t c = (imgp(l, so) + rel0 + u32p(l.sRel)[sp_])[v & 0xFFFFu];
+                        const uint32_t c = (imgp(l, so) + (uint32_t)(rel0 + u32p(l.sRel)[sp_]))[v & 0xFFFFu];
                         if (!is_acgt(c)) continue;  // ambiguous bases draw nothing (:190-192)
                         if (((bits & 15u) || ((bits >> (4u + base_code(c))) & 1u)) && atomicExch(&u32p(l.sFlag)[srd], 1u) == 0u)
                             u32p(l.sSlow)[atomicAdd(&u32p(l.sCtl)[1], 1u)] = srd;
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 const Philox4 w = philox4x32_10_rk(pos >> 1, iss_read_stream(to, ISS_K_QUAL) | (u32p(l.sAtt)[tp] << 8), (uint32_t)tP,
                                                    (uint32_t)(tP >> 32), p.rk);
                 const uint32_t q = quality_exact(p, trd, pos, (pos & 1u) ? w.z : w.x);
-                (imgp(l, to) + rel0 + u32p(l.sRel)[tp] + L + 3u)[pos] = (uint8_t)(q + 33u);
+                (imgp(l, to) + (uint32_t)(rel0 + u32p(l.sRel)[tp]) + L + 3u)[pos] = (uint8_t)(q + 33u);
                 if (((pos & 1u) ? w.w : w.y) > u32p(l.sErrThr)[q]) {  // a handful per tile: applied in place, no second list
                     apply_substitution(p, l, gp0, rel0, trd, pos);
                     atomicAdd(p.counters + 1, 1ull);
