@@ -14,7 +14,11 @@
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -34,10 +38,11 @@ extern "C" void iss_set_last_error(const char *msg);  // iss_runtime.cu
 namespace {
 
 struct WriteTask {
-    int fd;
+    int fd;             // < 0: memcpy into `dst` (a mapping of the output file)
     const uint8_t *ptr;
     uint64_t len;
-    int64_t off;  // < 0: append (write(2) on an O_APPEND descriptor; only ever issued by one thread at a time)
+    int64_t off;        // fd >= 0: file offset for pwrite; < 0: append (write(2) on an O_APPEND descriptor, one thread at a time)
+    uint8_t *dst;
 };
 
 class WriterPool {
@@ -73,6 +78,10 @@ private:
             }
             int e = 0;
             uint64_t done = 0;
+            if (t.fd < 0) {  // a piece of a mapped file: page faults of different pieces are served in parallel
+                memcpy(t.dst, t.ptr, t.len);
+                done = t.len;
+            }
             while (done < t.len) {
                 const ssize_t r = t.off < 0 ? write(t.fd, t.ptr + done, t.len - done)
                                             : pwrite(t.fd, t.ptr + done, t.len - done, (off_t)(t.off + (int64_t)done));
@@ -100,6 +109,23 @@ int fail_io(const std::string &msg) {
     return ISS_E_IO;
 }
 
+// One output stream.  Buffered write(2)/pwrite(2) to ONE file are serialised by the inode lock whatever the number of
+// threads (measured: 2.7 GB/s into tmpfs with 4 or with 16 threads), so regular files are written through a shared mapping
+// of the batch's byte range instead: ftruncate to the new end, mmap, parallel memcpy of 4 MB pieces, munmap.  Anything
+// that is not a regular file (/dev/null, a pipe) and ISS_WRITER=pwrite take the write(2) path.
+struct OutFile {
+    int fd = -1;
+    bool mapped = false;
+    uint64_t size = 0;  // current file size (mapped mode)
+    uint64_t pos = 0;   // where the next batch goes
+};
+
+bool room_for(int fd, uint64_t bytes) {  // a mapping of a full file system ends in SIGBUS, not in an error code
+    struct statvfs v;
+    if (fstatvfs(fd, &v) != 0) return true;
+    return (uint64_t)v.f_bavail * v.f_frsize > bytes + (64ull << 20);
+}
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -115,15 +141,30 @@ int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_ite
     const double t0 = now_ms();
     int fd[3] = {-1, -1, -1};
     const char *paths[3] = {sink->path_r1, sink->path_r2, sink->path_vcf};
+    const char *wmode = getenv("ISS_WRITER");
+    const bool want_map = !(wmode && !strcmp(wmode, "pwrite"));
+    OutFile of[2];
     for (int k = 0; k < 3; ++k) {
         if (!paths[k]) continue;
-        int flags = O_WRONLY | O_CREAT | (sink->truncate ? O_TRUNC : 0);
-        if (sink->append || k == 2) flags |= O_APPEND;
+        int flags = O_CREAT | (sink->truncate ? O_TRUNC : 0);
+        struct stat sb;
+        const bool regular = k < 2 && want_map && (stat(paths[k], &sb) != 0 || S_ISREG(sb.st_mode));
+        flags |= regular ? O_RDWR : O_WRONLY;  // a shared mapping needs read access
+        if (!regular && (sink->append || k == 2)) flags |= O_APPEND;
         fd[k] = open(paths[k], flags, 0666);
         if (fd[k] < 0) {
             const std::string msg = std::string("cannot open ") + paths[k] + ": " + strerror(errno);
             for (int j = 0; j < k; ++j) if (fd[j] >= 0) close(fd[j]);
             return fail_io(msg);
+        }
+        if (k < 2) {
+            of[k].fd = fd[k];
+            of[k].mapped = regular && fstat(fd[k], &sb) == 0 && S_ISREG(sb.st_mode);
+            of[k].size = of[k].mapped ? (uint64_t)sb.st_size : 0;
+            of[k].pos = sink->append ? of[k].size : (k == 0 ? sink->offset_r1 : sink->offset_r2);
+            if (!of[k].mapped && (sink->append)) { /* O_APPEND was not set for a would-be mapping that is not regular after all */
+                fcntl(fd[k], F_SETFL, fcntl(fd[k], F_GETFL) | O_APPEND);
+            }
         }
     }
     auto close_all = [&] { for (int k = 0; k < 3; ++k) if (fd[k] >= 0) close(fd[k]); };
@@ -131,10 +172,10 @@ int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_ite
     if (rc != ISS_OK) { close_all(); return rc; }
     const unsigned nthreads = sink->writer_threads ? sink->writer_threads : 8u;
     const uint64_t piece = 4ull << 20;
+    const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
     int io_err = 0;
     {
         WriterPool pool(nthreads);
-        uint64_t off[2] = {sink->offset_r1, sink->offset_r2};
         iss_batch b;
         int have = 0;
         for (;;) {
@@ -144,21 +185,48 @@ int iss_ctx_write_files(iss_ctx *ctx, const iss_work_item *items, uint64_t n_ite
             nvtxRangePushA("iss:write_batch");
             const uint8_t *src[2] = {b.r1, b.r2};
             const uint64_t len[2] = {b.nbytes, b.nbytes2};
+            struct Map { uint8_t *base; uint64_t bytes; } maps[2] = {{nullptr, 0}, {nullptr, 0}};
             for (int k = 0; k < 2; ++k) {
-                if (fd[k] < 0 || !src[k]) continue;
-                if (sink->append) {
-                    pool.push(WriteTask{fd[k], src[k], len[k], -1});  // one task per stream: appends stay ordered
-                } else {
-                    for (uint64_t at = 0; at < len[k]; at += piece)
-                        pool.push(WriteTask{fd[k], src[k] + at, std::min(piece, len[k] - at), (int64_t)(off[k] + at)});
+                if (fd[k] < 0 || !src[k] || !len[k]) continue;
+                OutFile &f = of[k];
+                if (f.mapped) {
+                    const uint64_t end = f.pos + len[k];
+                    if (end > f.size) {  // grow the file -- never shrink it: another worker may have extended it meanwhile
+                        struct stat sb;
+                        if (fstat(f.fd, &sb) == 0 && (uint64_t)sb.st_size > f.size) f.size = (uint64_t)sb.st_size;
+                        if (end > f.size) {
+                            if (!room_for(f.fd, end - f.size) || ftruncate(f.fd, (off_t)end) != 0) { if (!io_err) io_err = errno ? errno : ENOSPC; continue; }
+                            f.size = end;
+                        }
+                    }
+                    const uint64_t m0 = f.pos & ~(page - 1), mlen = end - m0;
+                    void *mp = mmap(nullptr, mlen, PROT_READ | PROT_WRITE, MAP_SHARED, f.fd, (off_t)m0);
+                    if (mp == MAP_FAILED) {  // e.g. a file system without shared mappings: fall back to pwrite for good
+                        f.mapped = false;
+                    } else {
+                        maps[k] = Map{(uint8_t *)mp, mlen};
+                        uint8_t *dst = (uint8_t *)mp + (f.pos - m0);
+                        for (uint64_t at = 0; at < len[k]; at += piece)
+                            pool.push(WriteTask{-1, src[k] + at, std::min(piece, len[k] - at), 0, dst + at});
+                    }
                 }
-                off[k] += len[k];
+                if (!f.mapped) {
+                    if (sink->append) {
+                        pool.push(WriteTask{fd[k], src[k], len[k], -1, nullptr});  // one task per stream: appends stay ordered
+                    } else {
+                        for (uint64_t at = 0; at < len[k]; at += piece)
+                            pool.push(WriteTask{fd[k], src[k] + at, std::min(piece, len[k] - at), (int64_t)(f.pos + at), nullptr});
+                    }
+                }
+                f.pos += len[k];
             }
             if (fd[2] >= 0 && b.vcf && b.vcf_bytes) {
-                pool.push(WriteTask{fd[2], b.vcf, b.vcf_bytes, -1});
+                pool.push(WriteTask{fd[2], b.vcf, b.vcf_bytes, -1, nullptr});
                 st.bytes_vcf += b.vcf_bytes;
             }
             const int e = pool.wait();  // the slot may be refilled once it is released
+            for (int k = 0; k < 2; ++k)
+                if (maps[k].base) munmap(maps[k].base, maps[k].bytes);
             nvtxRangePop();
             if (e && !io_err) io_err = e;
             st.write_ms += now_ms() - w0;

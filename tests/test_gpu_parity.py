@@ -157,6 +157,16 @@ def test_native_file_writer(tmp_path):
         e.write_files(items0, z1, z2, None, append=True, truncate=True, compress=True, batch_pairs=31)
         e.write_files(items1, z1, z2, None, append=True, compress=True, batch_pairs=31)
         assert gzip.decompress(open(z1, "rb").read()) == got1 and gzip.decompress(open(z2, "rb").read()) == got2
+        # not a regular file: the write(2) path; and the same through ISS_WRITER=pwrite on a regular file
+        st = e.write_files(items0, "/dev/null", "/dev/null", None)
+        assert st["bytes_r1"] == n0
+        os.environ["ISS_WRITER"] = "pwrite"
+        try:
+            p1, p2 = str(tmp_path / "p_R1.fastq"), str(tmp_path / "p_R2.fastq")
+            e.write_files(items0, p1, p2, None, truncate=True, batch_pairs=19)
+            assert open(p1, "rb").read() == exp["R1"] and open(p2, "rb").read() == exp["R2"]
+        finally:
+            del os.environ["ISS_WRITER"]
         # a path that cannot be opened: ISS_E_IO, and the engine stays usable
         from insilicoseq_b200 import _lib
 
