@@ -111,6 +111,7 @@ struct ModelHeader {
     uint32_t L, qual_mode, n_insert, frag_mode, n_frag, const_phred, n_basic, store_mutations;
     int32_t fixed_insert;
     uint32_t n_grp;        // groups of 4 indel draw sites (= one Philox block; RNG contract v2), all lists together
+    float surv_per_pair;   // expected number of sites whose draw passes, per pair (host statistic: picks the scan mode)
     uint32_t grp_begin[5]; // first group of: insertion sites fwd, deletion sites fwd, insertion sites rev, deletion sites rev; end
     uint32_t pad[3];
     int64_t frag_lo;
@@ -288,6 +289,7 @@ struct GenParams {
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)
     uint32_t err_cap;         // entries of the substitution list
     uint32_t tie_cap;         // entries of the tie queue (exact pass)
+    uint32_t surv_direct;     // 1: the model's indel tables are dense (expected survivors per tile beyond the queue): scan once, after the gather
     uint32_t amplicon;
     uint32_t gc_bias;
     uint32_t chunk_magic;     // ceil(2^32 / nchunk) for idx / nchunk (unused when nchunk == 1: the value would be 2^32)

@@ -258,6 +258,19 @@ __device__ __noinline__ void replay_indels_warp(const GenParams &p, const Lay &l
     uint8_t *orig = scratch;       // [L]  the read before indels
     uint8_t *stk = scratch + L;    // [4L] LIFO of inserted bases (lane 0 only)
     for (uint32_t i = lane; i < L; i += 32u) orig[i] = seq[i];
+    // which loop positions have a non-zero mask: one bit each, word r of the bitmap in lane r (up to 1024 positions; the loads
+    // are independent of each other, so this costs one memory latency instead of one per 32 positions scanned later)
+    const uint32_t nwords = (L + 30u) >> 5;  // positions 0 .. L - 2
+    const bool bitmap = nwords <= 32u;
+    uint32_t myword = 0;
+    if (bitmap) {
+#pragma unroll 4
+        for (uint32_t r = 0; r < nwords; ++r) {
+            const uint32_t pos = 32u * r + lane;
+            const uint32_t bal = __ballot_sync(FULL, pos + 1u < L && mask[pos] != 0u);
+            if (lane == r) myword = bal;
+        }
+    }
     __syncwarp();
     uint32_t nucl = 0, k = 0, sp = 0;  // loop position == bytes written so far; next unread original base; LIFO depth
     bool broke = false;                // the reference's loop ended on an IndexError
@@ -266,11 +279,21 @@ __device__ __noinline__ void replay_indels_warp(const GenParams &p, const Lay &l
         uint32_t e = nucl;
         if (sp == 0) {
             e = L - 1u;
-            for (uint32_t base = nucl; base + 1u < L; base += 32u) {
-                const uint32_t pos = base + lane;
-                const uint32_t m = pos + 1u < L ? mask[pos] : 0u;
-                const uint32_t bal = __ballot_sync(FULL, m != 0u);
-                if (bal) { e = base + (uint32_t)__ffs((int)bal) - 1u; break; }
+            if (bitmap) {
+                const uint32_t w0 = nucl >> 5;
+                const uint32_t cand = lane > w0 ? myword : (lane == w0 ? (myword & (0xFFFFFFFFu << (nucl & 31u))) : 0u);
+                const uint32_t bal = __ballot_sync(FULL, cand != 0u);
+                if (bal) {
+                    const uint32_t src = (uint32_t)__ffs((int)bal) - 1u;
+                    e = 32u * src + (uint32_t)__ffs((int)__shfl_sync(FULL, cand, src)) - 1u;
+                }
+            } else {
+                for (uint32_t base = nucl; base + 1u < L; base += 32u) {
+                    const uint32_t pos = base + lane;
+                    const uint32_t m = pos + 1u < L ? mask[pos] : 0u;
+                    const uint32_t bal = __ballot_sync(FULL, m != 0u);
+                    if (bal) { e = base + (uint32_t)__ffs((int)bal) - 1u; break; }
+                }
             }
             // (b) the run in front of it comes straight from the original read
             const uint32_t want = e - nucl, have = L - k, run = want < have ? want : have;
@@ -614,7 +637,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         const uint32_t seq_off = rel0 + (valid ? u32p(l.sRel)[pair] : 0);
         uint8_t *seq = imgp(l, o) + seq_off;
         const uint32_t g_begin = (q4 * p.n_grp) >> (p.split_shift + 1u), g_end = ((q4 + 1u) * p.n_grp) >> (p.split_shift + 1u);
-        if (valid && p.n_grp) {
+        if (p.surv_direct) {  // dense indel tables: the queue would overflow in every tile -- scan once, behind the barrier
+            if (tid == 0 && p.n_grp) u32p(l.sCtl)[6] = ISS_SURV_CAP + 1u;
+        } else if (valid && p.n_grp) {
             for (uint32_t g = g_begin; g < g_end; ++g) {
                 const uint32_t li = (g >= p.grp_begin[1] ? 1u : 0u) + (g >= p.grp_begin[2] ? 1u : 0u) + (g >= p.grp_begin[3] ? 1u : 0u);
                 const uint32_t so = li >> 1, kind = li & 1u;

@@ -299,6 +299,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.img_cap = c->img_cap;
     p.err_cap = c->err_cap;
     p.tie_cap = kTieCap;
+    p.surv_direct = (double)h.surv_per_pair * c->tile_pairs > ISS_SURV_CAP / 4 ? 1u : 0u;
     p.amplicon = c->opts.sequence_type == ISS_SEQ_AMPLICON;
     p.gc_bias = c->opts.gc_bias;
     p.nchunk = (L + 15u) / 16u;
@@ -638,6 +639,13 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
             }
         }
     h.grp_begin[4] = h.n_grp = (uint32_t)grps.size();
+    {
+        double e = 0.0;  // a site passes when word <= thr: probability (thr + 1) / 2^32
+        for (const Grp &g : grps)
+            for (int k = 0; k < 4; ++k)
+                if ((g.meta[k] >> 16) & 1u) e += ((double)g.thr[k] + 1.0) / 4294967296.0;
+        h.surv_per_pair = (float)e;
+    }
     uint64_t off = align_up(sizeof(ModelHeader), 16);
     auto place = [&](uint64_t bytes) { uint64_t at = off; off = align_up(off + std::max<uint64_t>(bytes, 16), 16); return at; };
     // 16-bit quality rows (layout: iss_kernels.cu).  Only populated bins get rows.

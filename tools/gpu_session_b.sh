@@ -27,6 +27,8 @@ for c in 2 3 4; do
   ( timeout 900 python bench.py --config $c --steps 3 --warmup 3 ) > $OUT/bench_cfg$c.json 2> $OUT/bench_cfg$c.err; echo "bench cfg$c rc=$?" | tee -a $OUT/summary.txt
   show $OUT/bench_cfg$c.json cfg$c
 done
+( timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"iss_gz|iss_deflate" -c 36 --csv --log-file $OUT/gzip_launches.csv python tools/gz_profile.py ) > $OUT/gz_profile.log 2>&1
+( ISS_TRACE=1 timeout 120 python tools/gz_profile.py ) > $OUT/gz_trace.log 2>&1
 ( timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline ) > $OUT/ncu_list.log 2>&1
 ( timeout 900 ncu --set full --clock-control none --import-source on -k regex:iss_generate_kernel -s 6 -c 1 -o $OUT/gen_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/gen_full.ncu-rep --page details > $OUT/ncu_details.txt 2>&1
