@@ -112,6 +112,8 @@ struct ModelHeader {
     int32_t fixed_insert;
     uint32_t n_grp;        // groups of 4 indel draw sites (= one Philox block; RNG contract v2), all lists together
     float surv_per_pair;   // expected number of sites whose draw passes, per pair (host statistic: picks the scan mode)
+    uint32_t ins_stride;   // insert-size search, first level: ins_coarse[k] = insert_thr[min((k + 1) * ins_stride, n_insert) - 1]
+    uint32_t ins_coarse[31];
     uint32_t grp_begin[5]; // first group of: insertion sites fwd, deletion sites fwd, insertion sites rev, deletion sites rev; end
     uint32_t pad[3];
     int64_t frag_lo;
@@ -289,6 +291,8 @@ struct GenParams {
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)
     uint32_t err_cap;         // entries of the substitution list
     uint32_t tie_cap;         // entries of the tie queue (exact pass)
+    uint32_t ins_stride;      // two-level insert-size search (copied from the ModelHeader)
+    uint32_t ins_coarse[31];
     uint32_t surv_direct;     // 1: the model's indel tables are dense (expected survivors per tile beyond the queue): scan once, after the gather
     uint32_t amplicon;
     uint32_t gc_bias;

@@ -89,15 +89,17 @@ __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t
     qB = (b - rowB) >> 1;
 }
 
-// queue (read, position) for the exact pass; a full queue makes the whole tile take it (ctl word 5)
-__device__ __forceinline__ void defer_position(const Lay &l, uint32_t cap, uint32_t rd, uint32_t pos) {
+// queue (read, 16-bit count, position) for the exact pass; a full queue makes the whole tile take it
+__device__ __forceinline__ void defer_position(const Lay &l, uint32_t cap, uint32_t rd, uint32_t pos, uint32_t c16) {
     const uint32_t slot = atomicAdd(&u32p(l.sCtl)[4], 1u);
-    if (slot < cap) u32p(l.sTie)[slot] = (rd << 16) | pos;
+    if (slot < cap) u32p(l.sTie)[slot] = (rd << 24) | (c16 << 16) | pos;
 }
 
 // The definition the fast paths must agree with: phred of (read rd, position pos) for the quality draw wq, from the
 // model's full-precision tables (kde.py:82-85 on the 64 sorted 32-bit thresholds; basic.py:41-53; perfect.py:35-42).
-__device__ __noinline__ uint32_t quality_exact(const GenParams &p, uint32_t rd, uint32_t pos, uint32_t wq) {
+// c16: thresholds known to be below the draw (0: none known) -- the 16-bit search has already counted the entries whose top
+// half is smaller, so only the few that share the draw's top half are compared in full
+__device__ __noinline__ uint32_t quality_exact(const GenParams &p, uint32_t rd, uint32_t pos, uint32_t wq, uint32_t c16) {
     if (p.qual_mode == ISS_QUAL_CONST_MODE) return p.const_phred;
     if (p.qual_mode == ISS_QUAL_TABLE_MODE) {
         uint32_t a = 0, e = p.n_basic;
@@ -107,7 +109,11 @@ __device__ __noinline__ uint32_t quality_exact(const GenParams &p, uint32_t rd, 
     const uint32_t o = rd >= p.tile_pairs ? 1u : 0u;
     const uint32_t bin = u32p(p.lay.sQrow)[rd] >> 16;
     const uint32_t *__restrict__ row = p.m.qual_exact + (((size_t)(o * 4u + bin) * p.L + pos) << 6);
-    uint32_t c = 0;
+    uint32_t c = c16;
+    if (c16) {
+        while (c < ISS_QROW && wq > __ldg(row + c)) ++c;  // the row is sorted: stop at the first threshold not below the draw
+        return c;
+    }
 #pragma unroll 1
     for (uint32_t s = 32; s >= 1; s >>= 1)
         if (wq > __ldg(row + c + s - 1u)) c += s;  // row[63] == 0xFFFFFFFF: c <= 63
@@ -470,7 +476,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             } else if (p.n_insert == 0) {
                 insert = p.fixed_insert;
             } else {  // np.searchsorted(i_size_cdf, u): the CDF index is the insert size (kde.py:97)
-                uint32_t a = 0, b = p.n_insert;
+                uint32_t c = 0;  // coarse[k] = last threshold of the k-th run of ins_stride entries (constant bank)
+#pragma unroll
+                for (uint32_t s = 16; s >= 1; s >>= 1)
+                    if (c + s <= 31u && b0.x > p.ins_coarse[c + s - 1u]) c += s;
+                uint32_t a = c * p.ins_stride, b = a + p.ins_stride < p.n_insert ? a + p.ins_stride : p.n_insert;
                 while (a < b) { const uint32_t mid = (a + b) >> 1; if (b0.x > __ldg(p.m.insert_thr + mid)) a = mid + 1; else b = mid; }
                 insert = (int64_t)a;
             }
@@ -679,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         uint32_t q0, q1;  // the row behind an odd L is all pad: q1 = 0 there, and not used
                         q16_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
                         if (tie0) {
-                            defer_position(l, p.tie_cap, rd, pos);
+                            defer_position(l, p.tie_cap, rd, pos, q0);
                         } else {
                             qual[pos] = (uint8_t)(q0 + 33u);
                             if (w.y > u32p(l.sErrThr)[q0]) {
@@ -689,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         }
                         if (pos + 1u < L) {
                             if (tie1) {
-                                defer_position(l, p.tie_cap, rd, pos + 1u);
+                                defer_position(l, p.tie_cap, rd, pos + 1u, q1);
                             } else {
                                 qual[pos + 1u] = (uint8_t)(q1 + 33u);
                                 if (w.w > u32p(l.sErrThr)[q1]) {
@@ -848,12 +858,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         if (ntie && !redo_all) {
             for (uint32_t e = tid; e < ntie; e += blockDim.x) {
                 const uint32_t v = u32p(l.sTie)[e];
-                const uint32_t trd = v >> 16, pos = v & 0xFFFFu;
+                const uint32_t trd = v >> 24, pos = v & 0xFFFFu;
                 const uint32_t to = trd >= T ? 1u : 0u, tp = trd - to * T;
                 const uint64_t tP = u64p(l.sP)[tp];
                 const Philox4 w = philox4x32_10_rk(pos >> 1, iss_read_stream(to, ISS_K_QUAL) | (u32p(l.sAtt)[tp] << 8), (uint32_t)tP,
                                                    (uint32_t)(tP >> 32), p.rk);
-                const uint32_t q = quality_exact(p, trd, pos, (pos & 1u) ? w.z : w.x);
+                const uint32_t q = quality_exact(p, trd, pos, (pos & 1u) ? w.z : w.x, (v >> 16) & 0xFFu);
                 (imgp(l, to) + (uint32_t)(rel0 + u32p(l.sRel)[tp]) + L + 3u)[pos] = (uint8_t)(q + 33u);
                 if (((pos & 1u) ? w.w : w.y) > u32p(l.sErrThr)[q]) {  // a handful per tile: applied in place, no second list
                     apply_substitution(p, l, gp0, rel0, trd, pos);
@@ -881,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 for (uint32_t h = 0; h < 2; ++h) {
                     const uint32_t pos = 2u * b + h;
                     if (pos >= L) break;
-                    const uint32_t q = quality_exact(p, rd, pos, h ? w.z : w.x);
+                    const uint32_t q = quality_exact(p, rd, pos, h ? w.z : w.x, 0u);
                     qual[pos] = (uint8_t)(q + 33u);
                     if ((h ? w.w : w.y) > u32p(l.sErrThr)[q]) { apply_substitution(p, l, gp0, rel0, rd, pos); ++napplied; }
                 }

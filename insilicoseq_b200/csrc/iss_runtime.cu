@@ -299,6 +299,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.img_cap = c->img_cap;
     p.err_cap = c->err_cap;
     p.tie_cap = kTieCap;
+    p.ins_stride = h.ins_stride;
+    memcpy(p.ins_coarse, h.ins_coarse, sizeof p.ins_coarse);
     p.surv_direct = (double)h.surv_per_pair * c->tile_pairs > ISS_SURV_CAP / 4 ? 1u : 0u;
     p.amplicon = c->opts.sequence_type == ISS_SEQ_AMPLICON;
     p.gc_bias = c->opts.gc_bias;
@@ -638,6 +640,11 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
                 }
             }
         }
+    h.ins_stride = std::max<uint32_t>(1u, (m->n_insert + 31u) / 32u);
+    for (uint32_t k = 0; k < 31; ++k) {
+        const uint64_t last = std::min<uint64_t>((uint64_t)(k + 1) * h.ins_stride, m->n_insert);
+        h.ins_coarse[k] = (uint64_t)k * h.ins_stride < m->n_insert ? m->insert_thr[last - 1] : 0xFFFFFFFFu;
+    }
     h.grp_begin[4] = h.n_grp = (uint32_t)grps.size();
     {
         double e = 0.0;  // a site passes when word <= thr: probability (thr + 1) / 2^32
