@@ -62,7 +62,17 @@ __device__ __forceinline__ bool is_record_start(const uint8_t *__restrict__ b, u
 __device__ __forceinline__ uint32_t name_match(const uint8_t *__restrict__ b, uint32_t n, uint32_t s, uint32_t q) {
     if (s - q > 32768u) return 0u;
     uint32_t m = 0;
+    while (s + m + 4u <= n && m + 4u <= 256u) {  // four bytes of each line per step: eight independent loads
+        const uint32_t a0 = b[s + m], a1 = b[s + m + 1u], a2 = b[s + m + 2u], a3 = b[s + m + 3u];
+        const uint32_t c0 = b[q + m], c1 = b[q + m + 1u], c2 = b[q + m + 2u], c3 = b[q + m + 3u];
+        if (a0 != c0 || a0 == '\n') break;
+        if (a1 != c1 || a1 == '\n') { m += 1u; goto done; }
+        if (a2 != c2 || a2 == '\n') { m += 2u; goto done; }
+        if (a3 != c3 || a3 == '\n') { m += 3u; goto done; }
+        m += 4u;
+    }
     while (s + m < n && m < 258u && b[s + m] == b[q + m] && b[s + m] != '\n') ++m;
+done:
     return m >= 3u ? m : 0u;
 }
 constexpr uint32_t kPoly = 0xedb88320u;
@@ -381,6 +391,7 @@ struct Smem {
     int32_t last_start[kThreads];  // last record start inside each slice (-1: none)
     uint16_t tok_off[kThreads + 1];  // matches that start before each slice
     uint8_t len8[288];
+    uint8_t lcode[256];      // match length - 3 -> length code 0..28
 };
 
 extern __shared__ __align__(16) uint8_t iss_gz_smem[];
@@ -388,7 +399,7 @@ extern __shared__ __align__(16) uint8_t iss_gz_smem[];
 namespace {
 // bits of one match: length code + extra, distance code + extra
 __device__ __forceinline__ uint32_t match_bits(const Smem &s, uint32_t len, uint32_t dist) {
-    const uint32_t lc = len_code(len), dc = dist_code(dist);
+    const uint32_t lc = s.lcode[len - 3u], dc = dist_code(dist);
     return (s.cl[257u + lc] >> 16) + kLenExtra[lc] + (s.dl[dc] >> 16) + kDistExtra[dc];
 }
 __device__ __forceinline__ void flush_acc(Smem &s, uint64_t &acc, uint32_t &accbits, uint32_t &wi) {
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         s.len8[i] = (uint8_t)(e >> 16);
     }
     if (tid < 32) s.dl[tid] = code->dl[tid];
+    if (tid < 256) s.lcode[tid] = (uint8_t)len_code(tid + 3u);
     for (;;) {
         __syncthreads();  // previous chunk fully written out; tables loaded
         if (tid == 0) s.misc[0] = atomicAdd(&work[kWorkTicket], 1u);
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);  // chunk base and slices are 16-byte aligned
         uint32_t bits = 0, crc = 0;
         int32_t st0 = -1, st1 = -1;  // the last two record starts of the slice (st0 < st1)
+        uint32_t prev_word = lo ? (uint32_t)src[lo - 1u] << 24 : 0u;  // its top byte: the byte in front of the current word
         for (uint32_t i = lo; i < hi; i += 16u) {
             const uint4 v = __ldg(src4 + ((i - lo) >> 4));
             const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
@@ -446,13 +459,17 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                         crc = s.crcT[0][(crc ^ b) & 0xFFu] ^ (crc >> 8);
                     }
                 }
-                const uint32_t z = wd ^ 0x40404040u;  // any '@' in this word?
-                if ((z - 0x01010101u) & ~z & 0x80808080u) {
+                // '@' right behind '\n'?  bytes of `before` = the byte in front of each byte of wd
+                const uint32_t before = (wd << 8) | (prev_word >> 24);
+                const uint32_t za = wd ^ 0x40404040u, zn = before ^ 0x0A0A0A0Au;
+                const uint32_t hit = ((za - 0x01010101u) & ~za & 0x80808080u) & ((zn - 0x01010101u) & ~zn & 0x80808080u);
+                if (hit) {  // a line that starts with '@' (a candidate only: the borrow of the zero-byte test can leak upwards)
                     for (uint32_t j = 0; j < 4u; ++j) {
                         const uint32_t x = i + 4u * k + j;
-                        if (x < hi && ((wd >> (8u * j)) & 0xFFu) == '@' && is_record_start(src, x)) { st0 = st1; st1 = (int32_t)x; }
+                        if (((hit >> (8u * j + 7u)) & 1u) && x < hi && is_record_start(src, x)) { st0 = st1; st1 = (int32_t)x; }
                     }
                 }
+                prev_word = wd;
             }
         }
         s.last_start[tid] = st1;
@@ -540,24 +557,53 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             for (uint32_t i = lo; i < hi; i += 16u) {
                 const uint4 v = __ldg(src4 + ((i - lo) >> 4));
                 const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-                if (skip_to <= i && next_tok >= i + 16u) {  // 16 plain literals
+                // One code path for every lane of the warp (the lanes that meet a match in this group must not drag the
+                // others through a per-byte loop): `lit` = the bytes of the group that go out as literals, `tk` = where a
+                // match token starts (16: nowhere).  A second match in the same 16 bytes (records of a few bytes) is rare
+                // enough for the byte loop below.
+                uint32_t lit = hi - i >= 16u ? 0xFFFFu : ((1u << (hi - i)) - 1u);
+                if (skip_to > i) lit &= skip_to - i >= 16u ? 0u : ~((1u << (skip_to - i)) - 1u);
+                uint32_t tk = 16u, tlen = 0, tdist = 0;
+                bool again = false;
+                if (next_tok < i + 16u && next_tok < hi) {
+                    tk = next_tok - i;
+                    const uint32_t ld = s.tok_ld[t];
+                    tlen = ld & 0xFFFFu;
+                    tdist = (ld >> 16) ? (ld >> 16) : 32768u;
+                    const uint32_t tend = tk + tlen;  // first byte of the group behind the match (may be >= 16)
+                    lit &= ~((tend >= 16u ? 0xFFFFu : ((1u << tend) - 1u)) & ~((1u << tk) - 1u));
+                    skip_to = next_tok + tlen;
+                    ++t;
+                    next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
+                    if (next_tok < i + 16u) { again = true; lit &= (1u << (tend < 16u ? tend : 16u)) - 1u; }  // literals behind the first match: byte loop
+                }
 #pragma unroll
-                    for (uint32_t k = 0; k < 16; ++k) {
-                        if (i + k < hi) {
-                            const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
-                            acc |= (uint64_t)(e & 0xFFFFu) << accbits;
-                            accbits += e >> 16;
-                            flush_acc(s, acc, accbits, wi);
-                        }
+                for (uint32_t k = 0; k < 16; ++k) {
+                    if (k == tk) {
+                        const uint32_t lc = s.lcode[tlen - 3u], dc = dist_code(tdist);
+                        const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
+                        acc |= (uint64_t)((le & 0xFFFFu) | ((tlen - kLenBase[lc]) << (le >> 16))) << accbits;
+                        accbits += (le >> 16) + kLenExtra[lc];
+                        flush_acc(s, acc, accbits, wi);
+                        acc |= (uint64_t)((de & 0xFFFFu) | ((tdist - kDistBase[dc]) << (de >> 16))) << accbits;
+                        accbits += (de >> 16) + kDistExtra[dc];
+                        flush_acc(s, acc, accbits, wi);
                     }
-                } else {
+                    if ((lit >> k) & 1u) {
+                        const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
+                        acc |= (uint64_t)(e & 0xFFFFu) << accbits;
+                        accbits += e >> 16;
+                        flush_acc(s, acc, accbits, wi);
+                    }
+                }
+                if (again) {  // the rest of the group, byte by byte
 #pragma unroll 1
-                    for (uint32_t k = 0; k < 16 && i + k < hi; ++k) {
+                    for (uint32_t k = tk + tlen; k < 16 && i + k < hi; ++k) {
                         const uint32_t x = i + k;
                         if (x < skip_to) continue;
                         if (x == next_tok) {
                             const uint32_t ld = s.tok_ld[t], len = ld & 0xFFFFu, dist = (ld >> 16) ? (ld >> 16) : 32768u;
-                            const uint32_t lc = len_code(len), dc = dist_code(dist);
+                            const uint32_t lc = s.lcode[len - 3u], dc = dist_code(dist);
                             const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
                             acc |= (uint64_t)((le & 0xFFFFu) | ((len - kLenBase[lc]) << (le >> 16))) << accbits;
                             accbits += (le >> 16) + kLenExtra[lc];

@@ -291,6 +291,8 @@ struct GenParams {
     uint32_t img_cap;         // bytes of one stream image in shared memory (multiple of 16)
     uint32_t err_cap;         // entries of the substitution list
     uint32_t tie_cap;         // entries of the tie queue (exact pass)
+    uint32_t err_ovf_cap;     // entries per CTA of the substitution list's overflow in global memory
+    uint32_t *err_ovf;        // [gridDim.x][err_ovf_cap]
     uint32_t ins_stride;      // two-level insert-size search (copied from the ModelHeader)
     uint32_t ins_coarse[31];
     uint32_t surv_direct;     // 1: the model's indel tables are dense (expected survivors per tile beyond the queue): scan once, after the gather

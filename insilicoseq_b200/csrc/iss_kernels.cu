@@ -89,6 +89,12 @@ __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t
     qB = (b - rowB) >> 1;
 }
 
+// substitution list full: the entry goes to this CTA's stretch of a list in global memory (models with ~ 4 or more errors
+// per read at 64 pairs per tile); only beyond that does the tile fall back to the exact pass
+__device__ __forceinline__ void err_overflow(const GenParams &p, uint32_t slot, uint32_t v) {
+    const uint32_t k = slot - p.err_cap;
+    if (k < p.err_ovf_cap) p.err_ovf[(size_t)blockIdx.x * p.err_ovf_cap + k] = v;
+}
 // queue (read, 16-bit count, position) for the exact pass; a full queue makes the whole tile take it
 __device__ __forceinline__ void defer_position(const Lay &l, uint32_t cap, uint32_t rd, uint32_t pos, uint32_t c16) {
     const uint32_t slot = atomicAdd(&u32p(l.sCtl)[4], 1u);
@@ -393,38 +399,36 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
     //      fixed cyclic sequence: block b -> the rows of positions 2b, 2b + 1 for the populated bins of orientation o,
     //      contiguous in the model blob.  Two shared-memory stages per stream: blocks b_begin, b_begin + 2, ... go through
     //      stage 0 and b_begin + 1, b_begin + 3, ... through stage 1, for every tile alike (with an odd block count the
-    //      last turn of stage 1 is simply skipped), so the loop is unrolled by two with static stage addresses.  A stage is
-    //      refilled the instant it is free: every warp of the stream counts itself out of the stage (shared-memory
-    //      atomic), and the warp that counts last issues the cp.async.bulk of the block that uses the stage next -- no
-    //      producer role, nobody waits to issue.  `full` mbarriers carry the byte counts; bit s of `qpar` = consumptions of
-    //      stage s so far, mod 2.
+    //      last turn of stage 1 is simply skipped), so the loop is unrolled by two with static stage addresses.  The
+    //      stream's first lane issues one cp.async.bulk per block, one block ahead of the consumers; `full` mbarriers carry
+    //      the byte counts, `empty` ones (one arrival per warp of the stream) hand a stage back.  Phase parities: bit s of
+    //      `qpar` = consumptions of stage s so far, mod 2; the producer's wait on `empty[s]` before its (c + 1)-th fill of
+    //      stage s uses parity (c + 1) & 1, which passes at once on the fresh barrier (c = 0).
     const bool kde = p.qual_mode == ISS_QUAL_KDE_MODE;
     const uint32_t nblk = (L + 1u) >> 1;
     const uint32_t b_begin = (half * nblk) >> p.split_shift, b_end = ((half + 1u) * nblk) >> p.split_shift;
-    const uint32_t bar0 = smem0 + l.sBar + (q4 << 5);            // full[0] +0, count[0] +8, full[1] +16, count[1] +24
+    const uint32_t bar0 = smem0 + l.sBar + (q4 << 5);            // full[0] +0, empty[0] +8, full[1] +16, empty[1] +24
     const uint32_t stage0 = l.sQst + q4 * (2u * p.q_stage_cap);  // offset of the stream's two stages from iss_smem
     uint32_t qpar = 0;
-    // stage `stg` <- the rows of block `blk` (one lane)
-    auto q_fill = [&](uint32_t stg, uint32_t blk) {
-        const uint32_t fb = bar0 + (stg << 4), bytes = p.q_stage_bytes[o];
-        mbar_arrive_expect_tx(fb, bytes);
-        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * bytes, bytes, fb);
-    };
     if (kde) {
         if (tid == 0) {
-            const uint32_t nstream = 2u << p.split_shift;
-            for (uint32_t k = 0; k < 2u * nstream; ++k) {
+            const uint32_t nbar = (2u << p.split_shift) * 2u;
+            for (uint32_t k = 0; k < nbar; ++k) {
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + l.sBar + 16u * k), "r"(1u) : "memory");
-                u32p(l.sBar + 16u * k + 8u)[0] = 0;  // warps that have left the stage
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + l.sBar + 16u * k + 8u), "r"(T >> 5) : "memory");
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (pair == 0 && blockIdx.x < ntiles) {  // both stages start full
-            if (b_begin < b_end) q_fill(0u, b_begin);
-            if (b_begin + 1u < b_end) q_fill(1u, b_begin + 1u);
-        }
     }
+    // producer lane only: stage `stg` <- the rows of block `blk`, after every warp of the stream released the stage
+    auto q_fill = [&](uint32_t stg, uint32_t blk, uint32_t done /* consumptions of the stage so far */) {
+        const uint32_t fb = bar0 + (stg << 4), bytes = p.q_stage_bytes[o];
+        mbar_wait(fb + 8u, (done + 1u) & 1u);
+        mbar_arrive_expect_tx(fb, bytes);
+        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * bytes, bytes, fb);
+    };
+    if (kde && pair == 0 && blockIdx.x < ntiles && b_begin < b_end) q_fill(0u, b_begin, 0u);
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t gp0 = (uint64_t)tile * T;
@@ -675,8 +679,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
             if (kde) {
                 const uint32_t row0 = smem0 + stage0 + (valid ? (u32p(l.sQrow)[rd] & 0xFFFFu) : 0u);  // shared-window address of the read's row in stage 0, first position
+                const bool producer = pair == 0;
                 const bool more_tiles = tile + gridDim.x < ntiles;
-                const uint32_t nwarp_stream = T >> 5;
                 // one block: wait for its rows, draw + search two positions, hand the stage back
                 auto q_block = [&](uint32_t b, uint32_t stg) {
                     mbar_wait(bar0 + (stg << 4), (qpar >> stg) & 1u);
@@ -694,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                             qual[pos] = (uint8_t)(q0 + 33u);
                             if (w.y > u32p(l.sErrThr)[q0]) {
                                 const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos;  // a full list switches phase 5 to the exact pass
+                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else err_overflow(p, slot, (rd << 16) | pos);
                             }
                         }
                         if (pos + 1u < L) {
@@ -704,31 +708,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                                 qual[pos + 1u] = (uint8_t)(q1 + 33u);
                                 if (w.w > u32p(l.sErrThr)[q1]) {
                                     const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                                    if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u);
+                                    if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else err_overflow(p, slot, (rd << 16) | (pos + 1u));
                                 }
                             }
                         }
                     }
                     __syncwarp();
-                    if ((tid & 31u) == 0) {  // this warp is done with the stage; the last one out refills it
-                        uint32_t left;
-                        asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(left) : "r"(bar0 + (stg << 4) + 8u) : "memory");
-                        if (left + 1u == nwarp_stream) {
-                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(bar0 + (stg << 4) + 8u), "r"(0u) : "memory");
-                            // the block that uses this stage next: two blocks on, or the same turn of the next tile
-                            uint32_t nb = b + 2u;
-                            bool any = true;
-                            if (nb >= b_end) { nb = b_begin + stg; any = more_tiles && nb < b_end; }
-                            if (any) {
-                                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our reads of the stage before the copy engine's writes
-                                q_fill(stg, nb);
-                            }
-                        }
-                    }
+                    if ((tid & 31u) == 0) mbar_arrive(bar0 + (stg << 4) + 8u);  // this warp is done with the stage
                 };
                 for (uint32_t b = b_begin; b < b_end; b += 2u) {
+                    const bool second = b + 1u < b_end;
+                    if (producer && second) q_fill(1u, b + 1u, (qpar >> 1) & 1u);
                     q_block(b, 0u);
-                    if (b + 1u < b_end) q_block(b + 1u, 1u);
+                    if (producer) {  // stage 0 for the next turn: the next pair of blocks, or the first block of the next tile
+                        if (b + 2u < b_end) q_fill(0u, b + 2u, qpar & 1u);
+                        else if (more_tiles) q_fill(0u, b_begin, qpar & 1u);
+                    }
+                    if (second) q_block(b + 1u, 1u);
                 }
             } else if (valid) {
                 for (uint32_t b = b_begin; b < b_end; ++b) {
@@ -748,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         qual[pos] = (uint8_t)(q + 33u);
                         if (wt > u32p(l.sErrThr)[q]) {
                             const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos;
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else err_overflow(p, slot, (rd << 16) | pos);
                         }
                     }
                 }
@@ -854,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         //      thread walks its positions again on the exact tables and applies its substitutions directly.
         const uint32_t ntie = u32p(l.sCtl)[4];
         const uint32_t nerr_fast = u32p(l.sCtl)[0];
-        const bool redo_all = ntie > p.tie_cap || nerr_fast > p.err_cap;  // block-uniform
+        const bool redo_all = ntie > p.tie_cap || nerr_fast > p.err_cap + p.err_ovf_cap;  // block-uniform
         if (ntie && !redo_all) {
             for (uint32_t e = tid; e < ntie; e += blockDim.x) {
                 const uint32_t v = u32p(l.sTie)[e];
@@ -875,8 +871,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         // ---- phase 5: substitutions, compacted over the whole tile (error_models/__init__.py:95-109)
         if (!redo_all) {
             const uint32_t nerr = nerr_fast;
+            const uint32_t *ovf = p.err_ovf + (size_t)blockIdx.x * p.err_ovf_cap - p.err_cap;  // entries err_cap .. nerr - 1
             for (uint32_t e = tid; e < nerr; e += blockDim.x) {
-                const uint32_t v = u32p(l.sErr)[e];
+                const uint32_t v = e < p.err_cap ? u32p(l.sErr)[e] : ovf[e];
                 apply_substitution(p, l, gp0, rel0, v >> 16, v & 0xFFFFu);
             }
             if (tid == 0 && nerr) atomicAdd(p.counters + 1, (unsigned long long)nerr);

@@ -55,6 +55,7 @@ int fail(int code, const std::string &msg) {
 constexpr uint64_t kGenomeMagic = 0x31474e4547535349ull;  // "ISSGENG1"
 constexpr uint64_t kModelMagic = 0x314c444f4d535349ull;   // "ISSMODL1"
 constexpr size_t kMaxSmem = 232448;                        // 227 KB opt-in per CTA on sm_100
+constexpr uint32_t kErrOvfCap = 4096;                      // overflow of the substitution list per CTA, in global memory (16 KB)
 constexpr uint32_t kTieCap = 64;                           // exact-pass queue per tile (~ 11 ties expected per 64-pair tile at L = 150)
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -86,7 +87,7 @@ struct Slot {
     uint32_t gz_chunks = 0;
     uint64_t nbytes2 = 0;
     uint8_t *d_scratch = nullptr;  // slow-path scratch of the kernel running in this slot (kernels of different slots overlap)
-    uint64_t scratch_bytes = 0;
+    uint64_t scratch_bytes = 0;    // (the substitution list's overflow stretches sit behind the replay scratch)
     std::vector<uint4> h_events;
     std::string vcf;
 };
@@ -121,6 +122,7 @@ struct iss_ctx {
     uint32_t n_slots = 0, max_segs = 0;
     uint32_t tile_pairs = 64, img_cap = 0, err_cap = 512, grid = 0, split_shift = 1;
     uint32_t q_stage_cap = 0;  // quality-row pipeline: bytes per stage
+    uint64_t scratch_replay_bytes = 0;  // replay part of a slot's scratch; the substitution overflow lists follow
     Lay lay{};
     size_t smem = 0;
     std::vector<Slot> slots;
@@ -299,6 +301,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.img_cap = c->img_cap;
     p.err_cap = c->err_cap;
     p.tie_cap = kTieCap;
+    p.err_ovf_cap = kErrOvfCap;
+    p.err_ovf = reinterpret_cast<uint32_t *>(s.d_scratch + c->scratch_replay_bytes);
     p.ins_stride = h.ins_stride;
     memcpy(p.ins_coarse, h.ins_coarse, sizeof p.ins_coarse);
     p.surv_direct = (double)h.surv_per_pair * c->tile_pairs > ISS_SURV_CAP / 4 ? 1u : 0u;
@@ -902,6 +906,16 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             if (bps4 >= bps) { split_shift = 2; bps = bps4; lay = lay4; smem = lay4.total; }
         }
     }
+    // the substitution list takes whatever shared memory the occupancy leaves (long-read tiles run 2 CTAs/SM with room to
+    // spare; a model with ~ 5 errors per read fills 512 entries): largest power of two that keeps the CTAs per SM
+    for (uint32_t cap = 8192; cap > c->err_cap; cap >>= 1) {
+        const uint32_t keep = c->err_cap;
+        c->err_cap = cap;
+        const Lay big = layout(T, split_shift);
+        int b2 = 0;
+        if (big.total <= kMaxSmem && iss_occupancy(T, split_shift, big.total, &b2) == cudaSuccess && b2 >= bps) { lay = big; smem = big.total; break; }
+        c->err_cap = keep;
+    }
     c->split_shift = split_shift;
     c->lay = lay;
     c->q_stage_cap = q_cap;
@@ -961,7 +975,8 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         c->max_segs = max_segs;
     }
     for (auto &s : c->slots) s.state = 0;
-    const uint64_t scratch = (uint64_t)grid * ISS_SLOW_SLOTS * (align_up(5ull * L + 8, 16) + align_up(L, 16));
+    c->scratch_replay_bytes = align_up((uint64_t)grid * ISS_SLOW_SLOTS * (align_up(5ull * L + 8, 16) + align_up(L, 16)), 256);
+    const uint64_t scratch = c->scratch_replay_bytes + (uint64_t)grid * kErrOvfCap * sizeof(uint32_t);
     for (auto &s : c->slots) {
         if (scratch > s.scratch_bytes) {
             if (s.d_scratch) cudaFree(s.d_scratch);
