@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);  // chunk base and slices are 16-byte aligned
         uint32_t bits = 0, crc = 0;
         int32_t st0 = -1, st1 = -1;  // the last two record starts of the slice (st0 < st1)
-        uint32_t prev_word = lo ? (uint32_t)src[lo - 1u] << 24 : 0u;  // its top byte: the byte in front of the current word
+        uint32_t prev_word = (lo && lo < hi) ? (uint32_t)src[lo - 1u] << 24 : 0u;  // its top byte: the byte in front of the current word (slices behind the end of the chunk read nothing)
         for (uint32_t i = lo; i < hi; i += 16u) {
             const uint4 v = __ldg(src4 + ((i - lo) >> 4));
             const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
