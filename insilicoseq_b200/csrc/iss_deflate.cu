@@ -459,14 +459,15 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                         crc = s.crcT[0][(crc ^ b) & 0xFFu] ^ (crc >> 8);
                     }
                 }
-                // '@' right behind '\n'?  bytes of `before` = the byte in front of each byte of wd
-                const uint32_t before = (wd << 8) | (prev_word >> 24);
-                const uint32_t za = wd ^ 0x40404040u, zn = before ^ 0x0A0A0A0Au;
-                const uint32_t hit = ((za - 0x01010101u) & ~za & 0x80808080u) & ((zn - 0x01010101u) & ~zn & 0x80808080u);
-                if (hit) {  // a line that starts with '@' (a candidate only: the borrow of the zero-byte test can leak upwards)
+                // line starts: bytes of `before` = the byte in front of each byte of wd; a zero-byte test finds the '\n' among
+                // them (4 per record).  Only there is the byte itself looked at ('@'?) and, rarer still, the line before it.
+                const uint32_t before = __funnelshift_l(prev_word, wd, 8);
+                const uint32_t zn = before ^ 0x0A0A0A0Au;
+                const uint32_t hit = (zn - 0x01010101u) & ~zn & 0x80808080u;  // candidates: the borrow can leak into higher bytes
+                if (hit) {
                     for (uint32_t j = 0; j < 4u; ++j) {
                         const uint32_t x = i + 4u * k + j;
-                        if (((hit >> (8u * j + 7u)) & 1u) && x < hi && is_record_start(src, x)) { st0 = st1; st1 = (int32_t)x; }
+                        if (((hit >> (8u * j + 7u)) & 1u) && ((wd >> (8u * j)) & 0xFFu) == '@' && x < hi && is_record_start(src, x)) { st0 = st1; st1 = (int32_t)x; }
                     }
                 }
                 prev_word = wd;

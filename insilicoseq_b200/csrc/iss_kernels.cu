@@ -91,7 +91,7 @@ __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t
 
 // substitution list full: the entry goes to this CTA's stretch of a list in global memory (models with ~ 4 or more errors
 // per read at 64 pairs per tile); only beyond that does the tile fall back to the exact pass
-__device__ __forceinline__ void err_overflow(const GenParams &p, uint32_t slot, uint32_t v) {
+__device__ __noinline__ void err_overflow(const GenParams &p, uint32_t slot, uint32_t v) {
     const uint32_t k = slot - p.err_cap;
     if (k < p.err_ovf_cap) p.err_ovf[(size_t)blockIdx.x * p.err_ovf_cap + k] = v;
 }
