@@ -73,8 +73,10 @@ __device__ __forceinline__ uint32_t name_match(const uint8_t *__restrict__ b, ui
     }
     while (s + m < n && m < 258u && b[s + m] == b[q + m] && b[s + m] != '\n') ++m;
 done:
-    return m >= 3u ? m : 0u;
+    return m >= 4u ? m : 0u;  // 4, not DEFLATE's 3: a match then always reaches the end of the 32-bit word it starts in (see the packing loop)
 }
+// 0x80 in every byte of x that is zero (exact for any x: no borrow between bytes)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
 constexpr uint32_t kPoly = 0xedb88320u;
 
 __device__ __forceinline__ uint32_t multmodp(uint32_t a, uint32_t b) {  // a * b mod P over GF(2), reflected (zlib)
@@ -441,7 +443,8 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);  // chunk base and slices are 16-byte aligned
         uint32_t bits = 0, crc = 0;
         int32_t st0 = -1, st1 = -1;  // the last two record starts of the slice (st0 < st1)
-        uint32_t prev_word = (lo && lo < hi) ? (uint32_t)src[lo - 1u] << 24 : 0u;  // its top byte: the byte in front of the current word (slices behind the end of the chunk read nothing)
+        // the four bytes in front of the slice (slices behind the end of the chunk read nothing; the chunk's first slice has none)
+        uint32_t prev_word = (lo && lo < hi) ? __ldg(reinterpret_cast<const uint32_t *>(src + lo - 4u)) : 0u;
         for (uint32_t i = lo; i < hi; i += 16u) {
             const uint4 v = __ldg(src4 + ((i - lo) >> 4));
             const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
@@ -459,16 +462,14 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                         crc = s.crcT[0][(crc ^ b) & 0xFFu] ^ (crc >> 8);
                     }
                 }
-                // line starts: bytes of `before` = the byte in front of each byte of wd; a zero-byte test finds the '\n' among
-                // them (4 per record).  Only there is the byte itself looked at ('@'?) and, rarer still, the line before it.
-                const uint32_t before = __funnelshift_l(prev_word, wd, 8);
-                const uint32_t zn = before ^ 0x0A0A0A0Au;
-                const uint32_t hit = (zn - 0x01010101u) & ~zn & 0x80808080u;  // candidates: the borrow can leak into higher bytes
-                if (hit) {
-                    for (uint32_t j = 0; j < 4u; ++j) {
-                        const uint32_t x = i + 4u * k + j;
-                        if (((hit >> (8u * j + 7u)) & 1u) && ((wd >> (8u * j)) & 0xFFu) == '@' && x < hi && is_record_start(src, x)) { st0 = st1; st1 = (int32_t)x; }
-                    }
+                // record starts, from registers and without a branch for all but the starts themselves: byte j of b1 / b2 /
+                // b3 is the byte 1 / 2 / 3 places in front of byte j of wd; a start is '@' behind '\n' but not behind "\n+\n"
+                const uint32_t b1 = __funnelshift_l(prev_word, wd, 8), b2 = __funnelshift_l(prev_word, wd, 16), b3 = __funnelshift_l(prev_word, wd, 24);
+                uint32_t starts = zero_bytes(wd ^ 0x40404040u) & zero_bytes(b1 ^ 0x0A0A0A0Au) & ~(zero_bytes(b2 ^ 0x2B2B2B2Bu) & zero_bytes(b3 ^ 0x0A0A0A0Au));
+                while (starts) {  // once per record
+                    const uint32_t x = i + 4u * k + ((uint32_t)(__ffs((int)starts) - 1) >> 3);
+                    starts &= starts - 1u;
+                    if (x >= 3u && x < hi) { st0 = st1; st1 = (int32_t)x; }
                 }
                 prev_word = wd;
             }
@@ -578,9 +579,27 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                     next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
                     if (next_tok < i + 16u) { again = true; lit &= (1u << (tend < 16u ? tend : 16u)) - 1u; }  // literals behind the first match: byte loop
                 }
+                // Four bytes at a time: the codes of two literals are joined in 32 bits (<= 15 bits each) before they enter
+                // the 64-bit accumulator, and a byte that a match covers simply contributes a code of length 0.  A match
+                // is at least 4 bytes long, so it covers the rest of the word it starts in: its token goes out behind the
+                // word's literals -- the only divergent step, once per record.
 #pragma unroll
-                for (uint32_t k = 0; k < 16; ++k) {
-                    if (k == tk) {
+                for (uint32_t kw = 0; kw < 4; ++kw) {
+                    const uint32_t wd = wds[kw], l4 = lit >> (4u * kw);
+                    uint32_t e0 = s.cl[wd & 0xFFu], e1 = s.cl[(wd >> 8) & 0xFFu], e2 = s.cl[(wd >> 16) & 0xFFu], e3 = s.cl[wd >> 24];
+                    e0 = (l4 & 1u) ? e0 : 0u;
+                    e1 = (l4 & 2u) ? e1 : 0u;
+                    e2 = (l4 & 4u) ? e2 : 0u;
+                    e3 = (l4 & 8u) ? e3 : 0u;
+                    const uint32_t n0 = e0 >> 16, n2 = e2 >> 16;
+                    const uint32_t cA = (e0 & 0xFFFFu) | ((e1 & 0xFFFFu) << n0), cB = (e2 & 0xFFFFu) | ((e3 & 0xFFFFu) << n2);
+                    acc |= (uint64_t)cA << accbits;
+                    accbits += n0 + (e1 >> 16);
+                    flush_acc(s, acc, accbits, wi);
+                    acc |= (uint64_t)cB << accbits;
+                    accbits += n2 + (e3 >> 16);
+                    flush_acc(s, acc, accbits, wi);
+                    if ((tk >> 2) == kw) {
                         const uint32_t lc = s.lcode[tlen - 3u], dc = dist_code(tdist);
                         const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
                         acc |= (uint64_t)((le & 0xFFFFu) | ((tlen - kLenBase[lc]) << (le >> 16))) << accbits;
@@ -588,12 +607,6 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                         flush_acc(s, acc, accbits, wi);
                         acc |= (uint64_t)((de & 0xFFFFu) | ((tdist - kDistBase[dc]) << (de >> 16))) << accbits;
                         accbits += (de >> 16) + kDistExtra[dc];
-                        flush_acc(s, acc, accbits, wi);
-                    }
-                    if ((lit >> k) & 1u) {
-                        const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
-                        acc |= (uint64_t)(e & 0xFFFFu) << accbits;
-                        accbits += e >> 16;
                         flush_acc(s, acc, accbits, wi);
                     }
                 }

@@ -484,8 +484,31 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
 #pragma unroll
                 for (uint32_t s = 16; s >= 1; s >>= 1)
                     if (c + s <= 31u && b0.x > p.ins_coarse[c + s - 1u]) c += s;
-                uint32_t a = c * p.ins_stride, b = a + p.ins_stride < p.n_insert ? a + p.ins_stride : p.n_insert;
-                while (a < b) { const uint32_t mid = (a + b) >> 1; if (b0.x > __ldg(p.m.insert_thr + mid)) a = mid + 1; else b = mid; }
+                // inside the run: 9-way steps with 8 independent probes each (two load latencies for runs of <= 80 entries,
+                // where a binary search has six or seven -- this thread's chain of loads is what the tile's other warps wait for)
+                uint32_t a = c * p.ins_stride, n = a + p.ins_stride < p.n_insert ? p.ins_stride : p.n_insert - a;
+                while (n > 8u) {
+                    const uint32_t q = (n + 8u) / 9u;
+                    uint32_t j = 0;
+#pragma unroll
+                    for (uint32_t k = 1; k <= 8u; ++k) {
+                        const uint32_t at = k * q - 1u;
+                        const uint32_t thr = at < n ? __ldg(p.m.insert_thr + a + at) : 0xFFFFFFFFu;
+                        j += b0.x > thr ? 1u : 0u;
+                    }
+                    a += j * q;                      // thr[a - 1] < x, and x <= thr[a + q - 1] if that entry was probed
+                    const uint32_t left = n - j * q, cap = j < 8u ? q - 1u : q;  // behind the last probe nothing bounds the rest
+                    n = left < cap ? left : cap;
+                }
+                {
+                    uint32_t j = 0;
+#pragma unroll
+                    for (uint32_t k = 0; k < 8u; ++k) {
+                        const uint32_t thr = k < n ? __ldg(p.m.insert_thr + a + k) : 0xFFFFFFFFu;
+                        j += b0.x > thr ? 1u : 0u;
+                    }
+                    a += j;
+                }
                 insert = (int64_t)a;
             }
             const int64_t frag = insert + 2 * (int64_t)L;
@@ -654,19 +677,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         if (p.surv_direct) {  // dense indel tables: the queue would overflow in every tile -- scan once, behind the barrier
             if (tid == 0 && p.n_grp) u32p(l.sCtl)[6] = ISS_SURV_CAP + 1u;
         } else if (valid && p.n_grp) {
-            for (uint32_t g = g_begin; g < g_end; ++g) {
-                const uint32_t li = (g >= p.grp_begin[1] ? 1u : 0u) + (g >= p.grp_begin[2] ? 1u : 0u) + (g >= p.grp_begin[3] ? 1u : 0u);
-                const uint32_t so = li >> 1, kind = li & 1u;
-                const uint4 t = __ldg(p.m.ent + 2u * g), mt = __ldg(p.m.ent + 2u * g + 1u);
-                const Philox4 w = philox4x32_10_rk(g - p.grp_begin[li], iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8, Plo, Phi, p.rk);
-                if ((w.x <= t.x) | (w.y <= t.y) | (w.z <= t.z) | (w.w <= t.w)) {  // rare: some site may fire
+            // one loop per list (insertion fwd, deletion fwd, insertion rev, deletion rev): the stream id and the rank of a
+            // group inside its list are loop invariants, and a group's meta words are fetched only for a survivor
 #pragma unroll 1
-                    for (uint32_t r = 0; r < 4; ++r) {
-                        const uint32_t meta = pick(mt, r);
-                        const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
-                        if (!bits) continue;
-                        const uint32_t slot = atomicAdd(&u32p(l.sCtl)[6], 1u);
-                        if (slot < ISS_SURV_CAP) u32p(l.sSurv)[slot] = ((so * T + pair) << 24) | (bits << 16) | (meta & 0xFFFFu);
+            for (uint32_t li = 0; li < 4u; ++li) {
+                const uint32_t lb = p.grp_begin[li], le = p.grp_begin[li + 1u];
+                const uint32_t ga = g_begin > lb ? g_begin : lb, gb = g_end < le ? g_end : le;
+                const uint32_t so = li >> 1, kind = li & 1u;
+                const uint32_t stream = iss_read_stream(so, kind ? ISS_K_DEL : ISS_K_INS) | att8;
+                for (uint32_t g = ga; g < gb; ++g) {
+                    const uint4 t = __ldg(p.m.ent + 2u * g);
+                    const Philox4 w = philox4x32_10_rk(g - lb, stream, Plo, Phi, p.rk);
+                    if ((w.x <= t.x) | (w.y <= t.y) | (w.z <= t.z) | (w.w <= t.w)) {  // rare: some site may fire
+                        const uint4 mt = __ldg(p.m.ent + 2u * g + 1u);
+#pragma unroll 1
+                        for (uint32_t r = 0; r < 4; ++r) {
+                            const uint32_t meta = pick(mt, r);
+                            const uint32_t bits = site_bits(p, so, kind, pick(w, r), pick(t, r), meta);
+                            if (!bits) continue;
+                            const uint32_t slot = atomicAdd(&u32p(l.sCtl)[6], 1u);
+                            if (slot < ISS_SURV_CAP) u32p(l.sSurv)[slot] = ((so * T + pair) << 24) | (bits << 16) | (meta & 0xFFFFu);
+                        }
                     }
                 }
             }
