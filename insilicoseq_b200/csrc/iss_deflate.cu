@@ -96,6 +96,7 @@ struct GzTables {
     uint32_t crc[4][256];  // slicing-by-4 CRC-32 tables: crc[k][i] = CRC of byte i followed by k zero bytes
     uint32_t x2n[32];      // x^(2^n) mod P
     uint32_t pow_slice[kChunk / kSlice];  // x^(8 * kSlice * j) mod P
+    uint32_t init_full;    // 0xFFFFFFFF * x^(8 * kChunk) mod P
 };
 __device__ GzTables g_gz;
 
@@ -182,12 +183,14 @@ __device__ void merge_tree(TableSmem &s, uint32_t n) {
 #define kValue ((1ull << 61) - 1ull)
 #define kSpinLimit 4000000000ll
 
-__device__ uint64_t look_back(volatile unsigned long long *status, uint32_t c, uint32_t msize, uint32_t lane) {
-    if (c == 0) {
-        if (lane == 0) status[0] = kInc | msize;
-        return 0;
-    }
-    if (lane == 0) status[c] = kAgg | msize;
+// Decoupled look-back over the member sizes, in two steps so that the wait never sits in front of the packing: the size is
+// published as soon as it is known (`publish`), the exclusive offset is resolved by warp 0 when its own packing is done --
+// by then the predecessors' sizes are there.
+__device__ __forceinline__ void look_back_publish(volatile unsigned long long *status, uint32_t c, uint32_t msize) {
+    status[c] = (c == 0 ? kInc : kAgg) | msize;
+}
+__device__ uint64_t look_back_resolve(volatile unsigned long long *status, uint32_t c, uint32_t msize, uint32_t lane) {
+    if (c == 0) return 0;
     uint64_t excl = 0;
     int64_t j = (int64_t)c - 1;
     const long long t0 = clock64();
@@ -387,7 +390,8 @@ struct Smem {
     uint32_t crcT[4][256];
     uint32_t cl[288];
     uint32_t dl[32];
-    uint32_t misc[64];       // 0 ticket, 3 crc accumulator, 4 x^(8*(n % kSlice)), 5/6 member offset, 7 matches, 8.. warp sums
+    uint32_t ticket;         // the chunk being compressed
+    uint32_t misc[64];       // 3 crc accumulator, 4 x^(8*(n % kSlice)), 5/6 member offset, 7 matches, 8.. warp sums
     uint32_t tok_pos[kMaxTok];   // the member's matches in stream order: start inside the chunk,
     uint32_t tok_ld[kMaxTok];    //   length | distance << 16 (distance 32768 stored as 0)
     int32_t last_start[kThreads];  // last record start inside each slice (-1: none)
@@ -427,17 +431,19 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
     }
     if (tid < 32) s.dl[tid] = code->dl[tid];
     if (tid < 256) s.lcode[tid] = (uint8_t)len_code(tid + 3u);
+    if (tid == 0) s.ticket = atomicAdd(&work[kWorkTicket], 1u);
     for (;;) {
-        __syncthreads();  // previous chunk fully written out; tables loaded
-        if (tid == 0) s.misc[0] = atomicAdd(&work[kWorkTicket], 1u);
-        __syncthreads();
-        const uint32_t c = s.misc[0];
+        __syncthreads();  // previous chunk fully written out; tables loaded; this chunk's ticket in place
+        const uint32_t c = s.ticket;
         if (c >= n_chunks) break;
+        // the next ticket is asked for now and put in place at the end of this chunk: the round trip of the atomic is hidden
+        uint32_t next_ticket = 0;
+        if (tid == 0) next_ticket = atomicAdd(&work[kWorkTicket], 1u);
         const uint64_t base = (uint64_t)c * kChunk;
         const uint32_t n = (uint32_t)((n_in - base < kChunk) ? (n_in - base) : kChunk);
         const uint8_t *src = in + base;
         for (uint32_t i = tid; i < kOutWords; i += kThreads) s.out[i] = i < kHdrWords ? code->hdr[i] : 0u;
-        if (tid >= 1 && tid < 64) s.misc[tid] = 0;
+        if (tid < 64) s.misc[tid] = 0;
         // 1. my slice (kSlice contiguous bytes, read 16 at a time): literal bit count + raw CRC (slicing-by-4) + record starts
         const uint32_t lo = tid * kSlice, hi = (lo + kSlice < n) ? lo + kSlice : n;
         const uint4 *src4 = reinterpret_cast<const uint4 *>(src + lo);  // chunk base and slices are 16-byte aligned
@@ -445,11 +451,11 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         int32_t st0 = -1, st1 = -1;  // the last two record starts of the slice (st0 < st1)
         // the four bytes in front of the slice (slices behind the end of the chunk read nothing; the chunk's first slice has none)
         uint32_t prev_word = (lo && lo < hi) ? __ldg(reinterpret_cast<const uint32_t *>(src + lo - 4u)) : 0u;
-        for (uint32_t i = lo; i < hi; i += 16u) {
-            const uint4 v = __ldg(src4 + ((i - lo) >> 4));
-            const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+        for (uint32_t i = lo; i < hi; i += 32u) {  // one 32-byte sector per step: both halves are asked for before either is used
+            const uint4 va = __ldg(src4 + ((i - lo) >> 4)), vb = i + 16u < hi ? __ldg(src4 + ((i - lo) >> 4) + 1) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t wds[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
+            for (uint32_t k = 0; k < 8; ++k) {
                 const uint32_t wd = wds[k];
                 if (i + 4u * k + 4u <= hi) {
                     bits += (uint32_t)s.len8[wd & 0xFFu] + s.len8[(wd >> 8) & 0xFFu] + s.len8[(wd >> 16) & 0xFFu] + s.len8[wd >> 24];
@@ -545,10 +551,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         const bool too_big = end_bits > kOutWords * 32u - 64u;
         const uint32_t n1 = n > 65535u ? 65535u : n, n2 = n - n1;  // stored blocks hold at most 65535 bytes each
         const uint32_t nbytes = too_big ? 5u + n1 + (n2 ? 5u + n2 : 0u) : (end_bits + 7u) >> 3;
-        if (warp == 0) {  // the size is known: publish it and find my place while the other warps pack
-            const uint64_t excl = look_back(status, c, 18u + nbytes, lane);
-            if (lane == 0) { s.misc[5] = (uint32_t)excl; s.misc[6] = (uint32_t)(excl >> 32); }
-        }
+        if (tid == 0) look_back_publish(status, c, 18u + nbytes);  // the size is known: the members behind this one can be placed
         // 4. pack my tokens
         if (!too_big) {
             uint64_t acc = 0;
@@ -640,6 +643,10 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             if (accbits) atomicOr(&s.out[wi], (uint32_t)acc);
             if (tid == 0) put_bits(s.out, kHeaderBits + total, eob & 0xFFFFu, eob >> 16);
         }
+        if (warp == 0) {  // my place in the output
+            const uint64_t excl = look_back_resolve(status, c, 18u + nbytes, lane);
+            if (lane == 0) { s.misc[5] = (uint32_t)excl; s.misc[6] = (uint32_t)(excl >> 32); }
+        }
         // 5. CRC-32 of the chunk: raw slice CRCs advanced over the bytes that follow them, XOR-reduced
         uint32_t part = 0;
         if (hi > lo) {
@@ -654,7 +661,10 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         // 6. the member at its final place: header, deflate bytes, CRC32, ISIZE
         const uint64_t off = (uint64_t)s.misc[5] | ((uint64_t)s.misc[6] << 32);
         if (off >= kFail) {
-            if (tid == 0 && c + 1u == n_chunks) status[n_chunks] = ~0ull;
+            if (tid == 0) {
+                if (c + 1u == n_chunks) status[n_chunks] = ~0ull;
+                s.ticket = next_ticket;
+            }
             continue;
         }
         uint8_t *dst = out + off;
@@ -684,12 +694,14 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             for (uint32_t i = tid; i < n2; i += kThreads) dst[20 + n1 + i] = src[n1 + i];
         }
         if (tid == 0) {
-            const uint32_t crc32 = s.misc[3] ^ multmodp(x2nmodp(n, 3), 0xFFFFFFFFu) ^ 0xFFFFFFFFu;
+            // CRC register start value 0xFFFFFFFF carried over the n bytes: a constant for every full chunk
+            const uint32_t crc32 = s.misc[3] ^ (n == kChunk ? g_gz.init_full : multmodp(x2nmodp(n, 3), 0xFFFFFFFFu)) ^ 0xFFFFFFFFu;
             const uint8_t hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
             for (int k = 0; k < 10; ++k) dst[k] = hdr[k];
             uint8_t *t = dst + 10 + nbytes;
             for (int k = 0; k < 4; ++k) { t[k] = (uint8_t)(crc32 >> (8 * k)); t[4 + k] = (uint8_t)(n >> (8 * k)); }
             if (c + 1u == n_chunks) status[n_chunks] = off + 18u + nbytes;  // total bytes of the stream
+            s.ticket = next_ticket;
         }
     }
 }
@@ -724,6 +736,11 @@ cudaError_t iss_gz_init_device(void) {  // once per device
     for (uint32_t j = 0; j < kSlice; ++j) xs = h_multmodp(xs, t.x2n[3]);
     t.pow_slice[0] = 1u << 31;  // x^0
     for (uint32_t j = 1; j < kChunk / kSlice; ++j) t.pow_slice[j] = h_multmodp(t.pow_slice[j - 1], xs);
+    {
+        uint32_t xc = 1u << 31;  // x^(8 * kChunk) = (x^(8 * kSlice))^(kChunk / kSlice)
+        for (uint32_t j = 0; j < kChunk / kSlice; ++j) xc = h_multmodp(xc, xs);
+        t.init_full = h_multmodp(xc, 0xFFFFFFFFu);
+    }
     cudaError_t e = cudaMemcpyToSymbol(g_gz, &t, sizeof t);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(iss_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));

@@ -56,6 +56,14 @@ __device__ __forceinline__ uint64_t u64of(uint32_t lo, uint32_t hi) { return (ui
 __device__ __forceinline__ uint64_t *u64p(uint32_t off) { return reinterpret_cast<uint64_t *>(iss_smem + off); }
 __device__ __forceinline__ uint32_t *u32p(uint32_t off) { return reinterpret_cast<uint32_t *>(iss_smem + off); }
 __device__ __forceinline__ uint8_t *imgp(const Lay &l, uint32_t o) { return iss_smem + (o ? l.img[1] : l.img[0]); }
+// explicit shared-window accesses for the hot loop: a 32-bit address held in ONE register, where a generic pointer costs two
+// and makes the compiler re-derive the window base (S2R CgaCtaId, MOV, LEA) at every use
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
 
 // Quality rows (kde.py:82-85: q = searchsorted(cdf_pos, u) = #{j : w > thr[j]}) are searched on the top 16 bits of the
 // draw: a row is the 64 sorted entries e[j] = thr[j] >> 16 as u16 (pad = 0xFFFF; e[63] is always pad), staged into shared
@@ -710,6 +718,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             const uint32_t sQ = iss_read_stream(o, ISS_K_QUAL) | att8;
             if (kde) {
                 const uint32_t row0 = smem0 + stage0 + (valid ? (u32p(l.sQrow)[rd] & 0xFFFFu) : 0u);  // shared-window address of the read's row in stage 0, first position
+                const uint32_t qual_s = smem0 + (o ? l.img[1] : l.img[0]) + seq_off + L + 3u;  // the quality line, and the
+                const uint32_t thr_s = smem0 + l.sErrThr;                                       //   error thresholds by phred
                 const bool producer = pair == 0;
                 const bool more_tiles = tile + gridDim.x < ntiles;
                 // one block: wait for its rows, draw + search two positions, hand the stage back
@@ -726,8 +736,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         if (tie0) {
                             defer_position(l, p.tie_cap, rd, pos, q0);
                         } else {
-                            qual[pos] = (uint8_t)(q0 + 33u);
-                            if (w.y > u32p(l.sErrThr)[q0]) {
+                            sts_u8(qual_s + pos, q0 + 33u);
+                            if (w.y > lds_u32(thr_s + 4u * q0)) {
                                 const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
                                 if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else err_overflow(p, slot, (rd << 16) | pos);
                             }
@@ -736,8 +746,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                             if (tie1) {
                                 defer_position(l, p.tie_cap, rd, pos + 1u, q1);
                             } else {
-                                qual[pos + 1u] = (uint8_t)(q1 + 33u);
-                                if (w.w > u32p(l.sErrThr)[q1]) {
+                                sts_u8(qual_s + pos + 1u, q1 + 33u);
+                                if (w.w > lds_u32(thr_s + 4u * q1)) {
                                     const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
                                     if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else err_overflow(p, slot, (rd << 16) | (pos + 1u));
                                 }

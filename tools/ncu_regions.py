@@ -7,7 +7,7 @@ import csv, os, re, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "insilicoseq_b200/csrc/libiss_b200.so")], cwd=tmp,
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("ISS_SO", os.path.join(ROOT, "insilicoseq_b200/csrc/libiss_b200.so"))], cwd=tmp,
                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 KFILE = os.environ.get("ISS_KERNEL_FILE", "iss_kernels")
 cub = [f for f in os.listdir(tmp) if f.startswith(KFILE + ".") and f.endswith(".cubin")][0]
