@@ -431,14 +431,15 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
     }
     if (tid < 32) s.dl[tid] = code->dl[tid];
     if (tid < 256) s.lcode[tid] = (uint8_t)len_code(tid + 3u);
-    if (tid == 0) s.ticket = atomicAdd(&work[kWorkTicket], 1u);
     for (;;) {
-        __syncthreads();  // previous chunk fully written out; tables loaded; this chunk's ticket in place
+        __syncthreads();  // previous chunk fully written out; tables loaded
+        // A ticket is taken when its chunk is started, never ahead: the look-back of the chunks behind it waits for this
+        // chunk's size, and a ticket held back for the length of another chunk makes every one of them wait that long
+        // (measured: prefetching the ticket cost a factor of five in the pipeline).
+        if (tid == 0) s.ticket = atomicAdd(&work[kWorkTicket], 1u);
+        __syncthreads();
         const uint32_t c = s.ticket;
         if (c >= n_chunks) break;
-        // the next ticket is asked for now and put in place at the end of this chunk: the round trip of the atomic is hidden
-        uint32_t next_ticket = 0;
-        if (tid == 0) next_ticket = atomicAdd(&work[kWorkTicket], 1u);
         const uint64_t base = (uint64_t)c * kChunk;
         const uint32_t n = (uint32_t)((n_in - base < kChunk) ? (n_in - base) : kChunk);
         const uint8_t *src = in + base;
@@ -661,10 +662,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         // 6. the member at its final place: header, deflate bytes, CRC32, ISIZE
         const uint64_t off = (uint64_t)s.misc[5] | ((uint64_t)s.misc[6] << 32);
         if (off >= kFail) {
-            if (tid == 0) {
-                if (c + 1u == n_chunks) status[n_chunks] = ~0ull;
-                s.ticket = next_ticket;
-            }
+            if (tid == 0 && c + 1u == n_chunks) status[n_chunks] = ~0ull;
             continue;
         }
         uint8_t *dst = out + off;
@@ -701,7 +699,6 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             uint8_t *t = dst + 10 + nbytes;
             for (int k = 0; k < 4; ++k) { t[k] = (uint8_t)(crc32 >> (8 * k)); t[4 + k] = (uint8_t)(n >> (8 * k)); }
             if (c + 1u == n_chunks) status[n_chunks] = off + 18u + nbytes;  // total bytes of the stream
-            s.ticket = next_ticket;
         }
     }
 }

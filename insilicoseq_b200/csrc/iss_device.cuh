@@ -284,7 +284,8 @@ struct GenParams {
     uint8_t *out2;
     // quality-row pipeline (phase 4): every position stream (orientation x part) of a tile walks the same rows for every
     // tile; its producer lane stages them one block ahead with cp.async.bulk + mbarriers (two stages per stream)
-    uint32_t q_stage_cap;     // bytes reserved per stage (>= q_stage_bytes[o], multiple of 16)
+    uint32_t q_stage_cap;     // bytes reserved per stage (>= q_blocks * q_stage_bytes[o], multiple of 16)
+    uint32_t q_blocks;        // Philox blocks per stage: 1, or 2 (the <512, 2, 2> build)
     uint32_t q_stage_bytes[2];  // 2 * q16_ps[o]: the rows of one block of orientation o
     uint32_t q_pos_stride[2];   // q16_ps[o]
     uint32_t q_row_off[2][4];   // bin -> byte offset of its row inside a position (q16_cbin * ISS_Q16_ROW_BYTES)

@@ -385,7 +385,7 @@ __device__ __noinline__ void replay_indels_warp(const GenParams &p, const Lay &l
 
 }  // namespace
 
-template <int kThreads, int kMinBlocks>
+template <int kThreads, int kMinBlocks, int kQB>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const Lay &l = p.lay;
@@ -431,10 +431,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
     }
     // producer lane only: stage `stg` <- the rows of block `blk`, after every warp of the stream released the stage
     auto q_fill = [&](uint32_t stg, uint32_t blk, uint32_t done /* consumptions of the stage so far */) {
-        const uint32_t fb = bar0 + (stg << 4), bytes = p.q_stage_bytes[o];
+        // kQB blocks per stage (their rows are contiguous in the blob); the stream's last turn may hold fewer
+        const uint32_t fb = bar0 + (stg << 4), bytes1 = p.q_stage_bytes[o];
+        const uint32_t bytes = (kQB == 1 || blk + 1u >= b_end) ? bytes1 : 2u * bytes1;
         mbar_wait(fb + 8u, (done + 1u) & 1u);
         mbar_arrive_expect_tx(fb, bytes);
-        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * bytes, bytes, fb);
+        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * bytes1, bytes, fb);
     };
     if (kde && pair == 0 && blockIdx.x < ntiles && b_begin < b_end) q_fill(0u, b_begin, 0u);
 
@@ -723,49 +725,55 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 const bool producer = pair == 0;
                 const bool more_tiles = tile + gridDim.x < ntiles;
                 // one block: wait for its rows, draw + search two positions, hand the stage back
-                auto q_block = [&](uint32_t b, uint32_t stg) {
+                // one block: draw + search two positions against the rows at r0
+                auto q_block = [&](uint32_t b, uint32_t r0) {
+                    const uint32_t pos = 2u * b;
+                    const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
+                    bool tie0, tie1;
+                    uint32_t q0, q1;  // the row behind an odd L is all pad: q1 = 0 there, and not used
+                    q16_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
+                    if (tie0) {
+                        defer_position(l, p.tie_cap, rd, pos, q0);
+                    } else {
+                        sts_u8(qual_s + pos, q0 + 33u);
+                        if (w.y > lds_u32(thr_s + 4u * q0)) {
+                            const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else err_overflow(p, slot, (rd << 16) | pos);
+                        }
+                    }
+                    if (pos + 1u < L) {
+                        if (tie1) {
+                            defer_position(l, p.tie_cap, rd, pos + 1u, q1);
+                        } else {
+                            sts_u8(qual_s + pos + 1u, q1 + 33u);
+                            if (w.w > lds_u32(thr_s + 4u * q1)) {
+                                const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else err_overflow(p, slot, (rd << 16) | (pos + 1u));
+                            }
+                        }
+                    }
+                };
+                // one turn of a stage: wait for its rows, its kQB blocks, hand the stage back
+                auto q_stage = [&](uint32_t b, uint32_t stg) {
                     mbar_wait(bar0 + (stg << 4), (qpar >> stg) & 1u);
                     qpar ^= 1u << stg;
                     if (valid) {
-                        const uint32_t pos = 2u * b;
                         const uint32_t r0 = row0 + stg * p.q_stage_cap;
-                        const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
-                        bool tie0, tie1;
-                        uint32_t q0, q1;  // the row behind an odd L is all pad: q1 = 0 there, and not used
-                        q16_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
-                        if (tie0) {
-                            defer_position(l, p.tie_cap, rd, pos, q0);
-                        } else {
-                            sts_u8(qual_s + pos, q0 + 33u);
-                            if (w.y > lds_u32(thr_s + 4u * q0)) {
-                                const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                                if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else err_overflow(p, slot, (rd << 16) | pos);
-                            }
-                        }
-                        if (pos + 1u < L) {
-                            if (tie1) {
-                                defer_position(l, p.tie_cap, rd, pos + 1u, q1);
-                            } else {
-                                sts_u8(qual_s + pos + 1u, q1 + 33u);
-                                if (w.w > lds_u32(thr_s + 4u * q1)) {
-                                    const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
-                                    if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | (pos + 1u); else err_overflow(p, slot, (rd << 16) | (pos + 1u));
-                                }
-                            }
-                        }
+                        q_block(b, r0);
+                        if (kQB == 2 && b + 1u < b_end) q_block(b + 1u, r0 + p.q_stage_bytes[o]);
                     }
                     __syncwarp();
                     if ((tid & 31u) == 0) mbar_arrive(bar0 + (stg << 4) + 8u);  // this warp is done with the stage
                 };
-                for (uint32_t b = b_begin; b < b_end; b += 2u) {
-                    const bool second = b + 1u < b_end;
-                    if (producer && second) q_fill(1u, b + 1u, (qpar >> 1) & 1u);
-                    q_block(b, 0u);
-                    if (producer) {  // stage 0 for the next turn: the next pair of blocks, or the first block of the next tile
-                        if (b + 2u < b_end) q_fill(0u, b + 2u, qpar & 1u);
+                for (uint32_t b = b_begin; b < b_end; b += 2u * kQB) {
+                    const bool second = b + kQB < b_end;
+                    if (producer && second) q_fill(1u, b + kQB, (qpar >> 1) & 1u);
+                    q_stage(b, 0u);
+                    if (producer) {  // stage 0 for the next turn: the next blocks, or the first ones of the next tile
+                        if (b + 2u * kQB < b_end) q_fill(0u, b + 2u * kQB, qpar & 1u);
                         else if (more_tiles) q_fill(0u, b_begin, qpar & 1u);
                     }
-                    if (second) q_block(b + 1u, 1u);
+                    if (second) q_stage(b + kQB, 1u);
                 }
             } else if (valid) {
                 for (uint32_t b = b_begin; b < b_end; ++b) {
@@ -989,29 +997,38 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 // ---- host-visible launch helpers --------------------------------------------------------------------
 size_t iss_tile_smem_bytes(const Lay &l) { return l.total; }
 
-cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
-    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+// Three builds: 256 threads x 4 CTAs/SM (64-pair tiles), 512 x 2 with one Philox block per quality stage (long reads, each
+// read split over 4 threads) and 512 x 2 with two blocks per stage (128-pair tiles of short reads).
+template <typename F>
+static cudaError_t for_each_build(F f) {
+    cudaError_t e = f(iss_generate_kernel<256, 4, 1>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    e = f(iss_generate_kernel<512, 2, 1>);
+    if (e != cudaSuccess) return e;
+    return f(iss_generate_kernel<512, 2, 2>);
+}
+
+cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
+    return for_each_build([&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem); });
 }
 
 cudaError_t iss_kernel_carveout(int percent) {  // shared-memory share of the SM's unified L1/shared array
-    cudaError_t e = cudaFuncSetAttribute(iss_generate_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(iss_generate_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, percent);
+    return for_each_build([&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, percent); });
 }
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
-    if (threads > 256) iss_generate_kernel<512, 2><<<grid, threads, smem, stream>>>(p);
-    else iss_generate_kernel<256, 4><<<grid, threads, smem, stream>>>(p);
+    if (threads > 256 && p.q_blocks == 2) iss_generate_kernel<512, 2, 2><<<grid, threads, smem, stream>>>(p);
+    else if (threads > 256) iss_generate_kernel<512, 2, 1><<<grid, threads, smem, stream>>>(p);
+    else iss_generate_kernel<256, 4, 1><<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, size_t smem, int *blocks_per_sm) {
+cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_blocks, size_t smem, int *blocks_per_sm) {
     const int threads = (int)((2u << split_shift) * T);
-    if (threads > 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2>, threads, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4>, threads, smem);
+    if (threads > 256 && q_blocks == 2) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2>, threads, smem);
+    if (threads > 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 1>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 1>, threads, smem);
 }
 
 cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {

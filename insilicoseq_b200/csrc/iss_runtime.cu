@@ -122,6 +122,7 @@ struct iss_ctx {
     uint32_t n_slots = 0, max_segs = 0;
     uint32_t tile_pairs = 64, img_cap = 0, err_cap = 512, grid = 0, split_shift = 1;
     uint32_t q_stage_cap = 0;  // quality-row pipeline: bytes per stage
+    uint32_t q_blocks = 1;     //   and Philox blocks (2 positions each) per stage
     uint64_t scratch_replay_bytes = 0;  // replay part of a slot's scratch; the substitution overflow lists follow
     Lay lay{};
     size_t smem = 0;
@@ -291,6 +292,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     philox_round_keys(batch_key, p.rk);
     p.lay = c->lay;
     p.q_stage_cap = c->q_stage_cap;
+    p.q_blocks = c->q_blocks;
     for (uint32_t o = 0; o < 2; ++o) {
         p.q_pos_stride[o] = h.q16_ps[o];
         p.q_stage_bytes[o] = 2u * h.q16_ps[o];
@@ -873,37 +875,52 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     if (total == 0) { c->active = true; return ISS_OK; }
     const uint64_t batch_pairs = std::min<uint64_t>(o.batch_pairs, total);
     // tile geometry: T pairs per CTA so that both stream images + bookkeeping fit in shared memory
-    uint32_t T = 64;
-    if (const char *e = getenv("ISS_TILE")) {  // A/B switch for benchmarks: 128 pairs per tile (512-thread CTAs, 2 per SM)
-        if (atoi(e) == 128) T = 128;
-    }
+    uint32_t T = 64, q_blocks = 1;
+    int tile_env = 0;
+    if (const char *e = getenv("ISS_TILE")) tile_env = atoi(e);  // A/B switch for benchmarks and tests: 64 or 128 pairs per tile, one block per stage
+    if (tile_env == 128) T = 128;
     uint32_t img_cap = 0;
     size_t smem = 0;
     c->err_cap = 512;
-    // quality-row pipeline geometry: one stage = the 16-bit rows of 2 positions for the populated bins of an orientation
+    // quality-row pipeline geometry: one stage = the 16-bit rows of q_blocks Philox blocks (2 positions each) for the
+    // populated bins of an orientation
     const bool kde = c->mh.qual_mode == ISS_QUAL_KDE;
-    const uint32_t q_cap = kde ? 2u * std::max(c->mh.q16_ps[0], c->mh.q16_ps[1]) : 0u;
-    auto layout = [&](uint32_t T_, uint32_t split) {
-        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, kTieCap, 2u << split, q_cap);
+    const uint32_t q_cap1 = kde ? 2u * std::max(c->mh.q16_ps[0], c->mh.q16_ps[1]) : 0u;
+    auto layout = [&](uint32_t T_, uint32_t split, uint32_t qb) {
+        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, kTieCap, 2u << split, qb * q_cap1);
     };
     Lay lay{};
-    for (;; T >>= 1) {
-        img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
-        lay = layout(T, 1);
-        smem = lay.total;
-        if (smem <= kMaxSmem) break;
-        if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
-    }
     int bps = 0;
     uint32_t split_shift = 1;
-    CU(iss_occupancy(T, split_shift, smem, &bps));
-    if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
-    if (bps <= 2 && T == 64) {  // long reads: the images leave room for <= 2 CTAs/SM -> 4 threads per read keep 32 warps/SM
-        int bps4 = 0;
-        const Lay lay4 = layout(T, 2);
-        if (lay4.total <= kMaxSmem) {
-            CU(iss_occupancy(T, 2, lay4.total, &bps4));
-            if (bps4 >= bps) { split_shift = 2; bps = bps4; lay = lay4; smem = lay4.total; }
+    bool wide = false;
+    if (kde && tile_env == 0) {
+        // short reads: 128-pair tiles (512 threads, 2 CTAs/SM) with TWO blocks per stage.  Half as many CTAs per SM hold
+        // half as many stages, so a stage can be twice as long in the same shared memory; every wait, hand-back and
+        // cp.async.bulk of the row pipeline then serves four positions instead of two.
+        const Lay w = layout(128, 1, 2);
+        int b = 0;
+        if (w.total <= kMaxSmem && iss_occupancy(128, 1, 2, w.total, &b) == cudaSuccess && b >= 2) {
+            wide = true; T = 128; q_blocks = 2; lay = w; smem = w.total; bps = b;
+            img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
+        }
+    }
+    if (!wide) {
+        for (;; T >>= 1) {
+            img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
+            lay = layout(T, 1, 1);
+            smem = lay.total;
+            if (smem <= kMaxSmem) break;
+            if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
+        }
+        CU(iss_occupancy(T, split_shift, 1, smem, &bps));
+        if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
+        if (bps <= 2 && T == 64) {  // long reads: the images leave room for <= 2 CTAs/SM -> 4 threads per read keep 32 warps/SM
+            int bps4 = 0;
+            const Lay lay4 = layout(T, 2, 1);
+            if (lay4.total <= kMaxSmem) {
+                CU(iss_occupancy(T, 2, 1, lay4.total, &bps4));
+                if (bps4 >= bps) { split_shift = 2; bps = bps4; lay = lay4; smem = lay4.total; }
+            }
         }
     }
     // the substitution list takes whatever shared memory the occupancy leaves (long-read tiles run 2 CTAs/SM with room to
@@ -911,14 +928,15 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     for (uint32_t cap = 8192; cap > c->err_cap; cap >>= 1) {
         const uint32_t keep = c->err_cap;
         c->err_cap = cap;
-        const Lay big = layout(T, split_shift);
+        const Lay big = layout(T, split_shift, q_blocks);
         int b2 = 0;
-        if (big.total <= kMaxSmem && iss_occupancy(T, split_shift, big.total, &b2) == cudaSuccess && b2 >= bps) { lay = big; smem = big.total; break; }
+        if (big.total <= kMaxSmem && iss_occupancy(T, split_shift, q_blocks, big.total, &b2) == cudaSuccess && b2 >= bps) { lay = big; smem = big.total; break; }
         c->err_cap = keep;
     }
     c->split_shift = split_shift;
     c->lay = lay;
-    c->q_stage_cap = q_cap;
+    c->q_stage_cap = q_blocks * q_cap1;
+    c->q_blocks = q_blocks;
     if (const char *e = getenv("ISS_BPS")) {  // A/B switch for benchmarks: fewer CTAs per SM (with ISS_CARVEOUT: more L1)
         const int cap = atoi(e);
         if (cap >= 1 && cap < bps) bps = cap;

@@ -101,9 +101,12 @@ def test_against_oracle_at_scale(spec, npairs):
 
 @pytest.mark.parametrize("name", ["miseq150_bench_model", "stress_indels_dense", "hiseq_multi_short", "quality_ties_16bit",
                                   "nextseq_large_digest", "read_length_2"])
-def test_128_pair_tiles(name, monkeypatch):
-    """ISS_TILE=128: 512-thread CTAs, four warps per position stream (four arrivals per `empty` barrier of the quality-row ring)."""
-    monkeypatch.setenv("ISS_TILE", "128")
+@pytest.mark.parametrize("tile", ["64", "128"])
+def test_tile_geometries(name, tile, monkeypatch):
+    """The default for short KDE reads is 128-pair tiles with two Philox blocks per quality-row stage (the <512, 2, 2>
+    build); ISS_TILE=64 forces 64-pair tiles (256-thread CTAs, the <256, 4, 1> build), ISS_TILE=128 the 128-pair tiles with
+    one block per stage (<512, 2, 1>, four warps per position stream)."""
+    monkeypatch.setenv("ISS_TILE", tile)
     case, exp = fixtures.load_case(name)
     r1, r2, _ = run_product(case, batch_pairs=300)
     assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]

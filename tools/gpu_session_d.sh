@@ -20,8 +20,10 @@ PY
 }
 export OUT
 summ $OUT/bench_n1.json cfg1
-( ISS_TILE=128 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/bench_tile128.json 2> $OUT/bench_tile128.err
-summ $OUT/bench_tile128.json tile128
+for t in 64 128; do
+( ISS_TILE=$t timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/bench_tile$t.json 2> $OUT/bench_tile$t.err
+summ $OUT/bench_tile$t.json tile$t
+done
 ( timeout 300 python bench.py --config 3 --steps 3 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/bench_cfg3_dev.json 2> $OUT/bench_cfg3_dev.err
 summ $OUT/bench_cfg3_dev.json cfg3dev
 ( timeout 200 python tools/profile_model.py MiSeq 1000000 ) > $OUT/legacy_run.log 2>&1; tail -3 $OUT/legacy_run.log | head -2 | tee -a $OUT/summary.txt
@@ -35,11 +37,13 @@ for r in csv.reader(open(os.environ["OUT"] + "/gzip_launches.csv")):
 for k, v in d.items():
     print("%s: %d launches, mean %.1f us" % (k, len(v), sum(v) / len(v) / 1000))
 PY
+( timeout 120 python tools/gz_trace.py ) > $OUT/gz_trace.out 2> $OUT/gz_trace.log
+grep device_only $OUT/gz_trace.log | tee -a $OUT/summary.txt
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:iss_deflate_kernel -s 4 -c 1 -o $OUT/deflate_full -f python tools/gz_profile.py ) > $OUT/ncu_deflate.log 2>&1
 ncu -i $OUT/deflate_full.ncu-rep --page details > $OUT/deflate_ncu_details.txt 2>&1
 ISS_KERNEL_FILE=iss_deflate ISS_KERNEL_SYM=_Z18iss_deflate_kernel python tools/ncu_lines.py $OUT/deflate_full.ncu-rep 50 > $OUT/deflate_by_source_line.txt 2>&1
 ( timeout 600 ncu --set full --clock-control none --import-source on -k regex:iss_generate_kernel -s 6 -c 1 -o $OUT/gen_full -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --device-only ) > $OUT/ncu_full.log 2>&1
 ncu -i $OUT/gen_full.ncu-rep --page details > $OUT/ncu_details.txt 2>&1
 ncu -i $OUT/gen_full.ncu-rep --page raw --csv > $OUT/ncu_raw.csv 2>&1
-python tools/ncu_lines.py $OUT/gen_full.ncu-rep 60 > $OUT/ncu_by_source_line.txt 2>&1
+ISS_KERNEL_SYM=${GEN_SYM:-_Z19iss_generate_kernelILi512ELi2ELi2E} python tools/ncu_lines.py $OUT/gen_full.ncu-rep 60 > $OUT/ncu_by_source_line.txt 2>&1
 cat $OUT/summary.txt

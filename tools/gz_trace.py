@@ -11,7 +11,7 @@ with eng_mod.Engine(0) as e:
     e.set_genome([("syn5M", genome)])
     e.set_model(error_models.KDErrorModel(os.path.join(error_models.PROFILE_DIR, "miSeq_0.npz")).truncate(150))
     items = eng_mod.worker_items([(0, 24 << 18)], 0, 42, e.record_lengths, e.read_length)
-    for dev_only in (False,):
+    for dev_only in (True, False):
         for rep in range(2):
             e.mark(0)
             t = time.time()
