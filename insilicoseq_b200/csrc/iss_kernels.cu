@@ -450,8 +450,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         // ---- phase 1: one thread per pair (generator.py:121-177, kde.py:72-78,97).  Nothing here touches the stream
         //      images, which the previous tile's copy-out may still be reading; its bulk stores are waited for by thread 0
         //      before the barrier that ends the phase.
+        if (tid == blockDim.x - 1u) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the thread that issued them; returns at once when nothing is pending
         if (tid == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // returns at once when nothing is pending
             u32p(l.sCtl)[0] = 0; u32p(l.sCtl)[1] = 0; u32p(l.sCtl)[4] = 0; u32p(l.sCtl)[6] = 0;
             u32p(l.sCtl)[2] ^= 1u;  // phase parity of the gather mbarrier for this tile (1, 0, 1, ... ; read as parity ^ 1)
         }
@@ -901,7 +901,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         const uint32_t nerr_fast = u32p(l.sCtl)[0];
         const bool redo_all = ntie > p.tie_cap || nerr_fast > p.err_cap + p.err_ovf_cap;  // block-uniform
         if (ntie && !redo_all) {
-            for (uint32_t e = tid; e < ntie; e += blockDim.x) {
+            for (uint32_t e = blockDim.x - 1u - tid; e < ntie; e += blockDim.x) {  // from the CTA's last threads: beside the substitutions, which start at thread 0
                 const uint32_t v = u32p(l.sTie)[e];
                 const uint32_t trd = v >> 24, pos = v & 0xFFFFu;
                 const uint32_t to = trd >= T ? 1u : 0u, tp = trd - to * T;
@@ -944,6 +944,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
             }
             if (napplied) atomicAdd(p.counters + 1, (unsigned long long)napplied);
         }
+        // The copy-out geometry is read BEFORE the barrier (it dates from phase 1): behind it no thread reads the per-pair
+        // arrays any more, so the next tile's phase 1 -- which no barrier separates from this copy-out -- may overwrite them.
+        const uint64_t g0 = u64p(l.sOff)[0];
+        const uint32_t tile_bytes = (uint32_t)(u64p(l.sOff)[npairs - 1] - g0) + u32p(l.sCtl)[3];
         // generic-proxy writes to shared memory must be visible to the async (TMA) proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -951,9 +955,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         // ---- phase 6: copy-out.  [g0, g0 + tile_bytes) of each stream; the 16 B aligned middle goes through the
         //      bulk-copy engine, the ragged head/tail (< 16 B each) through plain byte stores.
         {
-            const uint64_t g0 = u64p(l.sOff)[0];
             const uint32_t a0 = (uint32_t)(g0 & 15u);
-            const uint32_t tile_bytes = (uint32_t)(u64p(l.sOff)[npairs - 1] - g0) + u32p(l.sCtl)[3];
             uint32_t head = (16u - a0) & 15u;
             if (head > tile_bytes) head = tile_bytes;
             const uint32_t mid = (tile_bytes - head) & ~15u;
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                 (st ? p.out2 : p.out1)[g0 + byte] = imgp(l, st)[a0 + byte];
             }
 #ifndef ISS_NO_BULK_STORE
-            if (tid == 0 && mid) {
+            if (tid == blockDim.x - 1u && mid) {  // a thread without a pair in phase 1: its wait for these stores runs beside that phase
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out1 + g0 + head),
                              "r"(smem_addr(imgp(l, 0) + a0 + head)), "r"(mid)
                              : "memory");
@@ -986,7 +988,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         }
         // the next tile's phase-1 barrier orders these reads before any new write to the images
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tid == blockDim.x - 1u) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out) {

@@ -128,6 +128,7 @@ struct iss_ctx {
     size_t smem = 0;
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
+    cudaEvent_t gen_done[2] = {nullptr, nullptr};  // end of the generate kernels of the last two launches (events of their slots)
     bool trace = getenv("ISS_TRACE") != nullptr;
     int ring_alloc = ISS_HOSTMEM_NUMA;  // ISS_RING_ALLOC=pinned|numa|wc
     double gz_ratio[2] = {0.4, 0.4};            // compressed / plain bytes per stream: a first guess, then the last returned batch
@@ -150,6 +151,7 @@ int set_device(iss_ctx *c) {
 }
 
 void free_slots(iss_ctx *c) {
+    c->gen_done[0] = c->gen_done[1] = nullptr;  // they belong to the slots
     for (auto &s : c->slots) {
         if (s.d_out[0]) cudaFree(s.d_out[0]);
         if (s.d_out[1]) cudaFree(s.d_out[1]);
@@ -327,9 +329,16 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     if (p.store_mutations) CU(cudaMemsetAsync(s.d_evcount, 0, sizeof(unsigned long long), s.stream));
     const uint64_t ntiles = (pairs + c->tile_pairs - 1) / c->tile_pairs;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, c->grid);
+    // At most two generate kernels in flight: this one starts when the one launched two batches ago has ended.  Two still
+    // hide each other's tails; but when the host hands back several slots at once (and when the ring is primed) their
+    // kernels would otherwise all share the GPU, every one of them several times slower, and the first compressed batch
+    // -- all the copy engine is waiting for -- would be late by that factor.
+    cudaEvent_t &prev2 = c->gen_done[c->next_launch & 1u];
+    if (prev2) CU(cudaStreamWaitEvent(s.stream, prev2, 0));
     CU(cudaEventRecord(s.ev_k0, s.stream));
     CU(iss_launch_generate(p, grid, c->smem, s.stream));
     CU(cudaEventRecord(s.ev_k1, s.stream));
+    prev2 = s.ev_k1;
     if (c->mh.store_mutations)
         CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     if (c->opts.compress) {
@@ -871,6 +880,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     c->opts = o;
     c->cur_item = 0; c->cur_off = 0;
     c->next_launch = 0; c->next_return = 0;
+    c->gen_done[0] = c->gen_done[1] = nullptr;
     c->exhausted = (total == 0);
     if (total == 0) { c->active = true; return ISS_OK; }
     const uint64_t batch_pairs = std::min<uint64_t>(o.batch_pairs, total);
