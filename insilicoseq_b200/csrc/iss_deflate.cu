@@ -34,7 +34,7 @@ constexpr uint32_t kPiece = 16384;     // granule of the histogram sample
 constexpr uint32_t kLitLen = 286, kDist = 30;  // symbols of the two alphabets (HLIT = 29, HDIST = 29)
 constexpr uint32_t kHeaderBits = 17 + 19 * 3 + (kLitLen + kDist) * 4;  // 1338
 constexpr uint32_t kHdrWords = (kHeaderBits + 31) / 32;                // 42
-constexpr uint32_t kMaxTok = 1024;     // matches per member kept (a 64 KB chunk of 150 bp FASTQ holds ~200 records)
+constexpr uint32_t kMaxTok = 512;      // name-line matches per member kept (a 64 KB chunk of 150 bp FASTQ holds ~200 records)
 constexpr uint32_t kSampleLz = 16384;  // bytes of the stream whose matches give the length / distance statistics
 
 // RFC 1951 3.2.5: length codes 257..285 and distance codes 0..29
@@ -77,6 +77,23 @@ done:
 }
 // 0x80 in every byte of x that is zero (exact for any x: no borrow between bytes)
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t x) { return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u; }
+// 4 bits of a word's byte flags (0x80 per byte, as zero_bytes returns them): bit j = byte j
+__device__ __forceinline__ uint32_t byte_flags4(uint32_t f) { return (((f >> 7) * 0x01020408u) >> 24) & 0xFu; }
+// the bits of m that lie in runs of at least 4 consecutive ones (m: 64 positions)
+__device__ __forceinline__ uint64_t runs4(uint64_t m) {
+    const uint64_t a = m & (m >> 1), b = a & (a >> 2);  // b: four ones start here
+    const uint64_t c = b | (b << 1);
+    return c | (c << 2);
+}
+// bits [a, b) of a 128-bit mask held in four words (a <= b <= 128)
+__device__ __forceinline__ void set_range128(uint32_t m[4], uint32_t a, uint32_t b) {
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t lo = a > 32u * j ? a - 32u * j : 0u, hi = b > 32u * j ? b - 32u * j : 0u;  // clamped below; above: >= 32 means all
+        const uint32_t mh = hi >= 32u ? 0xFFFFFFFFu : ((1u << hi) - 1u), ml = lo >= 32u ? 0xFFFFFFFFu : ((1u << lo) - 1u);
+        m[j] |= mh & ~ml;
+    }
+}
 constexpr uint32_t kPoly = 0xedb88320u;
 
 __device__ __forceinline__ uint32_t multmodp(uint32_t a, uint32_t b) {  // a * b mod P over GF(2), reflected (zlib)
@@ -136,6 +153,7 @@ struct TableSmem {
     uint8_t lens[288];
     uint32_t tokf[64];    // sample statistics: [0..28] match-length codes, [32..61] distance codes
     int32_t start[256];   // sample planning: record start inside each 64-byte slice of the first 16 KB (-1: none)
+    uint32_t sub[256];    // sample statistics: bytes of each value that the sample's runs cover (they are not literals)
 };
 
 __device__ __forceinline__ void put_bits(uint32_t *out, uint32_t pos, uint32_t v, uint32_t nbits) {
@@ -326,6 +344,7 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__rest
     if (tid == 0) s.total = 0;
     if (tid < 44) s.out[tid] = 0;
     if (tid < 64) s.tokf[tid] = 0;
+    s.sub[tid] = 0;
     __syncthreads();
     const uint32_t f0 = work[kWorkHist + tid];
     atomicAdd(&s.total, f0);
@@ -352,10 +371,32 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__rest
             }
         }
     }
+    {   // the distance-1 runs of the same window (the member kernel's rule, name lines not taken out: statistics only)
+        uint64_t m = 0;
+        for (uint32_t j = 0; j < 64u; ++j) {
+            const uint32_t x = tid * 64u + j;
+            if (x >= 1u && x < ns && in[x] == in[x - 1u]) m |= 1ull << j;
+        }
+        const uint64_t e = runs4(m);
+        uint64_t st = e & ~(e << 1);
+        while (st) {
+            const uint32_t x = (uint32_t)__ffsll((long long)st) - 1u;
+            st &= st - 1ull;
+            const uint64_t nz = ~(e >> x);
+            const uint32_t r = nz ? (uint32_t)__ffsll((long long)nz) - 1u : 64u;
+            atomicAdd(&s.tokf[len_code(r)], 1u);
+            atomicAdd(&s.tokf[32u], 1u);  // distance 1 = distance code 0
+            atomicAdd(&s.sub[in[tid * 64u + x]], r);
+        }
+    }
     __syncthreads();
     const uint32_t scale = ns ? (s.total / ns > 1u ? s.total / ns : 1u) : 1u;  // sampled bytes per byte of the 16 KB window
     if (tid == 0) s.freq[256] = (s.total >> 16) ? (s.total >> 16) : 1u;  // end of block: one per 64 KB member
     if (tid < 29) s.freq[257 + tid] = s.tokf[tid] * scale + 1u;
+    {
+        const uint32_t covered = s.sub[tid] * scale, f = s.freq[tid];
+        s.freq[tid] = f > covered + 1u ? f - covered : 1u;
+    }
     __syncthreads();
     build_code(s, kLitLen, tid);
     GzCode *code = reinterpret_cast<GzCode *>(work + kWorkCode);
@@ -395,6 +436,7 @@ struct Smem {
     uint32_t tok_pos[kMaxTok];   // the member's matches in stream order: start inside the chunk,
     uint32_t tok_ld[kMaxTok];    //   length | distance << 16 (distance 32768 stored as 0)
     int32_t last_start[kThreads];  // last record start inside each slice (-1: none)
+    uint4 cov[kThreads];     // per slice, one bit per byte: first "equals the byte in front of it", then "covered by a match"
     uint16_t tok_off[kThreads + 1];  // matches that start before each slice
     uint8_t len8[288];
     uint8_t lcode[256];      // match length - 3 -> length code 0..28
@@ -455,6 +497,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         for (uint32_t i = lo; i < hi; i += 32u) {  // one 32-byte sector per step: both halves are asked for before either is used
             const uint4 va = __ldg(src4 + ((i - lo) >> 4)), vb = i + 16u < hi ? __ldg(src4 + ((i - lo) >> 4) + 1) : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t wds[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+            uint32_t same32 = 0;
 #pragma unroll
             for (uint32_t k = 0; k < 8; ++k) {
                 const uint32_t wd = wds[k];
@@ -472,6 +515,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                 // record starts, from registers and without a branch for all but the starts themselves: byte j of b1 / b2 /
                 // b3 is the byte 1 / 2 / 3 places in front of byte j of wd; a start is '@' behind '\n' but not behind "\n+\n"
                 const uint32_t b1 = __funnelshift_l(prev_word, wd, 8), b2 = __funnelshift_l(prev_word, wd, 16), b3 = __funnelshift_l(prev_word, wd, 24);
+                same32 |= byte_flags4(zero_bytes(wd ^ b1)) << (4u * k);  // runs: byte == the byte in front of it
                 uint32_t starts = zero_bytes(wd ^ 0x40404040u) & zero_bytes(b1 ^ 0x0A0A0A0Au) & ~(zero_bytes(b2 ^ 0x2B2B2B2Bu) & zero_bytes(b3 ^ 0x0A0A0A0Au));
                 while (starts) {  // once per record
                     const uint32_t x = i + 4u * k + ((uint32_t)(__ffs((int)starts) - 1) >> 3);
@@ -480,7 +524,9 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                 }
                 prev_word = wd;
             }
+            reinterpret_cast<uint32_t *>(&s.cov[tid])[(i - lo) >> 5] = same32;
         }
+        for (uint32_t j = hi > lo ? (hi - lo + 31u) >> 5 : 0u; j < 4u; ++j) reinterpret_cast<uint32_t *>(&s.cov[tid])[j] = 0u;  // no data there
         s.last_start[tid] = st1;
         __syncthreads();  // out[] initialised, misc zeroed, record starts visible
         // 2. name-line matches that start in my slice: each record start against the one before it (inside this member)
@@ -517,19 +563,53 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             s.tok_off[kThreads] = (uint16_t)(tot < kMaxTok ? tot : kMaxTok);
         }
         __syncthreads();
-        // 3. my slice's bits: literals of the bytes no match covers + the matches that start here
+        // 3. my slice's plan: the bytes the name-line matches cover, then distance-1 runs (>= 4 bytes equal to the byte in
+        //    front of them: quality lines of binned instruments are mostly such runs) in what is left.  Runs are cut at the
+        //    slice's end and in its middle, never touch a name-line match, and a match is never followed by another one
+        //    without a literal in between -- so the cover mask alone tells where tokens start and how long a run is.
         const uint32_t t_begin = s.tok_off[tid], t_end = s.tok_off[tid + 1];
         uint32_t cov_end = lo;  // bytes [lo, cov_end) belong to a match that started in an earlier slice
         if (t_begin > 0) {
             const uint32_t e = s.tok_pos[t_begin - 1] + (s.tok_ld[t_begin - 1] & 0xFFFFu);
             if (e > lo) cov_end = e < hi ? e : hi;
         }
+        uint32_t nc[4] = {0u, 0u, 0u, 0u};  // name-line coverage
+        set_range128(nc, 0u, cov_end - lo);
         for (uint32_t x = lo; x < cov_end; ++x) bits -= s.len8[src[x]];
         for (uint32_t t = t_begin; t < t_end; ++t) {
             const uint32_t ps = s.tok_pos[t], ld = s.tok_ld[t], len = ld & 0xFFFFu, dist = (ld >> 16) ? (ld >> 16) : 32768u;
             const uint32_t e = ps + len < hi ? ps + len : hi;
             for (uint32_t x = ps; x < e; ++x) bits -= s.len8[src[x]];
             bits += match_bits(s, len, dist);
+            set_range128(nc, ps - lo, e - lo);
+        }
+        {
+            const uint4 sm = s.cov[tid];
+            uint32_t vm[4] = {0u, 0u, 0u, 0u};
+            set_range128(vm, lo ? 0u : 1u, hi > lo ? hi - lo : 0u);  // the member's first byte has nothing in front of it
+            // candidates: not covered, and not next to a covered byte on either side
+            const uint32_t r0 = sm.x & vm[0] & ~(nc[0] | (nc[0] << 1) | (nc[0] >> 1) | (nc[1] << 31));
+            const uint32_t r1 = sm.y & vm[1] & ~(nc[1] | (nc[1] << 1) | (nc[0] >> 31) | (nc[1] >> 1) | (nc[2] << 31));
+            const uint32_t r2 = sm.z & vm[2] & ~(nc[2] | (nc[2] << 1) | (nc[1] >> 31) | (nc[2] >> 1) | (nc[3] << 31));
+            const uint32_t r3 = sm.w & vm[3] & ~(nc[3] | (nc[3] << 1) | (nc[2] >> 31) | (nc[3] >> 1));
+            const uint64_t e0 = runs4((uint64_t)r0 | ((uint64_t)r1 << 32));
+            uint64_t m1 = (uint64_t)r2 | ((uint64_t)r3 << 32);
+            if (e0 >> 63) m1 &= ~1ull;  // the halves are planned apart: no run of the second one right behind a run of the first
+            const uint64_t e1 = runs4(m1);
+#pragma unroll 1
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint64_t e = h ? e1 : e0;
+                uint64_t st = e & ~(e << 1);  // run starts
+                while (st) {
+                    const uint32_t x = (uint32_t)__ffsll((long long)st) - 1u;
+                    st &= st - 1ull;
+                    const uint64_t nz = ~(e >> x);
+                    const uint32_t r = nz ? (uint32_t)__ffsll((long long)nz) - 1u : 64u;  // (e >> x has zeros above bit 63 - x)
+                    bits -= r * s.len8[src[lo + 64u * h + x - 1u]];
+                    bits += match_bits(s, r, 1u);
+                }
+            }
+            s.cov[tid] = make_uint4(nc[0] | (uint32_t)e0, nc[1] | (uint32_t)(e0 >> 32), nc[2] | (uint32_t)e1, nc[3] | (uint32_t)(e1 >> 32));
         }
         // block-wide exclusive scan of `bits`
         uint32_t incl = bits;
@@ -559,34 +639,19 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             uint32_t accbits = pos & 31u, wi = pos >> 5;
             uint32_t t = t_begin;
             uint32_t next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
-            uint32_t skip_to = cov_end;  // bytes below this position are covered by a match
+            uint4 cv = s.cov[tid];              // shift register: the low 16 bits are the group's cover bits
+            uint32_t carry = cov_end > lo ? 1u : 0u;  // the byte in front of the group is covered
             for (uint32_t i = lo; i < hi; i += 16u) {
                 const uint4 v = __ldg(src4 + ((i - lo) >> 4));
                 const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-                // One code path for every lane of the warp (the lanes that meet a match in this group must not drag the
-                // others through a per-byte loop): `lit` = the bytes of the group that go out as literals, `tk` = where a
-                // match token starts (16: nowhere).  A second match in the same 16 bytes (records of a few bytes) is rare
-                // enough for the byte loop below.
-                uint32_t lit = hi - i >= 16u ? 0xFFFFu : ((1u << (hi - i)) - 1u);
-                if (skip_to > i) lit &= skip_to - i >= 16u ? 0u : ~((1u << (skip_to - i)) - 1u);
-                uint32_t tk = 16u, tlen = 0, tdist = 0;
-                bool again = false;
-                if (next_tok < i + 16u && next_tok < hi) {
-                    tk = next_tok - i;
-                    const uint32_t ld = s.tok_ld[t];
-                    tlen = ld & 0xFFFFu;
-                    tdist = (ld >> 16) ? (ld >> 16) : 32768u;
-                    const uint32_t tend = tk + tlen;  // first byte of the group behind the match (may be >= 16)
-                    lit &= ~((tend >= 16u ? 0xFFFFu : ((1u << tend) - 1u)) & ~((1u << tk) - 1u));
-                    skip_to = next_tok + tlen;
-                    ++t;
-                    next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
-                    if (next_tok < i + 16u) { again = true; lit &= (1u << (tend < 16u ? tend : 16u)) - 1u; }  // literals behind the first match: byte loop
-                }
+                const uint32_t c16 = cv.x & 0xFFFFu;
+                const uint32_t st16 = c16 & ~((c16 << 1) | carry);  // a token starts where the cover starts
+                carry = c16 >> 15;
+                const uint32_t lit = ~c16 & (hi - i >= 16u ? 0xFFFFu : ((1u << (hi - i)) - 1u));
                 // Four bytes at a time: the codes of two literals are joined in 32 bits (<= 15 bits each) before they enter
                 // the 64-bit accumulator, and a byte that a match covers simply contributes a code of length 0.  A match
                 // is at least 4 bytes long, so it covers the rest of the word it starts in: its token goes out behind the
-                // word's literals -- the only divergent step, once per record.
+                // word's literals -- the only divergent step.
 #pragma unroll
                 for (uint32_t kw = 0; kw < 4; ++kw) {
                     const uint32_t wd = wds[kw], l4 = lit >> (4u * kw);
@@ -603,7 +668,22 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                     acc |= (uint64_t)cB << accbits;
                     accbits += n2 + (e3 >> 16);
                     flush_acc(s, acc, accbits, wi);
-                    if ((tk >> 2) == kw) {
+                    const uint32_t s4 = (st16 >> (4u * kw)) & 0xFu;
+                    if (s4) {
+                        const uint32_t x = 4u * kw + (uint32_t)__ffs((int)s4) - 1u;  // the token's first byte, inside the group
+                        uint32_t tlen, tdist;
+                        if (i + x == next_tok) {  // a name-line match
+                            const uint32_t ld = s.tok_ld[t];
+                            tlen = ld & 0xFFFFu;
+                            tdist = (ld >> 16) ? (ld >> 16) : 32768u;
+                            ++t;
+                            next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
+                        } else {  // a run: its length is the length of the cover (<= 64 by construction)
+                            const uint64_t w = (uint64_t)__funnelshift_r(cv.x, cv.y, x) | ((uint64_t)__funnelshift_r(cv.y, cv.z, x) << 32);
+                            const uint64_t nz = ~w;
+                            tlen = nz ? (uint32_t)__ffsll((long long)nz) - 1u : 64u;
+                            tdist = 1u;
+                        }
                         const uint32_t lc = s.lcode[tlen - 3u], dc = dist_code(tdist);
                         const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
                         acc |= (uint64_t)((le & 0xFFFFu) | ((tlen - kLenBase[lc]) << (le >> 16))) << accbits;
@@ -614,32 +694,10 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                         flush_acc(s, acc, accbits, wi);
                     }
                 }
-                if (again) {  // the rest of the group, byte by byte
-#pragma unroll 1
-                    for (uint32_t k = tk + tlen; k < 16 && i + k < hi; ++k) {
-                        const uint32_t x = i + k;
-                        if (x < skip_to) continue;
-                        if (x == next_tok) {
-                            const uint32_t ld = s.tok_ld[t], len = ld & 0xFFFFu, dist = (ld >> 16) ? (ld >> 16) : 32768u;
-                            const uint32_t lc = s.lcode[len - 3u], dc = dist_code(dist);
-                            const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
-                            acc |= (uint64_t)((le & 0xFFFFu) | ((len - kLenBase[lc]) << (le >> 16))) << accbits;
-                            accbits += (le >> 16) + kLenExtra[lc];
-                            flush_acc(s, acc, accbits, wi);
-                            acc |= (uint64_t)((de & 0xFFFFu) | ((dist - kDistBase[dc]) << (de >> 16))) << accbits;
-                            accbits += (de >> 16) + kDistExtra[dc];
-                            flush_acc(s, acc, accbits, wi);
-                            skip_to = x + len;
-                            ++t;
-                            next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
-                        } else {
-                            const uint32_t e = s.cl[(wds[k >> 2] >> (8u * (k & 3u))) & 0xFFu];
-                            acc |= (uint64_t)(e & 0xFFFFu) << accbits;
-                            accbits += e >> 16;
-                            flush_acc(s, acc, accbits, wi);
-                        }
-                    }
-                }
+                cv.x = __funnelshift_r(cv.x, cv.y, 16);
+                cv.y = __funnelshift_r(cv.y, cv.z, 16);
+                cv.z = __funnelshift_r(cv.z, cv.w, 16);
+                cv.w >>= 16;
             }
             if (accbits) atomicOr(&s.out[wi], (uint32_t)acc);
             if (tid == 0) put_bits(s.out, kHeaderBits + total, eob & 0xFFFFu, eob >> 16);
@@ -746,7 +804,7 @@ cudaError_t iss_gz_init_device(void) {  // once per device
 uint32_t iss_gz_chunks(uint64_t n_in) { return (uint32_t)((n_in + kChunk - 1) / kChunk); }
 
 cudaError_t iss_gz_compress(const uint8_t *d_in, uint64_t n_in, uint64_t *d_status, uint8_t *d_out, uint32_t *d_work, int sm_count,
-                            cudaStream_t stream) {
+                            int reuse_code, cudaStream_t stream) {
     const uint32_t nc = iss_gz_chunks(n_in);
     cudaError_t e = cudaMemsetAsync(d_status, 0, (nc + 1ull) * sizeof(uint64_t), stream);  // nc = 0: total = 0
     if (e != cudaSuccess || nc == 0) return e;
@@ -755,8 +813,10 @@ cudaError_t iss_gz_compress(const uint8_t *d_in, uint64_t n_in, uint64_t *d_stat
     const uint64_t n_pieces = (n_in + kPiece - 1) / kPiece;
     const uint32_t piece_stride = (uint32_t)((n_pieces + 255) / 256);
     const uint32_t n_sampled = (uint32_t)((n_pieces + piece_stride - 1) / piece_stride);
-    iss_gz_hist_kernel<<<n_sampled < (uint32_t)sm_count ? n_sampled : (uint32_t)sm_count, 256, 0, stream>>>(d_in, n_in, piece_stride, d_work);
-    iss_gz_table_kernel<<<1, 256, 0, stream>>>(d_in, n_in, d_work);
+    if (!reuse_code) {  // else: the code a previous call left in d_work (the words behind kWorkZeroed survive the memset above)
+        iss_gz_hist_kernel<<<n_sampled < (uint32_t)sm_count ? n_sampled : (uint32_t)sm_count, 256, 0, stream>>>(d_in, n_in, piece_stride, d_work);
+        iss_gz_table_kernel<<<1, 256, 0, stream>>>(d_in, n_in, d_work);
+    }
     const uint32_t grid = nc < (uint32_t)(sm_count * 3) ? nc : (uint32_t)(sm_count * 3);
     iss_deflate_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(d_in, n_in, d_out, reinterpret_cast<unsigned long long *>(d_status), d_work, nc);
     return cudaGetLastError();

@@ -13,5 +13,7 @@ uint32_t iss_gz_chunks(uint64_t n_in);
 // d_in: 16-byte aligned, readable up to the next multiple of 16 bytes.  d_status: chunks + 1 u64 of scratch; after the
 // call d_status[chunks] = total bytes of the gzip stream (check ISS_GZ_FAILED).  d_out: the contiguous gzip stream
 // (capacity chunks * ISS_GZ_STRIDE is always enough).  d_work: ISS_GZ_WORK_WORDS u32.
+// reuse_code != 0: skip the sampling and the code construction and compress with the code that an earlier call with the same
+// d_work built (streams of one run are statistically alike; any complete code is valid for any input).
 cudaError_t iss_gz_compress(const uint8_t *d_in, uint64_t n_in, uint64_t *d_status, uint8_t *d_out, uint32_t *d_work, int sm_count,
-                            cudaStream_t stream);
+                            int reuse_code, cudaStream_t stream);

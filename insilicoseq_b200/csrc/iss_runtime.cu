@@ -68,7 +68,8 @@ struct Slot {
     DevSegment *h_segs = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
-    cudaEvent_t ev_gz = nullptr, ev_end = nullptr;  // ISS_TRACE only: after the compressor, after the queued copies
+    cudaEvent_t ev_gz = nullptr, ev_end = nullptr;  // after the compressor; ISS_TRACE only: after the queued copies
+    bool gz_code_ready[2] = {false, false};  // the slot's work areas hold the Huffman codes of this run's streams
     int state = 0;  // 0 free, 1 in flight, 2 handed to the consumer
     uint64_t nbytes = 0, n_pairs = 0, first_item = 0, batch_index = 0;
     // --store_mutations: device event list -> host text
@@ -129,6 +130,7 @@ struct iss_ctx {
     std::vector<Slot> slots;
     uint64_t next_launch = 0, next_return = 0;  // batch counters
     cudaEvent_t gen_done[2] = {nullptr, nullptr};  // end of the generate kernels of the last two launches (events of their slots)
+    cudaEvent_t gz_done[2] = {nullptr, nullptr};   // the same for their compressors
     bool trace = getenv("ISS_TRACE") != nullptr;
     int ring_alloc = ISS_HOSTMEM_NUMA;  // ISS_RING_ALLOC=pinned|numa|wc
     double gz_ratio[2] = {0.4, 0.4};            // compressed / plain bytes per stream: a first guess, then the last returned batch
@@ -151,7 +153,7 @@ int set_device(iss_ctx *c) {
 }
 
 void free_slots(iss_ctx *c) {
-    c->gen_done[0] = c->gen_done[1] = nullptr;  // they belong to the slots
+    c->gen_done[0] = c->gen_done[1] = c->gz_done[0] = c->gz_done[1] = nullptr;  // they belong to the slots
     for (auto &s : c->slots) {
         if (s.d_out[0]) cudaFree(s.d_out[0]);
         if (s.d_out[1]) cudaFree(s.d_out[1]);
@@ -343,11 +345,23 @@ int launch_batch(iss_ctx *c, uint32_t si) {
         CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     if (c->opts.compress) {
         s.gz_chunks = iss_gz_chunks(bytes);
+        // Batches are compressed in launch order, two at a time (as the generate kernels above): the host takes batches back
+        // in order, so a batch that the GPU finishes late -- it shared the machine with the five launched behind it --
+        // holds up the copy engine and then frees all the slots at once.  And a slot builds the Huffman codes of its two
+        // streams once per run, from its first batch: the batches of a run are statistically alike (same model, same
+        // names), any complete code is valid for any input, and the two single-CTA table kernels (72 us each) would
+        // otherwise sit in every batch's chain.
+        cudaEvent_t &prevz = c->gz_done[c->next_launch & 1u];
+        if (prevz) CU(cudaStreamWaitEvent(s.stream, prevz, 0));
+        uint32_t built = 0;
         for (int k = 0; k < 2; ++k) {
-            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_status[k], s.d_gz_out[k], s.d_gz_work[k], c->sm_count, s.stream));
+            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_status[k], s.d_gz_out[k], s.d_gz_work[k], c->sm_count, s.gz_code_ready[k] ? 1 : 0, s.stream));
+            built += s.gz_code_ready[k] ? 0u : 2u;
+            s.gz_code_ready[k] = bytes > 0;  // (an empty stream builds nothing)
             CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_status[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
         }
-        if (c->trace) CU(cudaEventRecord(s.ev_gz, s.stream));
+        CU(cudaEventRecord(s.ev_gz, s.stream));
+        prevz = s.ev_gz;
         // The host learns the compressed size only when the batch is done; queuing the D2H copy after that costs a host
         // round trip per batch, and a late small copy would also wait behind the other slots' copies in the copy
         // engine's queue.  Batches of one run compress alike (same model, same read length), so the copy is queued now
@@ -361,7 +375,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
                 c->stats.d2h_bytes += pre;
             }
         }
-        c->stats.kernel_launches += 6;  // histogram, code table and member kernels, per stream
+        c->stats.kernel_launches += 2 + built;  // member kernels, and histogram + code table where a code was built
     } else if (!c->opts.device_only) {
         CU(cudaMemcpyAsync(s.h_out[0], s.d_out[0], bytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
@@ -880,7 +894,8 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     c->opts = o;
     c->cur_item = 0; c->cur_off = 0;
     c->next_launch = 0; c->next_return = 0;
-    c->gen_done[0] = c->gen_done[1] = nullptr;
+    c->gen_done[0] = c->gen_done[1] = c->gz_done[0] = c->gz_done[1] = nullptr;
+    for (auto &s : c->slots) s.gz_code_ready[0] = s.gz_code_ready[1] = false;  // the model or the genome may have changed
     c->exhausted = (total == 0);
     if (total == 0) { c->active = true; return ISS_OK; }
     const uint64_t batch_pairs = std::min<uint64_t>(o.batch_pairs, total);
@@ -1198,7 +1213,7 @@ int iss_ctx_gzip(iss_ctx *c, const uint8_t *in, uint64_t n, uint8_t *out, uint64
         CU(cudaMalloc(&d_work, ISS_GZ_WORK_WORDS * sizeof(uint32_t)));
         CU(cudaMalloc(&d_status, (nc + 2) * sizeof(uint64_t)));
         if (n) CU(cudaMemcpy(d_in, in, n, cudaMemcpyHostToDevice));
-        CU(iss_gz_compress(d_in, n, d_status, d_out, d_work, c->sm_count, 0));
+        CU(iss_gz_compress(d_in, n, d_status, d_out, d_work, c->sm_count, 0, 0));
         CU(cudaMemcpy(&total, d_status + nc, sizeof total, cudaMemcpyDeviceToHost));
         if (ISS_GZ_FAILED(total)) return fail(ISS_E_STATE, "internal: gzip member placement timed out");
         if (total > cap) return fail(ISS_E_ARG, "output buffer too small");

@@ -359,6 +359,44 @@ def test_gpu_gzip_name_line_matches():
         assert len(plain) / len(z) > 2.95, len(plain) / len(z)
 
 
+def test_gpu_gzip_distance_one_runs():
+    """The second kind of LZ77 token of the GPU gzip: runs (>= 4 bytes equal to the byte in front of them, distance 1), which
+    is most of a binned-quality line.  Runs of every length around the thresholds (3, 4, 5, 63..66, 127..130, 258+), runs
+    that cross the 64-byte half, the 128-byte slice and the 64 KB member, runs that touch a name line on either side
+    ("\n\n\n\n\n@", a quality line ending in the run byte), a member that is one run, and the NovaSeq fixture, whose
+    quality lines must now cost well under a bit per base."""
+    import gzip
+
+    from insilicoseq_b200.engine import Engine
+
+    rng = np.random.RandomState(17)
+
+    def binned_fastq(n, L, name):
+        out = []
+        for i in range(n):
+            seq = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), L))
+            q = np.full(L, ord("F"), dtype=np.uint8)
+            q[rng.rand(L) < 0.06] = ord(":")
+            q[rng.rand(L) < 0.02] = ord(",")
+            out.append(b"@%s_%d_0/1\n%s\n+\n%s\n" % (name, i, seq, q.tobytes()))
+        return b"".join(out)
+
+    ladders = b"".join(bytes([97 + (k % 7)]) * k + b"|" for k in list(range(1, 12)) + [62, 63, 64, 65, 66, 126, 127, 128, 129, 130, 257, 258, 259, 600])
+    samples = [binned_fastq(4000, 151, b"nova"), binned_fastq(20000, 12, b"s"), ladders * 40, b"\0" * 200_001,
+               (b"ab" * 40 + b"c" * 50) * 3000, b"z" * 65535 + b"y" * 3 + b"z" * 70000, (b"\n\n\n\n\n\n@q_1/1\nAC\n+\nFFFFFFFFFF\n") * 9000,
+               bytes(rng.choice(np.frombuffer(b"AAAAAAAB", dtype=np.uint8), 300_000)), b"Q" * 65536 * 3,
+               (b"@r_%d/1\n" % 7) + b"F" * 500 + b"\n"]
+    with Engine(0) as e:
+        for data in samples:
+            z = e.gzip(data)
+            assert gzip.decompress(z) == data, len(data)
+        assert len(samples[0]) / len(e.gzip(samples[0])) > 3.6
+        fq = open(os.path.join(fixtures.GOLDEN, "novaseq_single", "R1.fastq"), "rb").read() * 30
+        z = e.gzip(fq)
+        assert gzip.decompress(z) == fq
+        assert len(fq) / len(z) > 3.5, len(fq) / len(z)  # 3.15 without the runs (host prototype: 3.94 with them)
+
+
 def test_compressed_batches_decompress_to_the_plain_output():
     import gzip
 
