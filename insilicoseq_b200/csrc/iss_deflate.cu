@@ -85,6 +85,13 @@ __device__ __forceinline__ uint64_t runs4(uint64_t m) {
     const uint64_t c = b | (b << 1);
     return c | (c << 2);
 }
+// the same for runs of at least 8
+__device__ __forceinline__ uint64_t runs8(uint64_t m) {
+    const uint64_t a = m & (m >> 1), b = a & (a >> 2), c = b & (b >> 4);  // c: eight ones start here
+    uint64_t d = c | (c << 1);
+    d |= d << 2;
+    return d | (d << 4);
+}
 // bits [a, b) of a 128-bit mask held in four words (a <= b <= 128)
 __device__ __forceinline__ void set_range128(uint32_t m[4], uint32_t a, uint32_t b) {
 #pragma unroll
@@ -133,6 +140,7 @@ struct GzCode {
     uint32_t cl[288];   // bit-reversed canonical code | length << 16: literals 0..255, 256 = end of block, 257..285 = match lengths
     uint32_t dl[32];    // the same for the 30 distance codes
     uint32_t hdr[44];   // the kHeaderBits bits of the block header (lengths included)
+    uint32_t rmin;      // shortest run that becomes a token: 4 where runs are most of the text (binned qualities), else 8
 };
 constexpr uint32_t kWorkHist = 0;     // word offsets inside the caller's work area (ISS_GZ_WORK_WORDS u32)
 constexpr uint32_t kWorkTicket = 260;  // next chunk to hand out
@@ -154,6 +162,7 @@ struct TableSmem {
     uint32_t tokf[64];    // sample statistics: [0..28] match-length codes, [32..61] distance codes
     int32_t start[256];   // sample planning: record start inside each 64-byte slice of the first 16 KB (-1: none)
     uint32_t sub[256];    // sample statistics: bytes of each value that the sample's runs cover (they are not literals)
+    uint32_t cov8;        // bytes of the sample in runs of 8 and more
 };
 
 __device__ __forceinline__ void put_bits(uint32_t *out, uint32_t pos, uint32_t v, uint32_t nbits) {
@@ -345,6 +354,7 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__rest
     if (tid < 44) s.out[tid] = 0;
     if (tid < 64) s.tokf[tid] = 0;
     s.sub[tid] = 0;
+    if (tid == 0) s.cov8 = 0;
     __syncthreads();
     const uint32_t f0 = work[kWorkHist + tid];
     atomicAdd(&s.total, f0);
@@ -371,13 +381,19 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__rest
             }
         }
     }
-    {   // the distance-1 runs of the same window (the member kernel's rule, name lines not taken out: statistics only)
+    {   // the distance-1 runs of the same window (the member kernel's rule, name lines not taken out: statistics only).
+        // Runs of 4..7 are worth a token only where runs are what the text is made of: in random bases and broad quality
+        // distributions they save a few bits per record and cost the packing loop a divergent step per warp and word.
         uint64_t m = 0;
         for (uint32_t j = 0; j < 64u; ++j) {
             const uint32_t x = tid * 64u + j;
             if (x >= 1u && x < ns && in[x] == in[x - 1u]) m |= 1ull << j;
         }
-        const uint64_t e = runs4(m);
+        atomicAdd(&s.cov8, (uint32_t)__popcll((long long)runs8(m)));
+        __syncthreads();
+        const uint32_t rmin = s.cov8 * 8u > ns ? 4u : 8u;
+        if (tid == 0) reinterpret_cast<GzCode *>(work + kWorkCode)->rmin = rmin;
+        const uint64_t e = rmin == 4u ? runs4(m) : runs8(m);
         uint64_t st = e & ~(e << 1);
         while (st) {
             const uint32_t x = (uint32_t)__ffsll((long long)st) - 1u;
@@ -473,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
     }
     if (tid < 32) s.dl[tid] = code->dl[tid];
     if (tid < 256) s.lcode[tid] = (uint8_t)len_code(tid + 3u);
+    const bool wide_runs = code->rmin <= 4u;
     for (;;) {
         __syncthreads();  // previous chunk fully written out; tables loaded
         // A ticket is taken when its chunk is started, never ahead: the look-back of the chunks behind it waits for this
@@ -592,12 +609,13 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             const uint32_t r1 = sm.y & vm[1] & ~(nc[1] | (nc[1] << 1) | (nc[0] >> 31) | (nc[1] >> 1) | (nc[2] << 31));
             const uint32_t r2 = sm.z & vm[2] & ~(nc[2] | (nc[2] << 1) | (nc[1] >> 31) | (nc[2] >> 1) | (nc[3] << 31));
             const uint32_t r3 = sm.w & vm[3] & ~(nc[3] | (nc[3] << 1) | (nc[2] >> 31) | (nc[3] >> 1));
-            const uint64_t e0 = runs4((uint64_t)r0 | ((uint64_t)r1 << 32));
+            const uint64_t m0 = (uint64_t)r0 | ((uint64_t)r1 << 32);
+            const uint64_t e0 = wide_runs ? runs4(m0) : runs8(m0);
             uint64_t m1 = (uint64_t)r2 | ((uint64_t)r3 << 32);
             if (e0 >> 63) m1 &= ~1ull;  // the halves are planned apart: no run of the second one right behind a run of the first
-            const uint64_t e1 = runs4(m1);
+            const uint64_t e1 = wide_runs ? runs4(m1) : runs8(m1);
 #pragma unroll 1
-            for (uint32_t h = 0; h < 2; ++h) {
+            for (uint32_t h = 0; h < 2 && (e0 | e1); ++h) {
                 const uint64_t e = h ? e1 : e0;
                 uint64_t st = e & ~(e << 1);  // run starts
                 while (st) {

@@ -390,7 +390,7 @@ def test_gpu_gzip_distance_one_runs():
         for data in samples:
             z = e.gzip(data)
             assert gzip.decompress(z) == data, len(data)
-        assert len(samples[0]) / len(e.gzip(samples[0])) > 3.6
+        assert len(samples[0]) / len(e.gzip(samples[0])) > 3.4  # 2.9 with literals and name lines only
         fq = open(os.path.join(fixtures.GOLDEN, "novaseq_single", "R1.fastq"), "rb").read() * 30
         z = e.gzip(fq)
         assert gzip.decompress(z) == fq
