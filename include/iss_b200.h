@@ -68,6 +68,27 @@ typedef struct {
  * the reference.  Characters outside util.rev_comp's dictionary (iss/util.py:57-88) -> ISS_E_CHAR. */
 int iss_ctx_set_genome(iss_ctx *ctx, const iss_record *records, uint32_t n_records);
 
+/* FASTA text in, white space and title lines taken out on the device: replaces Bio.SeqIO.parse(genome_file, "fasta") and
+ * str(record.seq) per record (iss/generator.py:270,468-490; iss/app.py:74-76).  iss_fasta_index is host-only (a memchr
+ * scan for '>' at line starts; text in front of the first title is ignored, as Bio does); the records it returns are
+ * malloc'ed and released with iss_fasta_free.  iss_ctx_set_genome_fasta copies the text to the GPU as it is, fills in
+ * seq_len (bases per record = body bytes that are not white space) and builds the same genome blob as
+ * iss_ctx_set_genome called with (id, sequence) pairs.  `text` must stay readable for the duration of the call only. */
+typedef struct iss_fasta_rec {
+    uint64_t gt_pos;     /* position of the title line's '>' */
+    uint64_t title_off;  /* the title without '>' and without trailing white space: record.description */
+    uint64_t title_len;
+    uint64_t id_off;     /* its first white-space delimited token: record.id */
+    uint32_t id_len;
+    uint32_t reserved;
+    uint64_t body_off;   /* the lines between this title and the next one (or the end of the text) */
+    uint64_t body_len;
+    uint64_t seq_len;    /* out: set by iss_ctx_set_genome_fasta */
+} iss_fasta_rec;
+int iss_fasta_index(const char *text, uint64_t n, iss_fasta_rec **records, uint32_t *n_records);
+void iss_fasta_free(iss_fasta_rec *records);
+int iss_ctx_set_genome_fasta(iss_ctx *ctx, const char *text, uint64_t n, iss_fasta_rec *records, uint32_t n_records);
+
 /* ---- error model (replaces the pickled ErrorModel) ------------------------------------------ */
 /* Integer-threshold lowering of the model's f64 tables.  With w a 32-bit Philox word, u = w * 2^-32:
  *   searchsorted(cdf, u, 'left')  == #{j : w >  G[j]},  G[j] = min(floor(cdf[j] * 2^32), 2^32 - 1)

@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libiss_b200.so")
-SOURCES = ["iss_kernels.cu", "iss_deflate.cu", "iss_runtime.cu", "iss_hostmem.cu", "iss_io.cu", "iss_genome.cu"]
-HEADERS = ["iss_device.cuh", "iss_kernels.h", "iss_deflate.h", "iss_hostmem.h", "iss_genome.h", os.path.join("..", "..", "include", "iss_b200.h")]
+SOURCES = ["iss_kernels.cu", "iss_deflate.cu", "iss_runtime.cu", "iss_hostmem.cu", "iss_io.cu", "iss_genome.cu", "iss_fasta.cu"]
+HEADERS = ["iss_device.cuh", "iss_kernels.h", "iss_deflate.h", "iss_hostmem.h", "iss_genome.h", "iss_fasta.h", os.path.join("..", "..", "include", "iss_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

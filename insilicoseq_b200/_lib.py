@@ -18,6 +18,12 @@ class IssRecord(ctypes.Structure):
                 ("name_len", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class IssFastaRec(ctypes.Structure):
+    _fields_ = [("gt_pos", ctypes.c_uint64), ("title_off", ctypes.c_uint64), ("title_len", ctypes.c_uint64),
+                ("id_off", ctypes.c_uint64), ("id_len", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+                ("body_off", ctypes.c_uint64), ("body_len", ctypes.c_uint64), ("seq_len", ctypes.c_uint64)]
+
+
 class IssModel(ctypes.Structure):
     _fields_ = [
         ("read_length", ctypes.c_uint32), ("qual_mode", ctypes.c_uint32), ("n_insert", ctypes.c_uint32),
@@ -79,6 +85,11 @@ EXPORTS = {
     "iss_ctx_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "iss_ctx_destroy": (None, [ctypes.c_void_p]),
     "iss_ctx_set_genome": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssRecord), ctypes.c_uint32]),
+    "iss_fasta_index": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.POINTER(IssFastaRec)),
+                                       ctypes.POINTER(ctypes.c_uint32)]),
+    "iss_fasta_free": (None, [ctypes.POINTER(IssFastaRec)]),
+    "iss_ctx_set_genome_fasta": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(IssFastaRec),
+                                                ctypes.c_uint32]),
     "iss_ctx_set_model": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(IssModel)]),
     "iss_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "iss_comm_init_rank": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),

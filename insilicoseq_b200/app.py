@@ -48,7 +48,10 @@ def generate_reads(args):
     stop = threading.Event()  # set on Ctrl-C or when a device thread fails: workers finish their current chunk and return
     in_place = not args.compress  # plain FASTQ: chunk sizes are closed-form, the GPUs write the final files at their offsets
     try:
-        records = list(fasta.parse(genome_file))
+        # the genome file goes to GPU 0 as text: the host finds the title lines, the device takes the white space out
+        # and packs the bases (Engine.load_fasta) -- no per-record Python objects around the sequences
+        engines.append(Engine(0))
+        records = engines[0].load_fasta(genome_file)
         n_read_pairs = n_reads // 2
         chunk_size = -((n_read_pairs) // -args.cpus)
         logger.debug("Chunk size: %s" % chunk_size)
@@ -61,8 +64,7 @@ def generate_reads(args):
         n_gpus = args.gpus if args.gpus else n_dev
         n_gpus = max(1, min(n_gpus, n_dev, max(len(jobs), 1)))
         logger.info("Using %s GPU(s) for read generation" % n_gpus)
-        engines = [Engine(d) for d in range(n_gpus)]
-        register_records(engines[0], records)
+        engines.extend(Engine(d) for d in range(1, n_gpus))
         engines[0].set_model(error_model)
         if n_gpus > 1:  # one NCCL broadcast of the packed genome + model tables, then no communication
             Engine.comm_init_all(engines)

@@ -85,13 +85,6 @@ __device__ __forceinline__ uint64_t runs4(uint64_t m) {
     const uint64_t c = b | (b << 1);
     return c | (c << 2);
 }
-// the same for runs of at least 8
-__device__ __forceinline__ uint64_t runs8(uint64_t m) {
-    const uint64_t a = m & (m >> 1), b = a & (a >> 2), c = b & (b >> 4);  // c: eight ones start here
-    uint64_t d = c | (c << 1);
-    d |= d << 2;
-    return d | (d << 4);
-}
 // bits [a, b) of a 128-bit mask held in four words (a <= b <= 128)
 __device__ __forceinline__ void set_range128(uint32_t m[4], uint32_t a, uint32_t b) {
 #pragma unroll
@@ -140,7 +133,7 @@ struct GzCode {
     uint32_t cl[288];   // bit-reversed canonical code | length << 16: literals 0..255, 256 = end of block, 257..285 = match lengths
     uint32_t dl[32];    // the same for the 30 distance codes
     uint32_t hdr[44];   // the kHeaderBits bits of the block header (lengths included)
-    uint32_t rmin;      // shortest run that becomes a token: 4 where runs are most of the text (binned qualities), else 8
+    uint32_t rmin;      // shortest distance-1 run that becomes a token: 4, or 0 = none (the sample says they would not pay)
 };
 constexpr uint32_t kWorkHist = 0;     // word offsets inside the caller's work area (ISS_GZ_WORK_WORDS u32)
 constexpr uint32_t kWorkTicket = 260;  // next chunk to hand out
@@ -162,7 +155,9 @@ struct TableSmem {
     uint32_t tokf[64];    // sample statistics: [0..28] match-length codes, [32..61] distance codes
     int32_t start[256];   // sample planning: record start inside each 64-byte slice of the first 16 KB (-1: none)
     uint32_t sub[256];    // sample statistics: bytes of each value that the sample's runs cover (they are not literals)
-    uint32_t cov8;        // bytes of the sample in runs of 8 and more
+    int32_t gain;         // bits the sample's runs would save as tokens, at ~ -log2 p bits per literal and 10 per token
+    uint32_t wbits;       // sum over the byte values of count * ~ -log2 p
+    uint8_t lg[256];      // ~ -log2 p of each byte value, 1..15
 };
 
 __device__ __forceinline__ void put_bits(uint32_t *out, uint32_t pos, uint32_t v, uint32_t nbits) {
@@ -354,7 +349,7 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__rest
     if (tid < 44) s.out[tid] = 0;
     if (tid < 64) s.tokf[tid] = 0;
     s.sub[tid] = 0;
-    if (tid == 0) s.cov8 = 0;
+    if (tid == 0) { s.gain = 0; s.wbits = 0; }
     __syncthreads();
     const uint32_t f0 = work[kWorkHist + tid];
     atomicAdd(&s.total, f0);
@@ -382,19 +377,41 @@ __global__ void __launch_bounds__(256) iss_gz_table_kernel(const uint8_t *__rest
         }
     }
     {   // the distance-1 runs of the same window (the member kernel's rule, name lines not taken out: statistics only).
-        // Runs of 4..7 are worth a token only where runs are what the text is made of: in random bases and broad quality
-        // distributions they save a few bits per record and cost the packing loop a divergent step per warp and word.
+        // Do they pay?  A literal of value c costs about -log2 p(c) bits, a run token about 10: broad quality distributions
+        // (MiSeq) have many short runs of symbols that cost 1-2 bits anyway -- tokens would save ~ 1 % of the bits and
+        // make the packing loop diverge at every other word -- while binned qualities (NovaSeq, NextSeq, HiSeq X) are
+        // made of long runs and shrink by a fifth.  Runs become tokens when the estimate exceeds 1/64 of the bits.
         uint64_t m = 0;
         for (uint32_t j = 0; j < 64u; ++j) {
             const uint32_t x = tid * 64u + j;
             if (x >= 1u && x < ns && in[x] == in[x - 1u]) m |= 1ull << j;
         }
-        atomicAdd(&s.cov8, (uint32_t)__popcll((long long)runs8(m)));
+        __syncthreads();  // s.total complete
+        {
+            const uint32_t q = s.total / (f0 ? f0 : 1u);
+            const uint32_t lg = q > 1u ? 31u - (uint32_t)__clz((int)q) : 1u;
+            s.lg[tid] = (uint8_t)(lg > 15u ? 15u : lg);
+            atomicAdd(&s.wbits, f0 * s.lg[tid]);
+        }
         __syncthreads();
-        const uint32_t rmin = s.cov8 * 8u > ns ? 4u : 8u;
-        if (tid == 0) reinterpret_cast<GzCode *>(work + kWorkCode)->rmin = rmin;
-        const uint64_t e = rmin == 4u ? runs4(m) : runs8(m);
-        uint64_t st = e & ~(e << 1);
+        const uint64_t e = runs4(m);
+        {
+            uint64_t st = e & ~(e << 1);
+            int32_t g = 0;
+            while (st) {
+                const uint32_t x = (uint32_t)__ffsll((long long)st) - 1u;
+                st &= st - 1ull;
+                const uint64_t nz = ~(e >> x);
+                const uint32_t r = nz ? (uint32_t)__ffsll((long long)nz) - 1u : 64u;
+                g += (int32_t)(r * s.lg[in[tid * 64u + x]]) - 10;
+            }
+            if (g) atomicAdd(&s.gain, g);
+        }
+        __syncthreads();
+        // gain / (bits of the window) > 1/64, the window's bits being ns * wbits / total
+        const bool run_tokens = s.gain > 0 && (uint64_t)s.gain * 64ull * s.total > (uint64_t)ns * s.wbits;
+        if (tid == 0) reinterpret_cast<GzCode *>(work + kWorkCode)->rmin = run_tokens ? 4u : 0u;
+        uint64_t st = run_tokens ? e & ~(e << 1) : 0ull;
         while (st) {
             const uint32_t x = (uint32_t)__ffsll((long long)st) - 1u;
             st &= st - 1ull;
@@ -489,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
     }
     if (tid < 32) s.dl[tid] = code->dl[tid];
     if (tid < 256) s.lcode[tid] = (uint8_t)len_code(tid + 3u);
-    const bool wide_runs = code->rmin <= 4u;
+    const bool run_tokens = code->rmin != 0u;
     for (;;) {
         __syncthreads();  // previous chunk fully written out; tables loaded
         // A ticket is taken when its chunk is started, never ahead: the look-back of the chunks behind it waits for this
@@ -532,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                 // record starts, from registers and without a branch for all but the starts themselves: byte j of b1 / b2 /
                 // b3 is the byte 1 / 2 / 3 places in front of byte j of wd; a start is '@' behind '\n' but not behind "\n+\n"
                 const uint32_t b1 = __funnelshift_l(prev_word, wd, 8), b2 = __funnelshift_l(prev_word, wd, 16), b3 = __funnelshift_l(prev_word, wd, 24);
-                same32 |= byte_flags4(zero_bytes(wd ^ b1)) << (4u * k);  // runs: byte == the byte in front of it
+                if (run_tokens) same32 |= byte_flags4(zero_bytes(wd ^ b1)) << (4u * k);  // runs: byte == the byte in front of it
                 uint32_t starts = zero_bytes(wd ^ 0x40404040u) & zero_bytes(b1 ^ 0x0A0A0A0Au) & ~(zero_bytes(b2 ^ 0x2B2B2B2Bu) & zero_bytes(b3 ^ 0x0A0A0A0Au));
                 while (starts) {  // once per record
                     const uint32_t x = i + 4u * k + ((uint32_t)(__ffs((int)starts) - 1) >> 3);
@@ -609,11 +626,10 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
             const uint32_t r1 = sm.y & vm[1] & ~(nc[1] | (nc[1] << 1) | (nc[0] >> 31) | (nc[1] >> 1) | (nc[2] << 31));
             const uint32_t r2 = sm.z & vm[2] & ~(nc[2] | (nc[2] << 1) | (nc[1] >> 31) | (nc[2] >> 1) | (nc[3] << 31));
             const uint32_t r3 = sm.w & vm[3] & ~(nc[3] | (nc[3] << 1) | (nc[2] >> 31) | (nc[3] >> 1));
-            const uint64_t m0 = (uint64_t)r0 | ((uint64_t)r1 << 32);
-            const uint64_t e0 = wide_runs ? runs4(m0) : runs8(m0);
+            const uint64_t e0 = run_tokens ? runs4((uint64_t)r0 | ((uint64_t)r1 << 32)) : 0ull;
             uint64_t m1 = (uint64_t)r2 | ((uint64_t)r3 << 32);
             if (e0 >> 63) m1 &= ~1ull;  // the halves are planned apart: no run of the second one right behind a run of the first
-            const uint64_t e1 = wide_runs ? runs4(m1) : runs8(m1);
+            const uint64_t e1 = run_tokens ? runs4(m1) : 0ull;
 #pragma unroll 1
             for (uint32_t h = 0; h < 2 && (e0 | e1); ++h) {
                 const uint64_t e = h ? e1 : e0;
@@ -697,9 +713,12 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                             ++t;
                             next_tok = t < t_end ? s.tok_pos[t] : 0xFFFFFFFFu;
                         } else {  // a run: its length is the length of the cover (<= 64 by construction)
-                            const uint64_t w = (uint64_t)__funnelshift_r(cv.x, cv.y, x) | ((uint64_t)__funnelshift_r(cv.y, cv.z, x) << 32);
-                            const uint64_t nz = ~w;
-                            tlen = nz ? (uint32_t)__ffsll((long long)nz) - 1u : 64u;
+                            const uint32_t nz = ~__funnelshift_r(cv.x, cv.y, x);
+                            if (nz) tlen = (uint32_t)__ffs((int)nz) - 1u;
+                            else {
+                                const uint32_t nz2 = ~__funnelshift_r(cv.y, cv.z, x);
+                                tlen = nz2 ? 31u + (uint32_t)__ffs((int)nz2) : 64u;
+                            }
                             tdist = 1u;
                         }
                         const uint32_t lc = s.lcode[tlen - 3u], dc = dist_code(tdist);

@@ -17,12 +17,14 @@
 
 #include <algorithm>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/iss_b200.h"
 #include "iss_device.cuh"
 #include "iss_kernels.h"
 #include "iss_deflate.h"
+#include "iss_fasta.h"
 #include "iss_genome.h"
 #include "iss_hostmem.h"
 
@@ -505,23 +507,32 @@ void iss_ctx_destroy(iss_ctx *c) {
     delete c;
 }
 
-int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
-    if (!c || (!records && n)) return fail(ISS_E_ARG, "null argument");
-    if (int rc = set_device(c)) return rc;
-    if (c->active) return fail(ISS_E_STATE, "generation in progress");
-    NvtxRange nvtx("iss:set_genome");
-    // 1. the records' bytes to a staging buffer in HBM (16-byte aligned starts); classification and packing happen there
+// What a genome front end provides: the records' lengths and names, a way to put record r's ASCII at
+// d_stage + st[r].stage_off (queued on stream 0), and the character at a position (for the error message).
+struct GenomeSource {
+    uint32_t n = 0;
+    std::vector<uint64_t> len;
+    std::vector<const char *> name;
+    std::vector<uint32_t> name_len;
+    std::function<int(uint8_t *, const std::vector<IssStagedRecord> &)> fill;
+    std::function<unsigned(uint32_t, uint64_t)> char_at;
+    uint64_t h2d_bytes = 0;
+};
+
+// Staging buffer in HBM (16-byte aligned record starts) -> classification -> blob layout -> 2-bit / byte packing, all on
+// the device; the host builds the header, the record table and the names.
+static int set_genome_common(iss_ctx *c, const GenomeSource &src) {
+    const uint32_t n = src.n;
     std::vector<IssStagedRecord> st(n);
     std::vector<uint64_t> unit_begin(n + 1, 0);
     uint64_t stage_bytes = 0, names_bytes = 0;
     for (uint32_t r = 0; r < n; ++r) {
-        if (!records[r].seq && records[r].len) return fail(ISS_E_ARG, "record with a null sequence");
         st[r].stage_off = stage_bytes;
-        st[r].len = records[r].len;
+        st[r].len = src.len[r];
         st[r].data_off = 0; st[r].enc = 0; st[r].pad = 0;
-        stage_bytes = align_up(stage_bytes + records[r].len, 16);
-        unit_begin[r + 1] = unit_begin[r] + (records[r].len + 15) / 16;
-        names_bytes += records[r].name_len;
+        stage_bytes = align_up(stage_bytes + src.len[r], 16);
+        unit_begin[r + 1] = unit_begin[r] + (src.len[r] + 15) / 16;
+        names_bytes += src.name_len[r];
     }
     const uint64_t n_units = unit_begin[n];
     uint8_t *d_stage = nullptr;
@@ -540,9 +551,8 @@ int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
     uint64_t total = 0;
     const int rc = [&]() -> int {
         CU(cudaMalloc(&d_stage, stage_bytes + 32));
-        CU(cudaMemsetAsync(d_stage + (stage_bytes & ~(uint64_t)15), 0, 32, 0));
-        for (uint32_t r = 0; r < n; ++r)
-            if (records[r].len) CU(cudaMemcpyAsync(d_stage + st[r].stage_off, records[r].seq, records[r].len, cudaMemcpyHostToDevice, 0));
+        CU(cudaMemsetAsync(d_stage, 0, stage_bytes + 32, 0));  // the pads between records and behind the last one read as 0
+        if (int frc = src.fill(d_stage, st)) return frc;
         CU(cudaMalloc(&d_recs, sizeof(IssStagedRecord) * std::max<uint32_t>(n, 1)));
         CU(cudaMalloc(&d_units, sizeof(uint64_t) * (n + 1)));
         CU(cudaMalloc(&d_flags, sizeof(uint32_t) * std::max<uint32_t>(n, 1)));
@@ -551,7 +561,7 @@ int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
         CU(cudaMemsetAsync(d_bad, 0xFF, sizeof(unsigned long long) * std::max<uint32_t>(n, 1), 0));
         if (n) CU(cudaMemcpyAsync(d_recs, st.data(), sizeof(IssStagedRecord) * n, cudaMemcpyHostToDevice, 0));
         CU(cudaMemcpyAsync(d_units, unit_begin.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, 0));
-        // 2. classify on the device
+        // classify on the device
         CU(iss_genome_classify(d_stage, d_recs, d_units, n, n_units, d_flags, d_bad, c->sm_count, 0));
         std::vector<uint32_t> flags(n);
         std::vector<unsigned long long> bad(n);
@@ -563,22 +573,22 @@ int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
             if (bad[r] != ~0ull) {
                 char buf[160];
                 snprintf(buf, sizeof buf, "record %u: character 0x%02x at position %llu is outside the reference's alphabet", r,
-                         (unsigned)records[r].seq[bad[r]], bad[r]);
+                         src.char_at(r, bad[r]), bad[r]);
                 return fail(ISS_E_CHAR, buf);
             }
-        // 3. layout of the blob
+        // layout of the blob
         uint64_t packed_bases = 64, ascii_bytes = 64, name_off = 0;
         std::vector<DevRecord> dr(n);
         for (uint32_t r = 0; r < n; ++r) {
             const bool pure = !(flags[r] & 1u);
-            dr[r].len = records[r].len;
+            dr[r].len = src.len[r];
             dr[r].enc = pure ? ISS_ENC_2BIT : ISS_ENC_ASCII;
             dr[r].name_off = (uint32_t)name_off;
-            dr[r].name_len = records[r].name_len;
+            dr[r].name_len = src.name_len[r];
             dr[r].pad = 0;
-            name_off += records[r].name_len;
-            if (pure) { dr[r].data_off = packed_bases; packed_bases = align_up(packed_bases + records[r].len, 64); }
-            else { dr[r].data_off = ascii_bytes; ascii_bytes = align_up(ascii_bytes + records[r].len, 16); }
+            name_off += src.name_len[r];
+            if (pure) { dr[r].data_off = packed_bases; packed_bases = align_up(packed_bases + src.len[r], 64); }
+            else { dr[r].data_off = ascii_bytes; ascii_bytes = align_up(ascii_bytes + src.len[r], 16); }
             st[r].data_off = dr[r].data_off;
             st[r].enc = dr[r].enc;
         }
@@ -597,12 +607,12 @@ int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
         std::vector<uint8_t> head(gh.packed_off, 0);  // header + record table + names: the only part built on the host
         memcpy(head.data(), &gh, sizeof gh);
         if (n) memcpy(head.data() + gh.recs_off, dr.data(), sizeof(DevRecord) * (size_t)n);
-        for (uint32_t r = 0; r < n; ++r) memcpy(head.data() + gh.names_off + dr[r].name_off, records[r].name, records[r].name_len);
+        for (uint32_t r = 0; r < n; ++r) memcpy(head.data() + gh.names_off + dr[r].name_off, src.name[r], src.name_len[r]);
         CU(cudaMalloc(&d_blob, off));
         CU(cudaMemsetAsync(d_blob, 0, off, 0));
         CU(cudaMemcpyAsync(d_blob, head.data(), head.size(), cudaMemcpyHostToDevice, 0));
         if (n) CU(cudaMemcpyAsync(d_recs, st.data(), sizeof(IssStagedRecord) * n, cudaMemcpyHostToDevice, 0));
-        // 4. pack on the device
+        // pack on the device
         CU(iss_genome_pack(d_stage, d_recs, d_units, n, n_units, reinterpret_cast<uint32_t *>(d_blob + gh.packed_off), d_blob + gh.ascii_off,
                            c->sm_count, 0));
         CU(cudaStreamSynchronize(0));
@@ -616,8 +626,114 @@ int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
     if (c->d_genome) cudaFree(c->d_genome);
     c->d_genome = d_blob;
     c->genome_bytes = total;
-    c->stats.h2d_bytes += stage_bytes;
+    c->stats.h2d_bytes += src.h2d_bytes;
     return rebuild_views(c);
+}
+
+int iss_ctx_set_genome(iss_ctx *c, const iss_record *records, uint32_t n) {
+    if (!c || (!records && n)) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    if (c->active) return fail(ISS_E_STATE, "generation in progress");
+    NvtxRange nvtx("iss:set_genome");
+    GenomeSource src;
+    src.n = n;
+    src.len.resize(n); src.name.resize(n); src.name_len.resize(n);
+    for (uint32_t r = 0; r < n; ++r) {
+        if (!records[r].seq && records[r].len) return fail(ISS_E_ARG, "record with a null sequence");
+        src.len[r] = records[r].len;
+        src.name[r] = records[r].name;
+        src.name_len[r] = records[r].name_len;
+        src.h2d_bytes += records[r].len;
+    }
+    src.fill = [&](uint8_t *d_stage, const std::vector<IssStagedRecord> &st) -> int {
+        for (uint32_t r = 0; r < n; ++r)
+            if (records[r].len) CU(cudaMemcpyAsync(d_stage + st[r].stage_off, records[r].seq, records[r].len, cudaMemcpyHostToDevice, 0));
+        return ISS_OK;
+    };
+    src.char_at = [&](uint32_t r, uint64_t pos) { return (unsigned)(uint8_t)records[r].seq[pos]; };
+    return set_genome_common(c, src);
+}
+
+// FASTA text -> genome, white space and title lines taken out on the device (iss_fasta.cu).  The host only finds the title
+// lines (iss_fasta_index); what the reference does per record in Python -- SeqIO.parse, str(record.seq) -- does not happen.
+int iss_ctx_set_genome_fasta(iss_ctx *c, const char *text, uint64_t n_text, iss_fasta_rec *recs, uint32_t n) {
+    if (!c || (!text && n_text) || (!recs && n)) return fail(ISS_E_ARG, "null argument");
+    if (int rc = set_device(c)) return rc;
+    if (c->active) return fail(ISS_E_STATE, "generation in progress");
+    NvtxRange nvtx("iss:set_genome_fasta");
+    for (uint32_t r = 0; r < n; ++r) {
+        const iss_fasta_rec &f = recs[r];
+        const bool ok = f.gt_pos < f.body_off && f.body_off <= n_text && f.body_len <= n_text - f.body_off && f.id_off >= f.gt_pos &&
+                        f.id_off <= f.body_off && f.id_len <= f.body_off - f.id_off && (r == 0 || f.gt_pos >= recs[r - 1].body_off + recs[r - 1].body_len);
+        if (!ok) return fail(ISS_E_ARG, "FASTA index does not describe the text (records must be in file order)");
+    }
+    const uint64_t padded = align_up(n_text + 1, 4096);  // whole 4 KB blocks, '\n' behind the text
+    const uint64_t nblk = padded / 4096;
+    uint8_t *d_text = nullptr;
+    uint32_t *d_cnt = nullptr;
+    uint64_t *d_pre = nullptr, *d_pos = nullptr, *d_rank = nullptr, *d_tab = nullptr;
+    auto cleanup = [&] {
+        if (d_text) cudaFree(d_text);
+        if (d_cnt) cudaFree(d_cnt);
+        if (d_pre) cudaFree(d_pre);
+        if (d_pos) cudaFree(d_pos);
+        if (d_rank) cudaFree(d_rank);
+        if (d_tab) cudaFree(d_tab);
+    };
+    GenomeSource src;
+    src.n = n;
+    src.len.resize(n); src.name.resize(n); src.name_len.resize(n);
+    src.h2d_bytes = n_text;
+    std::vector<uint64_t> rank0(n);
+    int rc = [&]() -> int {
+        CU(cudaMalloc(&d_text, padded));
+        CU(cudaMemsetAsync(d_text + (n_text & ~(uint64_t)15), '\n', padded - (n_text & ~(uint64_t)15), 0));
+        if (n_text) CU(cudaMemcpyAsync(d_text, text, n_text, cudaMemcpyHostToDevice, 0));
+        CU(cudaMalloc(&d_cnt, sizeof(uint32_t) * nblk));
+        CU(cudaMalloc(&d_pre, sizeof(uint64_t) * (nblk + 1)));
+        CU(cudaMalloc(&d_pos, sizeof(uint64_t) * 3 * std::max<uint32_t>(n, 1)));
+        CU(cudaMalloc(&d_rank, sizeof(uint64_t) * 2 * std::max<uint32_t>(n, 1)));
+        // positions: [0, n) '>' of each title, [n, 2n) body starts, [2n, 3n) body ends
+        std::vector<uint64_t> pos(3 * (size_t)std::max<uint32_t>(n, 1), 0);
+        for (uint32_t r = 0; r < n; ++r) { pos[r] = recs[r].gt_pos; pos[n + r] = recs[r].body_off; pos[2 * (size_t)n + r] = recs[r].body_off + recs[r].body_len; }
+        CU(cudaMemcpyAsync(d_pos, pos.data(), sizeof(uint64_t) * pos.size(), cudaMemcpyHostToDevice, 0));
+        CU(iss_fasta_blank(d_text, d_pos, d_pos + n, n, 0));                     // title lines (and what stands before the first) -> '\n'
+        CU(iss_fasta_count(d_text, nblk, d_cnt, 0));                            // bases per 4 KB block
+        CU(iss_fasta_scan(d_cnt, nblk, d_pre, 0));                              // -> bases before each block
+        CU(iss_fasta_ranks(d_text, d_pre, d_pos + n, 2 * n, d_rank, 0));        // bases before each body start / end
+        std::vector<uint64_t> rank(2 * (size_t)std::max<uint32_t>(n, 1), 0);
+        if (n) CU(cudaMemcpy(rank.data(), d_rank, sizeof(uint64_t) * 2 * n, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < n; ++r) {
+            rank0[r] = rank[r];
+            src.len[r] = recs[r].seq_len = rank[(size_t)n + r] - rank[r];
+            src.name[r] = text + recs[r].id_off;
+            src.name_len[r] = recs[r].id_len;
+        }
+        return ISS_OK;
+    }();
+    if (rc != ISS_OK) { cleanup(); return rc; }
+    src.fill = [&](uint8_t *d_stage, const std::vector<IssStagedRecord> &st) -> int {
+        // per record: bases before its body, and where its bases go
+        std::vector<uint64_t> tab(2 * (size_t)std::max<uint32_t>(n, 1), 0);
+        for (uint32_t r = 0; r < n; ++r) { tab[r] = rank0[r]; tab[(size_t)n + r] = st[r].stage_off; }
+        CU(cudaMalloc(&d_tab, sizeof(uint64_t) * tab.size()));
+        CU(cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint64_t) * tab.size(), cudaMemcpyHostToDevice, 0));
+        CU(iss_fasta_scatter(d_text, nblk, d_pre, d_pos + n, d_pos + 2 * (size_t)n, d_tab, d_tab + n, n, d_stage, 0));
+        CU(cudaStreamSynchronize(0));  // `tab` leaves scope
+        return ISS_OK;
+    };
+    src.char_at = [&](uint32_t r, uint64_t p) -> unsigned {  // walk the body on the host: only on the error path
+        uint64_t seen = 0;
+        for (uint64_t x = recs[r].body_off; x < recs[r].body_off + recs[r].body_len; ++x) {
+            const uint8_t b = (uint8_t)text[x];
+            if (b == 0x20 || (uint8_t)(b - 9u) < 5u) continue;
+            if (seen++ == p) return b;
+        }
+        return 0u;
+    };
+    rc = set_genome_common(c, src);
+    cleanup();
+    return rc;
 }
 
 int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {

@@ -101,6 +101,44 @@ class Engine(object):
         self.record_lengths = [len(b) for b, _ in keep]
         self._records = {}
 
+    def load_fasta(self, path):
+        """Genome file -> device, the text itself: the host finds the title lines (iss_fasta_index, a memchr scan), the
+        GPU blanks them, squeezes the white space out and packs the bases (iss_ctx_set_genome_fasta).  Returns the
+        records as fasta.Record objects (id, description, len()) whose .seq reads the mapped file only on demand, and
+        registers them like register_records does.  Replaces list(SeqIO.parse(genome_file, "fasta")) + the upload."""
+        import mmap
+
+        from . import fasta
+
+        with open(path, "rb") as fh:
+            try:
+                mm = mmap.mmap(fh.fileno(), 0, access=mmap.ACCESS_READ)
+            except ValueError:  # empty file
+                mm = None
+        if mm is None:
+            self.set_genome([])
+            self._records = {}
+            return []
+        text = np.frombuffer(mm, dtype=np.uint8)
+        recs_p = ctypes.POINTER(_lib.IssFastaRec)()
+        n = ctypes.c_uint32(0)
+        _lib.check(self._lib.iss_fasta_index(text.ctypes.data, len(text), ctypes.byref(recs_p), ctypes.byref(n)))
+        try:
+            _lib.check(self._lib.iss_ctx_set_genome_fasta(self._h, text.ctypes.data, len(text), recs_p, n.value))
+            records = []
+            for k in range(n.value):
+                f = recs_p[k]
+                title = bytes(mm[f.title_off:f.title_off + f.title_len]).decode("ascii", errors="replace")
+                rid = bytes(mm[f.id_off:f.id_off + f.id_len]).decode("ascii", errors="replace")
+                records.append(fasta.Record(fasta.TextSeq(mm, f.body_off, f.body_len, f.seq_len), id=rid, description=title))
+        finally:
+            self._lib.iss_fasta_free(recs_p)
+        self._fasta_map = (mm, text)  # keeps the mapping alive for the lazy .seq of the records
+        self.record_names = [r.id for r in records]
+        self.record_lengths = [len(r) for r in records]
+        self._records = {id(r): (k, r) for k, r in enumerate(records)}
+        return records
+
     def register_records(self, records):
         """Upload record objects (anything with .id and .seq) and remember each one's device index INSIDE the engine:
         caller-owned records are not modified, and the same record may be registered with several engines."""

@@ -25,6 +25,32 @@ class Record(object):
 _WS = b" \t\n\r\x0b\x0c"  # what bytes.split() treats as white space
 
 
+class TextSeq(object):
+    """The sequence of a record whose bases went from the FASTA text to the GPU without passing through Python
+    (Engine.load_fasta): len() is the base count the device reported; the bytes are cut out of the (memory-mapped)
+    text only if somebody asks for them."""
+
+    __slots__ = ("_buf", "_off", "_len", "_n")
+
+    def __init__(self, buf, off, length, n_bases):
+        self._buf, self._off, self._len, self._n = buf, off, length, n_bases
+
+    def __len__(self):
+        return self._n
+
+    def __bytes__(self):
+        return bytes(self._buf[self._off:self._off + self._len]).translate(None, _WS)
+
+    def __str__(self):
+        return bytes(self).decode("ascii")
+
+    def __eq__(self, other):
+        return bytes(self) == (other.encode("ascii") if isinstance(other, str) else bytes(other))
+
+    def __getitem__(self, key):
+        return bytes(self)[key]
+
+
 def parse(handle):
     """Yield Record objects from a path or an open text/binary handle.
 

@@ -359,6 +359,63 @@ def test_gpu_gzip_name_line_matches():
         assert len(plain) / len(z) > 2.95, len(plain) / len(z)
 
 
+def test_genome_file_as_text_matches_the_record_upload(tmp_path):
+    """Engine.load_fasta (iss_fasta_index + iss_ctx_set_genome_fasta: title lines found on the host, white space squeezed
+    out and bases packed on the GPU) against fasta.parse + register_records: same ids, lengths and -- the proof that the
+    device blob is the same -- the same reads.  The file has a preamble, wrapped and unwrapped lines, CRLF line ends, empty
+    lines, blanks inside lines, a lower-case / IUPAC record (kept as bytes on the device), records far smaller and larger
+    than the 4 KB blocks of the device scan, and a last line without a line end."""
+    from insilicoseq_b200 import engine as eng_mod
+    from insilicoseq_b200 import error_models, fasta
+
+    rng = np.random.RandomState(23)
+
+    def bases(n, alphabet=b"ACGT"):
+        return bytes(rng.choice(np.frombuffer(alphabet, dtype=np.uint8), n))
+
+    def wrap(seq, width, eol=b"\n"):
+        return eol.join(seq[i:i + width] for i in range(0, len(seq), width)) + eol
+
+    parts = [b"# a comment in front of the first title\n\n",
+             b">chr1 the first one\n" + wrap(bases(70001), 60),
+             b">small\n" + wrap(bases(400), 80),
+             b">crlf_rec windows line ends\r\n" + wrap(bases(9000), 70, b"\r\n"),
+             b">iupac lower case and N\n" + wrap(bases(5000, b"ACGTNacgtRYKM"), 61),
+             b">gaps\n" + wrap(bases(3000), 50).replace(b"\n", b" \n\n", 7),
+             b">oneline\n" + bases(20000) + b"\n",
+             b">tiny1\n" + bases(350) + b"\n>tiny2\n" + bases(333) + b"\n>tiny3\n" + bases(360) + b"\n",
+             b">last no line end\n" + bases(1234)]
+    path = tmp_path / "genome.fasta"
+    path.write_bytes(b"".join(parts))
+    model = error_models.KDErrorModel(fixtures.model_path("models/miseq_150.npz"))
+    with eng_mod.Engine(0) as a, eng_mod.Engine(0) as b:
+        recs_a = a.register_records(list(fasta.parse(str(path))))
+        recs_b = b.load_fasta(str(path))
+        assert [r.id for r in recs_b] == [r.id for r in recs_a]
+        assert [r.description for r in recs_b] == [r.description for r in recs_a]
+        assert [len(r) for r in recs_b] == [len(r) for r in recs_a] == b.record_lengths
+        assert all(bytes(rb.seq) == ra.seq for ra, rb in zip(recs_a, recs_b))
+        outs = []
+        for e, recs in ((a, recs_a), (b, recs_b)):
+            e.set_model(model)
+            work = [(e.record_index(r), 900) for r in recs]
+            items = eng_mod.worker_items(work, 1, 77, e.record_lengths, e.read_length)
+            outs.append([(bt.r1.tobytes(), bt.r2.tobytes()) for bt in e.generate(items, batch_pairs=2000)])
+        assert outs[0] == outs[1]
+        assert sum(len(x) for x, _ in outs[0]) > 9 * 900 * 300
+        # an empty file, and a file without a title line: no records
+        empty = tmp_path / "empty.fasta"
+        empty.write_bytes(b"")
+        assert b.load_fasta(str(empty)) == []
+        empty.write_bytes(b"ACGT\nACGT\n")
+        assert b.load_fasta(str(empty)) == []
+        # a character outside the reference's alphabet is reported with its record and position
+        bad = tmp_path / "bad.fasta"
+        bad.write_bytes(b">ok\nACGT\n>bad\nAC\nG!T\n")
+        with pytest.raises(RuntimeError, match="record 1: character 0x21 at position 3"):
+            b.load_fasta(str(bad))
+
+
 def test_gpu_gzip_distance_one_runs():
     """The second kind of LZ77 token of the GPU gzip: runs (>= 4 bytes equal to the byte in front of them, distance 1), which
     is most of a binned-quality line.  Runs of every length around the thresholds (3, 4, 5, 63..66, 127..130, 258+), runs
