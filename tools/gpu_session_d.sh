@@ -28,6 +28,7 @@ done
 summ $OUT/bench_cfg3_dev.json cfg3dev
 ( timeout 400 python bench.py --config 2 --pairs 20000000 --steps 3 --warmup 3 --no-cpu-baseline ) > $OUT/bench_cfg2_20M.json 2> $OUT/bench_cfg2_20M.err
 summ $OUT/bench_cfg2_20M.json cfg2_20M
+( timeout 300 python tools/fasta_load_bench.py 330 3000000 ) > $OUT/fasta_load.json 2> $OUT/fasta_load.err; tail -1 $OUT/fasta_load.json | tee -a $OUT/summary.txt
 ( timeout 200 python tools/profile_model.py MiSeq 1000000 ) > $OUT/legacy_run.log 2>&1; tail -3 $OUT/legacy_run.log | head -2 | tee -a $OUT/summary.txt
 ( timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"iss_gz|iss_deflate" -c 36 --csv --log-file $OUT/gzip_launches.csv python tools/gz_profile.py ) > $OUT/gz_profile.log 2>&1
 python - <<'PY' | tee -a $OUT/summary.txt
