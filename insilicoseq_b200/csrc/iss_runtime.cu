@@ -343,8 +343,6 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     CU(iss_launch_generate(p, grid, c->smem, s.stream));
     CU(cudaEventRecord(s.ev_k1, s.stream));
     prev2 = s.ev_k1;
-    if (c->mh.store_mutations)
-        CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     if (c->opts.compress) {
         s.gz_chunks = iss_gz_chunks(bytes);
         // Batches are compressed in launch order, two at a time (as the generate kernels above): the host takes batches back
@@ -360,10 +358,15 @@ int launch_batch(iss_ctx *c, uint32_t si) {
             CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_status[k], s.d_gz_out[k], s.d_gz_work[k], c->sm_count, s.gz_code_ready[k] ? 1 : 0, s.stream));
             built += s.gz_code_ready[k] ? 0u : 2u;
             s.gz_code_ready[k] = bytes > 0;  // (an empty stream builds nothing)
-            CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_status[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
         }
+        // The event of the chain is recorded behind the kernels and IN FRONT of every copy of this batch: a device-to-host
+        // copy, however small, queues in the one copy engine behind the previous batches' 27 MB copies -- with the 8-byte
+        // totals between the two compressors (and in front of the event) the second compressor and the batch two launches
+        // later each waited for a copy that had nothing to do with them (a bubble after every second batch in the trace).
         CU(cudaEventRecord(s.ev_gz, s.stream));
         prevz = s.ev_gz;
+        for (int k = 0; k < 2; ++k)
+            CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_status[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
         // The host learns the compressed size only when the batch is done; queuing the D2H copy after that costs a host
         // round trip per batch, and a late small copy would also wait behind the other slots' copies in the copy
         // engine's queue.  Batches of one run compress alike (same model, same read length), so the copy is queued now
@@ -383,6 +386,8 @@ int launch_batch(iss_ctx *c, uint32_t si) {
         CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
         c->stats.d2h_bytes += 2 * bytes;
     }
+    if (c->mh.store_mutations)  // (behind the kernels, like every copy of the batch: see the compressor's event above)
+        CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     CU(cudaEventRecord(s.ev_done, s.stream));
     if (c->trace) CU(cudaEventRecord(s.ev_end, s.stream));
     s.state = 1;
