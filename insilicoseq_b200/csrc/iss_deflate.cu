@@ -472,7 +472,7 @@ struct Smem {
     uint4 cov[kThreads];     // per slice, one bit per byte: first "equals the byte in front of it", then "covered by a match"
     uint16_t tok_off[kThreads + 1];  // matches that start before each slice
     uint8_t len8[288];
-    uint8_t lcode[256];      // match length - 3 -> length code 0..28
+    uint32_t ltok[256];      // match length - 3 -> the length part of its token: code | extra bits << code length, bit count << 24
 };
 
 extern __shared__ __align__(16) uint8_t iss_gz_smem[];
@@ -480,8 +480,8 @@ extern __shared__ __align__(16) uint8_t iss_gz_smem[];
 namespace {
 // bits of one match: length code + extra, distance code + extra
 __device__ __forceinline__ uint32_t match_bits(const Smem &s, uint32_t len, uint32_t dist) {
-    const uint32_t lc = s.lcode[len - 3u], dc = dist_code(dist);
-    return (s.cl[257u + lc] >> 16) + kLenExtra[lc] + (s.dl[dc] >> 16) + kDistExtra[dc];
+    const uint32_t dc = dist_code(dist);
+    return (s.ltok[len - 3u] >> 24) + (s.dl[dc] >> 16) + kDistExtra[dc];
 }
 __device__ __forceinline__ void flush_acc(Smem &s, uint64_t &acc, uint32_t &accbits, uint32_t &wi) {
     if (accbits >= 32u) {
@@ -505,7 +505,10 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
         s.len8[i] = (uint8_t)(e >> 16);
     }
     if (tid < 32) s.dl[tid] = code->dl[tid];
-    if (tid < 256) s.lcode[tid] = (uint8_t)len_code(tid + 3u);
+    if (tid < 256) {  // one shared-memory word per match length instead of two constant-bank loads with a per-lane index
+        const uint32_t len = tid + 3u, lc = len_code(len), e = code->cl[257u + lc];
+        s.ltok[tid] = (e & 0xFFFFu) | ((len - kLenBase[lc]) << (e >> 16)) | (((e >> 16) + kLenExtra[lc]) << 24);
+    }
     const bool run_tokens = code->rmin != 0u;
     for (;;) {
         __syncthreads();  // previous chunk fully written out; tables loaded
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                     const uint32_t s4 = (st16 >> (4u * kw)) & 0xFu;
                     if (s4) {
                         const uint32_t x = 4u * kw + (uint32_t)__ffs((int)s4) - 1u;  // the token's first byte, inside the group
-                        uint32_t tlen, tdist;
+                        uint32_t tlen, tdist = 1u;
                         if (i + x == next_tok) {  // a name-line match
                             const uint32_t ld = s.tok_ld[t];
                             tlen = ld & 0xFFFFu;
@@ -719,15 +722,20 @@ __global__ void __launch_bounds__(kThreads, 3) iss_deflate_kernel(const uint8_t 
                                 const uint32_t nz2 = ~__funnelshift_r(cv.y, cv.z, x);
                                 tlen = nz2 ? 31u + (uint32_t)__ffs((int)nz2) : 64u;
                             }
-                            tdist = 1u;
                         }
-                        const uint32_t lc = s.lcode[tlen - 3u], dc = dist_code(tdist);
-                        const uint32_t le = s.cl[257u + lc], de = s.dl[dc];
-                        acc |= (uint64_t)((le & 0xFFFFu) | ((tlen - kLenBase[lc]) << (le >> 16))) << accbits;
-                        accbits += (le >> 16) + kLenExtra[lc];
+                        const uint32_t lt = s.ltok[tlen - 3u];
+                        acc |= (uint64_t)(lt & 0xFFFFFFu) << accbits;
+                        accbits += lt >> 24;
                         flush_acc(s, acc, accbits, wi);
-                        acc |= (uint64_t)((de & 0xFFFFu) | ((tdist - kDistBase[dc]) << (de >> 16))) << accbits;
-                        accbits += (de >> 16) + kDistExtra[dc];
+                        if (tdist == 1u) {  // distance code 0, no extra bits
+                            const uint32_t de = s.dl[0];
+                            acc |= (uint64_t)(de & 0xFFFFu) << accbits;
+                            accbits += de >> 16;
+                        } else {
+                            const uint32_t dc = dist_code(tdist), de = s.dl[dc];
+                            acc |= (uint64_t)((de & 0xFFFFu) | ((tdist - kDistBase[dc]) << (de >> 16))) << accbits;
+                            accbits += (de >> 16) + kDistExtra[dc];
+                        }
                         flush_acc(s, acc, accbits, wi);
                     }
                 }
