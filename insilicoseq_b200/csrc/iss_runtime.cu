@@ -72,6 +72,7 @@ struct Slot {
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
     cudaEvent_t ev_gz = nullptr, ev_end = nullptr;  // after the compressor; ISS_TRACE only: after the queued copies
     bool gz_code_ready[2] = {false, false};  // the slot's work areas hold the Huffman codes of this run's streams
+    cudaStream_t zstream = nullptr;  // the slot's compressor kernels: a stream of the highest priority (see launch_batch)
     int state = 0;  // 0 free, 1 in flight, 2 handed to the consumer
     uint64_t nbytes = 0, n_pairs = 0, first_item = 0, batch_index = 0;
     // --store_mutations: device event list -> host text
@@ -133,6 +134,7 @@ struct iss_ctx {
     uint64_t next_launch = 0, next_return = 0;  // batch counters
     cudaEvent_t gen_done[2] = {nullptr, nullptr};  // end of the generate kernels of the last two launches (events of their slots)
     cudaEvent_t gz_done[2] = {nullptr, nullptr};   // the same for their compressors
+    cudaEvent_t copy_done = nullptr;               // end of the previous launch's device-to-host copies
     bool trace = getenv("ISS_TRACE") != nullptr;
     int ring_alloc = ISS_HOSTMEM_NUMA;  // ISS_RING_ALLOC=pinned|numa|wc
     double gz_ratio[2] = {0.4, 0.4};            // compressed / plain bytes per stream: a first guess, then the last returned batch
@@ -155,7 +157,7 @@ int set_device(iss_ctx *c) {
 }
 
 void free_slots(iss_ctx *c) {
-    c->gen_done[0] = c->gen_done[1] = c->gz_done[0] = c->gz_done[1] = nullptr;  // they belong to the slots
+    c->gen_done[0] = c->gen_done[1] = c->gz_done[0] = c->gz_done[1] = c->copy_done = nullptr;  // they belong to the slots
     for (auto &s : c->slots) {
         if (s.d_out[0]) cudaFree(s.d_out[0]);
         if (s.d_out[1]) cudaFree(s.d_out[1]);
@@ -175,6 +177,7 @@ void free_slots(iss_ctx *c) {
         if (s.d_evcount) cudaFree(s.d_evcount);
         if (s.h_evcount) cudaFreeHost(s.h_evcount);
         if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.zstream) cudaStreamDestroy(s.zstream);
         if (s.ev_k0) cudaEventDestroy(s.ev_k0);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -351,11 +354,14 @@ int launch_batch(iss_ctx *c, uint32_t si) {
         // streams once per run, from its first batch: the batches of a run are statistically alike (same model, same
         // names), any complete code is valid for any input, and the two single-CTA table kernels (72 us each) would
         // otherwise sit in every batch's chain.
+        // The compressor runs in a stream of the highest priority: its CTAs take the SMs that a generate kernel of a
+        // LATER batch frees before that kernel's own next CTAs do -- what the copy engine is waiting for goes first.
         cudaEvent_t &prevz = c->gz_done[c->next_launch & 1u];
-        if (prevz) CU(cudaStreamWaitEvent(s.stream, prevz, 0));
+        CU(cudaStreamWaitEvent(s.zstream, s.ev_k1, 0));
+        if (prevz) CU(cudaStreamWaitEvent(s.zstream, prevz, 0));
         uint32_t built = 0;
         for (int k = 0; k < 2; ++k) {
-            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_status[k], s.d_gz_out[k], s.d_gz_work[k], c->sm_count, s.gz_code_ready[k] ? 1 : 0, s.stream));
+            CU(iss_gz_compress(s.d_out[k], bytes, s.d_gz_status[k], s.d_gz_out[k], s.d_gz_work[k], c->sm_count, s.gz_code_ready[k] ? 1 : 0, s.zstream));
             built += s.gz_code_ready[k] ? 0u : 2u;
             s.gz_code_ready[k] = bytes > 0;  // (an empty stream builds nothing)
         }
@@ -363,8 +369,10 @@ int launch_batch(iss_ctx *c, uint32_t si) {
         // copy, however small, queues in the one copy engine behind the previous batches' 27 MB copies -- with the 8-byte
         // totals between the two compressors (and in front of the event) the second compressor and the batch two launches
         // later each waited for a copy that had nothing to do with them (a bubble after every second batch in the trace).
-        CU(cudaEventRecord(s.ev_gz, s.stream));
+        CU(cudaEventRecord(s.ev_gz, s.zstream));
         prevz = s.ev_gz;
+        CU(cudaStreamWaitEvent(s.stream, s.ev_gz, 0));
+        if (c->copy_done) CU(cudaStreamWaitEvent(s.stream, c->copy_done, 0));  // copies in launch order (see below)
         for (int k = 0; k < 2; ++k)
             CU(cudaMemcpyAsync(&s.h_gz_total[k], s.d_gz_status[k] + s.gz_chunks, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
         // The host learns the compressed size only when the batch is done; queuing the D2H copy after that costs a host
@@ -382,6 +390,9 @@ int launch_batch(iss_ctx *c, uint32_t si) {
         }
         c->stats.kernel_launches += 2 + built;  // member kernels, and histogram + code table where a code was built
     } else if (!c->opts.device_only) {
+        // The host takes the batches back in launch order, but the copy engine serves the streams in its own order: a
+        // later batch's copy that goes first makes the host wait for the earlier one and release the slots in a burst.
+        if (c->copy_done) CU(cudaStreamWaitEvent(s.stream, c->copy_done, 0));
         CU(cudaMemcpyAsync(s.h_out[0], s.d_out[0], bytes, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaMemcpyAsync(s.h_out[1], s.d_out[1], bytes, cudaMemcpyDeviceToHost, s.stream));
         c->stats.d2h_bytes += 2 * bytes;
@@ -389,6 +400,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     if (c->mh.store_mutations)  // (behind the kernels, like every copy of the batch: see the compressor's event above)
         CU(cudaMemcpyAsync(s.h_evcount, s.d_evcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     CU(cudaEventRecord(s.ev_done, s.stream));
+    c->copy_done = s.ev_done;
     if (c->trace) CU(cudaEventRecord(s.ev_end, s.stream));
     s.state = 1;
     s.nbytes = bytes;
@@ -1015,7 +1027,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     c->opts = o;
     c->cur_item = 0; c->cur_off = 0;
     c->next_launch = 0; c->next_return = 0;
-    c->gen_done[0] = c->gen_done[1] = c->gz_done[0] = c->gz_done[1] = nullptr;
+    c->gen_done[0] = c->gen_done[1] = c->gz_done[0] = c->gz_done[1] = c->copy_done = nullptr;
     for (auto &s : c->slots) s.gz_code_ready[0] = s.gz_code_ready[1] = false;  // the model or the genome may have changed
     c->exhausted = (total == 0);
     if (total == 0) { c->active = true; return ISS_OK; }
@@ -1129,6 +1141,11 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             CU(cudaMalloc(&s.d_segs, sizeof(DevSegment) * max_segs));
             CU(cudaMallocHost(&s.h_segs, sizeof(DevSegment) * max_segs));
             CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            if (o.compress) {
+                int least = 0, greatest = 0;
+                CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+                CU(cudaStreamCreateWithPriority(&s.zstream, cudaStreamNonBlocking, greatest));
+            }
             CU(cudaEventCreate(&s.ev_k0));
             CU(cudaEventCreate(&s.ev_k1));
             CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
