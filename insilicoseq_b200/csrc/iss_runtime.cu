@@ -345,7 +345,7 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     // While the ring is primed in compressing mode the rule is stricter -- this kernel waits for the COMPRESSOR of the batch
     // two launches ago: the persistent generate CTAs hold all the shared memory of their SMs, so the first batch's
     // compressor (whose output the idle copy engine is waiting for) would get SMs only as each of the five kernels queued
-    // behind it ends (first copy at 2.4 ms in the trace instead of ~1.2).  In steady state the looser rule keeps more overlap.
+    // behind it ends (first copy at 2.4 ms in the trace instead of 1.5).  In steady state the looser rule keeps more overlap.
     if (c->opts.compress && c->next_launch < c->n_slots && c->gz_done[c->next_launch & 1u])
         CU(cudaStreamWaitEvent(s.stream, c->gz_done[c->next_launch & 1u], 0));
     CU(cudaEventRecord(s.ev_k0, s.stream));
