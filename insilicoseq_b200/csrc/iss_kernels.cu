@@ -192,11 +192,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t by
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     uint32_t done;
     do {
-        // with a suspend-time hint: a waiting warp sleeps until the phase completes instead of coming back to ask (the
-        // un-hinted loop was 8.8 % of all executed instructions -- YIELD, TRYWAIT, BRA -- taking issue slots from the others)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
-                     : "r"(mbar), "r"(parity), "r"(0x989680u)
+                     : "r"(mbar), "r"(parity)
                      : "memory");
     } while (!done);
 }
