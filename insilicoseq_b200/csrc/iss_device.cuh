@@ -12,7 +12,8 @@
 #define ISS_MAX_ALT 4
 #define ISS_SLOW_SLOTS 16
 #define ISS_SURV_CAP 64  // queued indel-site survivors per tile before the scan falls back to a second walk
-#define ISS_Q16_ROW_BYTES 132  // a 16-bit quality row: ISS_QROW u16 entries + 4 bytes, so that the rows of a position start in different banks
+#define ISS_Q16_ROW_BYTES 132
+#define ISS_Q8_ROW_BYTES 24   // 8 x u16 thresholds + 8 x u8 counts  // a 16-bit quality row: ISS_QROW u16 entries + 4 bytes, so that the rows of a position start in different banks
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. SC'11).  Slot schedule: DESIGN.md section 3 / oracle/philox.py.
@@ -128,6 +129,12 @@ struct ModelHeader {
     uint32_t q16_nb[2];       // populated quality bins of the orientation (rows per position)
     uint32_t q16_ps[2];       // bytes per position: q16_nb * ISS_Q16_ROW_BYTES rounded up to 16 (bulk copies are 16-byte granular)
     uint8_t q16_cbin[2][4];   // bin -> row index among the populated bins
+    // short rows: where no row of the model has more than 8 distinct 16-bit thresholds (binned qualities: NovaSeq, NextSeq,
+    // HiSeq), a row is also stored as its <= 8 distinct values (pad 0xFFFF) + 8 bytes "entries of the full row below value c"
+    uint64_t q8_off[2];
+    uint32_t q8_ps[2];        // bytes per position of the short rows: q16_nb * ISS_Q8_ROW_BYTES rounded up to 16
+    uint32_t q8_ok;           // the model has them
+    uint32_t q8_pad;
 };
 
 // pointer view built on each device from the blob base
@@ -137,6 +144,7 @@ struct DevModel {
     const uint32_t *insert_thr;
     const uint32_t *qual_exact; // [2][4][L][ISS_QROW] sorted 32-bit thresholds (tie fallback of the 16-bit search)
     const uint8_t *q16[2];      // 16-bit rows of orientation o, position-major (one bulk copy per 2 positions)
+    const uint8_t *q8[2];       // the short rows, same order
     const uint8_t *subst_n;     // [2][L][4]
     const uint64_t *subst_thr;  // [2][L][4][4]
     const uint8_t *subst_alt;   // [2][L][4][4]
@@ -286,6 +294,8 @@ struct GenParams {
     // tile; its producer lane stages them one block ahead with cp.async.bulk + mbarriers (two stages per stream)
     uint32_t q_stage_cap;     // bytes reserved per stage (>= q_blocks * q_stage_bytes[o], multiple of 16)
     uint32_t q_blocks;        // Philox blocks per stage: 1, or 2 (the <512, 2, 2> build)
+    uint32_t q_short;         // the staged rows are the short ones (kK = 8 builds); q_pos_stride / q_stage_bytes / q_row_off describe them
+    const uint8_t *q_rows[2]; // the rows the pipeline stages: m.q16 or m.q8
     uint32_t q_stage_bytes[2];  // 2 * q16_ps[o]: the rows of one block of orientation o
     uint32_t q_pos_stride[2];   // q16_ps[o]
     uint32_t q_row_off[2][4];   // bin -> byte offset of its row inside a position (q16_cbin * ISS_Q16_ROW_BYTES)

@@ -75,6 +75,32 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // row_off: offset of the read's staged row from iss_smem
 // rowA / rowB: shared-window addresses of the read's staged rows at two positions (smem_addr(iss_smem) + offset).  The
 // two lower-bound searches are independent chains of 7 dependent LDS; stepping them together halves what a warp waits.
+// Short rows (kK = 8): the row holds its <= 8 DISTINCT 16-bit values (pad 0xFFFF, the last distinct value is always the
+// pad) and, behind them, for c = 0..7 the number of entries of the full row below the c-th value -- which is what the
+// 64-entry search would have counted, for every draw that equals none of the values (that one is a tie there too).
+// Three steps instead of six, and a 24-byte row instead of 132.
+__device__ __forceinline__ void q8_search2(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t &qA, uint32_t &qB,
+                                           bool &tieA, bool &tieB) {
+    uint32_t a = rowA, b = rowB;
+#define ISS_Q8_STEP(S)                                                                                               \
+    {                                                                                                                \
+        uint32_t ea, eb;                                                                                             \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ea) : "r"(a));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(eb) : "r"(b));                                      \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(a) : "r"(wA), "r"(ea)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(b) : "r"(wB), "r"(eb)); \
+    }
+    ISS_Q8_STEP(4) ISS_Q8_STEP(2) ISS_Q8_STEP(1)
+#undef ISS_Q8_STEP
+    uint32_t ea, eb;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ea) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(eb) : "r"(b));
+    tieA = ea == wA;
+    tieB = eb == wB;
+    // a - rowA = 2 c: the count byte of value c sits at rowA + 16 + c
+    asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qA) : "r"(rowA + ((a - rowA) >> 1)));
+    asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qB) : "r"(rowB + ((b - rowB) >> 1)));
+}
 __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t &qA, uint32_t &qB,
                                             bool &tieA, bool &tieB) {
     uint32_t a = rowA, b = rowB;
@@ -385,7 +411,7 @@ __device__ __noinline__ void replay_indels_warp(const GenParams &p, const Lay &l
 
 }  // namespace
 
-template <int kThreads, int kMinBlocks, int kQB>
+template <int kThreads, int kMinBlocks, int kQB, int kK>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(const __grid_constant__ GenParams p) {
     const uint32_t T = p.tile_pairs, tid = threadIdx.x, L = p.L;
     const Lay &l = p.lay;
@@ -436,7 +462,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
         const uint32_t bytes = (kQB == 1 || blk + 1u >= b_end) ? bytes1 : 2u * bytes1;
         mbar_wait(fb + 8u, (done + 1u) & 1u);
         mbar_arrive_expect_tx(fb, bytes);
-        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.m.q16[o] + (size_t)blk * bytes1, bytes, fb);
+        bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.q_rows[o] + (size_t)blk * bytes1, bytes, fb);
     };
     if (kde && pair == 0 && blockIdx.x < ntiles && b_begin < b_end) q_fill(0u, b_begin, 0u);
 
@@ -731,7 +757,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                     const Philox4 w = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
                     bool tie0, tie1;
                     uint32_t q0, q1;  // the row behind an odd L is all pad: q1 = 0 there, and not used
-                    q16_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
+                    if (kK == 8) q8_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
+                    else q16_search2(r0, w.x >> 16, r0 + p.q_pos_stride[o], w.z >> 16, q0, q1, tie0, tie1);
                     if (tie0) {
                         defer_position(l, p.tie_cap, rd, pos, q0);
                     } else {
@@ -999,15 +1026,20 @@ __global__ void iss_philox_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 // ---- host-visible launch helpers --------------------------------------------------------------------
 size_t iss_tile_smem_bytes(const Lay &l) { return l.total; }
 
-// Three builds: 256 threads x 4 CTAs/SM (64-pair tiles), 512 x 2 with one Philox block per quality stage (long reads, each
-// read split over 4 threads) and 512 x 2 with two blocks per stage (128-pair tiles of short reads).
+// Builds of the one kernel template <threads, CTAs/SM, Philox blocks per quality-row stage, entries per staged row>:
+// 256 x 4 (64-pair tiles), 512 x 2 with one block per stage (long reads, each read split over 4 threads) and 512 x 2 with two
+// blocks per stage (128-pair tiles of short reads); the 512-thread ones also for short (8-entry) rows.
 template <typename F>
 static cudaError_t for_each_build(F f) {
-    cudaError_t e = f(iss_generate_kernel<256, 4, 1>);
+    cudaError_t e = f(iss_generate_kernel<256, 4, 1, 64>);
     if (e != cudaSuccess) return e;
-    e = f(iss_generate_kernel<512, 2, 1>);
+    e = f(iss_generate_kernel<512, 2, 1, 64>);
     if (e != cudaSuccess) return e;
-    return f(iss_generate_kernel<512, 2, 2>);
+    e = f(iss_generate_kernel<512, 2, 2, 64>);
+    if (e != cudaSuccess) return e;
+    e = f(iss_generate_kernel<512, 2, 1, 8>);
+    if (e != cudaSuccess) return e;
+    return f(iss_generate_kernel<512, 2, 2, 8>);
 }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
@@ -1018,19 +1050,31 @@ cudaError_t iss_kernel_carveout(int percent) {  // shared-memory share of the SM
     return for_each_build([&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, percent); });
 }
 
+bool iss_has_short_row_build(uint32_t T, uint32_t split_shift) { return (2u << split_shift) * T > 256u; }
+
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
-    if (threads > 256 && p.q_blocks == 2) iss_generate_kernel<512, 2, 2><<<grid, threads, smem, stream>>>(p);
-    else if (threads > 256) iss_generate_kernel<512, 2, 1><<<grid, threads, smem, stream>>>(p);
-    else iss_generate_kernel<256, 4, 1><<<grid, threads, smem, stream>>>(p);
+    if (threads > 256 && p.q_blocks == 2) {
+        if (p.q_short) iss_generate_kernel<512, 2, 2, 8><<<grid, threads, smem, stream>>>(p);
+        else iss_generate_kernel<512, 2, 2, 64><<<grid, threads, smem, stream>>>(p);
+    } else if (threads > 256) {
+        if (p.q_short) iss_generate_kernel<512, 2, 1, 8><<<grid, threads, smem, stream>>>(p);
+        else iss_generate_kernel<512, 2, 1, 64><<<grid, threads, smem, stream>>>(p);
+    } else {
+        iss_generate_kernel<256, 4, 1, 64><<<grid, threads, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
-cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_blocks, size_t smem, int *blocks_per_sm) {
+cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_blocks, uint32_t q_short, size_t smem, int *blocks_per_sm) {
     const int threads = (int)((2u << split_shift) * T);
-    if (threads > 256 && q_blocks == 2) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2>, threads, smem);
-    if (threads > 256) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 1>, threads, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 1>, threads, smem);
+    if (threads > 256 && q_blocks == 2)
+        return q_short ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2, 8>, threads, smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2, 64>, threads, smem);
+    if (threads > 256)
+        return q_short ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 1, 8>, threads, smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 1, 64>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<256, 4, 1, 64>, threads, smem);
 }
 
 cudaError_t iss_launch_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t *dev_out, cudaStream_t stream) {

@@ -127,6 +127,7 @@ struct iss_ctx {
     uint32_t tile_pairs = 64, img_cap = 0, err_cap = 512, grid = 0, split_shift = 1;
     uint32_t q_stage_cap = 0;  // quality-row pipeline: bytes per stage
     uint32_t q_blocks = 1;     //   and Philox blocks (2 positions each) per stage
+    uint32_t q_short = 0;      //   the staged rows are the model's short (8-entry) ones
     uint64_t scratch_replay_bytes = 0;  // replay part of a slot's scratch; the substitution overflow lists follow
     Lay lay{};
     size_t smem = 0;
@@ -222,6 +223,8 @@ int rebuild_views(iss_ctx *c) {
         c->mview.qual_exact = reinterpret_cast<const uint32_t *>(b + h.qual_exact_off);
         c->mview.q16[0] = b + h.q16_off[0];
         c->mview.q16[1] = b + h.q16_off[1];
+        c->mview.q8[0] = h.q8_ok ? b + h.q8_off[0] : nullptr;
+        c->mview.q8[1] = h.q8_ok ? b + h.q8_off[1] : nullptr;
         c->mview.subst_n = b + h.subst_n_off;
         c->mview.subst_thr = reinterpret_cast<const uint64_t *>(b + h.subst_thr_off);
         c->mview.subst_alt = b + h.subst_alt_off;
@@ -302,10 +305,13 @@ int launch_batch(iss_ctx *c, uint32_t si) {
     p.lay = c->lay;
     p.q_stage_cap = c->q_stage_cap;
     p.q_blocks = c->q_blocks;
+    p.q_short = c->q_short;
     for (uint32_t o = 0; o < 2; ++o) {
-        p.q_pos_stride[o] = h.q16_ps[o];
-        p.q_stage_bytes[o] = 2u * h.q16_ps[o];
-        for (uint32_t b = 0; b < 4; ++b) p.q_row_off[o][b] = h.q16_cbin[o][b] * ISS_Q16_ROW_BYTES;
+        const uint32_t ps = c->q_short ? h.q8_ps[o] : h.q16_ps[o];
+        p.q_pos_stride[o] = ps;
+        p.q_stage_bytes[o] = 2u * ps;
+        p.q_rows[o] = c->q_short ? c->mview.q8[o] : c->mview.q16[o];
+        for (uint32_t b = 0; b < 4; ++b) p.q_row_off[o][b] = h.q16_cbin[o][b] * (c->q_short ? ISS_Q8_ROW_BYTES : ISS_Q16_ROW_BYTES);
     }
     p.out1 = s.d_out[0];
     p.out2 = s.d_out[1];
@@ -844,12 +850,26 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
             }
             h.q16_nb[o] = std::max(nb, 1u);
             h.q16_ps[o] = (uint32_t)align_up((uint64_t)h.q16_nb[o] * ISS_Q16_ROW_BYTES, 16);
+            h.q8_ps[o] = (uint32_t)align_up((uint64_t)h.q16_nb[o] * ISS_Q8_ROW_BYTES, 16);
         }
+        // short rows: every row of the model has at most 8 distinct 16-bit values (the pad 0xFFFF is one of them)
+        h.q8_ok = 1;
+        for (uint32_t ob = 0; ob < 8 && h.q8_ok; ++ob) {
+            if (!m->bin_valid[ob]) continue;
+            for (uint64_t pos = 0; pos < L && h.q8_ok; ++pos) {
+                const uint32_t *src = m->qual_thr + ((uint64_t)ob * L + pos) * ISS_QROW;
+                uint32_t distinct = 1;
+                for (int j = 1; j < ISS_QROW; ++j) distinct += (src[j] >> 16) != (src[j - 1] >> 16) ? 1u : 0u;
+                if (distinct > 8) h.q8_ok = 0;
+            }
+        }
+        if (getenv("ISS_QROWS") && atoi(getenv("ISS_QROWS")) == 64) h.q8_ok = 0;  // A/B switch for benchmarks and tests: full rows only
     }
     h.frag_thr_off = place(8ull * m->n_frag);
     h.insert_thr_off = place(4ull * m->n_insert);
     h.qual_exact_off = place(kde ? 2ull * 4 * L * ISS_QROW * 4 : 0);
     for (uint32_t o = 0; o < 2; ++o) h.q16_off[o] = place(kde ? (uint64_t)(L + 1) * h.q16_ps[o] : 0);
+    for (uint32_t o = 0; o < 2; ++o) h.q8_off[o] = place(kde && h.q8_ok ? (uint64_t)(L + 1) * h.q8_ps[o] : 0);
     h.subst_n_off = place(2ull * L * 4);
     h.subst_thr_off = place(2ull * L * 4 * ISS_MAX_ALT * 8);
     h.subst_alt_off = place(2ull * L * 4 * ISS_MAX_ALT);
@@ -878,6 +898,33 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
                     for (uint32_t j = 0; j < ISS_QROW; ++j) {
                         const uint16_t e = (uint16_t)(src[j] >> 16);
                         memcpy(row + 2 * j, &e, 2);
+                    }
+                }
+            }
+        }
+    }
+    if (kde && h.q8_ok) {
+        for (uint32_t o = 0; o < 2; ++o) {
+            uint8_t *base = blob.data() + h.q8_off[o];
+            // pad positions / rows: values 0xFFFF (nothing is below a draw's tie with the pad), counts 0
+            for (uint64_t pos = 0; pos <= L; ++pos)
+                for (uint32_t r = 0; r < h.q16_nb[o]; ++r) {
+                    uint8_t *row = base + pos * h.q8_ps[o] + (size_t)r * ISS_Q8_ROW_BYTES;
+                    memset(row, 0xFF, 16);
+                    memset(row + 16, 0, 8);
+                }
+            for (uint32_t b = 0; b < 4; ++b) {
+                if (!m->bin_valid[o * 4 + b]) continue;
+                for (uint64_t pos = 0; pos < L; ++pos) {
+                    const uint32_t *src = m->qual_thr + ((uint64_t)(o * 4 + b) * L + pos) * ISS_QROW;
+                    uint8_t *row = base + pos * h.q8_ps[o] + (size_t)h.q16_cbin[o][b] * ISS_Q8_ROW_BYTES;
+                    uint32_t k = 0;
+                    for (uint32_t j = 0; j < ISS_QROW; ++j) {
+                        const uint16_t e = (uint16_t)(src[j] >> 16);
+                        if (j && e == (uint16_t)(src[j - 1] >> 16)) continue;
+                        memcpy(row + 2 * k, &e, 2);   // the k-th distinct value ...
+                        row[16 + k] = (uint8_t)j;     // ... and the entries of the full row below it
+                        ++k;
                     }
                 }
             }
@@ -1049,9 +1096,15 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
     // quality-row pipeline geometry: one stage = the 16-bit rows of q_blocks Philox blocks (2 positions each) for the
     // populated bins of an orientation
     const bool kde = c->mh.qual_mode == ISS_QUAL_KDE;
-    const uint32_t q_cap1 = kde ? 2u * std::max(c->mh.q16_ps[0], c->mh.q16_ps[1]) : 0u;
+    // bytes of one block's rows: the short rows where the model has them and the geometry has a build for them
+    auto q_cap1_of = [&](uint32_t T_, uint32_t split) -> uint32_t {
+        if (!kde) return 0u;
+        const bool sh = c->mh.q8_ok && iss_has_short_row_build(T_, split);
+        return 2u * (sh ? std::max(c->mh.q8_ps[0], c->mh.q8_ps[1]) : std::max(c->mh.q16_ps[0], c->mh.q16_ps[1]));
+    };
+    auto short_of = [&](uint32_t T_, uint32_t split) -> uint32_t { return kde && c->mh.q8_ok && iss_has_short_row_build(T_, split) ? 1u : 0u; };
     auto layout = [&](uint32_t T_, uint32_t split, uint32_t qb) {
-        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, kTieCap, 2u << split, qb * q_cap1);
+        return iss_make_layout(T_, (uint32_t)align_up(32 + (uint64_t)T_ * max_rec, 16), c->err_cap, kTieCap, 2u << split, qb * q_cap1_of(T_, split));
     };
     Lay lay{};
     int bps = 0;
@@ -1063,7 +1116,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         // cp.async.bulk of the row pipeline then serves four positions instead of two.
         const Lay w = layout(128, 1, 2);
         int b = 0;
-        if (w.total <= kMaxSmem && iss_occupancy(128, 1, 2, w.total, &b) == cudaSuccess && b >= 2) {
+        if (w.total <= kMaxSmem && iss_occupancy(128, 1, 2, short_of(128, 1), w.total, &b) == cudaSuccess && b >= 2) {
             wide = true; T = 128; q_blocks = 2; lay = w; smem = w.total; bps = b;
             img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
         }
@@ -1076,13 +1129,13 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
             if (smem <= kMaxSmem) break;
             if (T == 32) return fail(ISS_E_ARG, "records too long for one tile (read length / name length)");
         }
-        CU(iss_occupancy(T, split_shift, 1, smem, &bps));
+        CU(iss_occupancy(T, split_shift, 1, short_of(T, split_shift), smem, &bps));
         if (bps < 1) return fail(ISS_E_CUDA, "kernel does not fit on an SM");
         if (bps <= 2 && T == 64) {  // long reads: the images leave room for <= 2 CTAs/SM -> 4 threads per read keep 32 warps/SM
             int bps4 = 0;
             const Lay lay4 = layout(T, 2, 1);
             if (lay4.total <= kMaxSmem) {
-                CU(iss_occupancy(T, 2, 1, lay4.total, &bps4));
+                CU(iss_occupancy(T, 2, 1, short_of(T, 2), lay4.total, &bps4));
                 if (bps4 >= bps) { split_shift = 2; bps = bps4; lay = lay4; smem = lay4.total; }
             }
         }
@@ -1094,13 +1147,14 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         c->err_cap = cap;
         const Lay big = layout(T, split_shift, q_blocks);
         int b2 = 0;
-        if (big.total <= kMaxSmem && iss_occupancy(T, split_shift, q_blocks, big.total, &b2) == cudaSuccess && b2 >= bps) { lay = big; smem = big.total; break; }
+        if (big.total <= kMaxSmem && iss_occupancy(T, split_shift, q_blocks, short_of(T, split_shift), big.total, &b2) == cudaSuccess && b2 >= bps) { lay = big; smem = big.total; break; }
         c->err_cap = keep;
     }
     c->split_shift = split_shift;
     c->lay = lay;
-    c->q_stage_cap = q_blocks * q_cap1;
+    c->q_stage_cap = q_blocks * q_cap1_of(T, split_shift);
     c->q_blocks = q_blocks;
+    c->q_short = short_of(T, split_shift);
     if (const char *e = getenv("ISS_BPS")) {  // A/B switch for benchmarks: fewer CTAs per SM (with ISS_CARVEOUT: more L1)
         const int cap = atoi(e);
         if (cap >= 1 && cap < bps) bps = cap;
