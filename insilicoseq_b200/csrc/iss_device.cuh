@@ -130,7 +130,7 @@ struct ModelHeader {
     uint32_t q16_ps[2];       // bytes per position: q16_nb * ISS_Q16_ROW_BYTES rounded up to 16 (bulk copies are 16-byte granular)
     uint8_t q16_cbin[2][4];   // bin -> row index among the populated bins
     // short rows: where no row of the model has more than 8 distinct 16-bit thresholds (binned qualities: NovaSeq, NextSeq,
-    // HiSeq), a row is also stored as its <= 8 distinct values (pad 0xFFFF) + 8 bytes "entries of the full row below value c"
+    // HiSeq), a row is also stored as its <= 8 distinct non-zero values (pad 0xFFFF) + 8 bytes "entries of the full row below value c"
     uint64_t q8_off[2];
     uint32_t q8_ps[2];        // bytes per position of the short rows: q16_nb * ISS_Q8_ROW_BYTES rounded up to 16
     uint32_t q8_ok;           // the model has them

@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // row_off: offset of the read's staged row from iss_smem
 // rowA / rowB: shared-window addresses of the read's staged rows at two positions (smem_addr(iss_smem) + offset).  The
 // two lower-bound searches are independent chains of 7 dependent LDS; stepping them together halves what a warp waits.
-// Short rows (kK = 8): the row holds its <= 8 DISTINCT 16-bit values (pad 0xFFFF, the last distinct value is always the
+// Short rows (kK = 8): the row holds its <= 8 DISTINCT non-zero 16-bit values (pad 0xFFFF, the last distinct value is always the
 // pad) and, behind them, for c = 0..7 the number of entries of the full row below the c-th value -- which is what the
 // 64-entry search would have counted, for every draw that equals none of the values (that one is a tie there too).
 // Three steps instead of six, and a 24-byte row instead of 132.
@@ -95,11 +95,15 @@ __device__ __forceinline__ void q8_search2(uint32_t rowA, uint32_t wA, uint32_t 
     uint32_t ea, eb;
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ea) : "r"(a));
     asm volatile("ld.shared.u16 %0, [%1];" : "=r"(eb) : "r"(b));
-    tieA = ea == wA;
-    tieB = eb == wB;
     // a - rowA = 2 c: the count byte of value c sits at rowA + 16 + c
     asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qA) : "r"(rowA + ((a - rowA) >> 1)));
     asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qB) : "r"(rowB + ((b - rowB) >> 1)));
+    // The value 0 (qualities below the model's lowest: cumulative probability < 2^-16) is not stored: every draw with a
+    // non-zero top half is above it.  A draw whose top half IS zero goes to the exact pass with nothing known about it.
+    tieA = (ea == wA) | (wA == 0u);
+    tieB = (eb == wB) | (wB == 0u);
+    qA = wA ? qA : 0u;
+    qB = wB ? qB : 0u;
 }
 __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t &qA, uint32_t &qB,
                                             bool &tieA, bool &tieB) {
@@ -459,7 +463,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
     auto q_fill = [&](uint32_t stg, uint32_t blk, uint32_t done /* consumptions of the stage so far */) {
         // kQB blocks per stage (their rows are contiguous in the blob); the stream's last turn may hold fewer
         const uint32_t fb = bar0 + (stg << 4), bytes1 = p.q_stage_bytes[o];
-        const uint32_t bytes = (kQB == 1 || blk + 1u >= b_end) ? bytes1 : 2u * bytes1;
+        uint32_t bytes;
+        if constexpr (kQB <= 2) bytes = (kQB == 1 || blk + 1u >= b_end) ? bytes1 : 2u * bytes1;
+        else { const uint32_t left = b_end - blk; bytes = (left < (uint32_t)kQB ? left : (uint32_t)kQB) * bytes1; }
         mbar_wait(fb + 8u, (done + 1u) & 1u);
         mbar_arrive_expect_tx(fb, bytes);
         bulk_load(smem0 + stage0 + stg * p.q_stage_cap, p.q_rows[o] + (size_t)blk * bytes1, bytes, fb);
@@ -787,7 +793,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                     if (valid) {
                         const uint32_t r0 = row0 + stg * p.q_stage_cap;
                         q_block(b, r0);
-                        if (kQB == 2 && b + 1u < b_end) q_block(b + 1u, r0 + p.q_stage_bytes[o]);
+                        if constexpr (kQB == 2) {
+                            if (b + 1u < b_end) q_block(b + 1u, r0 + p.q_stage_bytes[o]);
+                        } else if constexpr (kQB > 2) {
+#pragma unroll
+                            for (uint32_t j = 1; j < (uint32_t)kQB; ++j)
+                                if (b + j < b_end) q_block(b + j, r0 + j * p.q_stage_bytes[o]);
+                        }
                     }
                     __syncwarp();
                     if ((tid & 31u) == 0) mbar_arrive(bar0 + (stg << 4) + 8u);  // this warp is done with the stage
@@ -1028,7 +1040,8 @@ size_t iss_tile_smem_bytes(const Lay &l) { return l.total; }
 
 // Builds of the one kernel template <threads, CTAs/SM, Philox blocks per quality-row stage, entries per staged row>:
 // 256 x 4 (64-pair tiles), 512 x 2 with one block per stage (long reads, each read split over 4 threads) and 512 x 2 with two
-// blocks per stage (128-pair tiles of short reads); the 512-thread ones also for short (8-entry) rows.
+// blocks per stage (128-pair tiles of short reads); the 512-thread ones also for short (8-entry) rows, which are small
+// enough for four blocks per stage.
 template <typename F>
 static cudaError_t for_each_build(F f) {
     cudaError_t e = f(iss_generate_kernel<256, 4, 1, 64>);
@@ -1039,7 +1052,9 @@ static cudaError_t for_each_build(F f) {
     if (e != cudaSuccess) return e;
     e = f(iss_generate_kernel<512, 2, 1, 8>);
     if (e != cudaSuccess) return e;
-    return f(iss_generate_kernel<512, 2, 2, 8>);
+    e = f(iss_generate_kernel<512, 2, 2, 8>);
+    if (e != cudaSuccess) return e;
+    return f(iss_generate_kernel<512, 2, 4, 8>);
 }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
@@ -1054,7 +1069,9 @@ bool iss_has_short_row_build(uint32_t T, uint32_t split_shift) { return (2u << s
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
-    if (threads > 256 && p.q_blocks == 2) {
+    if (threads > 256 && p.q_blocks == 4 && p.q_short) {
+        iss_generate_kernel<512, 2, 4, 8><<<grid, threads, smem, stream>>>(p);
+    } else if (threads > 256 && p.q_blocks == 2) {
         if (p.q_short) iss_generate_kernel<512, 2, 2, 8><<<grid, threads, smem, stream>>>(p);
         else iss_generate_kernel<512, 2, 2, 64><<<grid, threads, smem, stream>>>(p);
     } else if (threads > 256) {
@@ -1068,6 +1085,8 @@ cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, 
 
 cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_blocks, uint32_t q_short, size_t smem, int *blocks_per_sm) {
     const int threads = (int)((2u << split_shift) * T);
+    if (threads > 256 && q_blocks == 4 && q_short)
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 4, 8>, threads, smem);
     if (threads > 256 && q_blocks == 2)
         return q_short ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2, 8>, threads, smem)
                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2, 64>, threads, smem);

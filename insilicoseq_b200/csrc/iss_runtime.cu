@@ -852,13 +852,13 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
             h.q16_ps[o] = (uint32_t)align_up((uint64_t)h.q16_nb[o] * ISS_Q16_ROW_BYTES, 16);
             h.q8_ps[o] = (uint32_t)align_up((uint64_t)h.q16_nb[o] * ISS_Q8_ROW_BYTES, 16);
         }
-        // short rows: every row of the model has at most 8 distinct 16-bit values (the pad 0xFFFF is one of them)
+        // short rows: every row of the model has at most 8 distinct non-zero 16-bit values (the pad 0xFFFF is one of them)
         h.q8_ok = 1;
         for (uint32_t ob = 0; ob < 8 && h.q8_ok; ++ob) {
             if (!m->bin_valid[ob]) continue;
             for (uint64_t pos = 0; pos < L && h.q8_ok; ++pos) {
                 const uint32_t *src = m->qual_thr + ((uint64_t)ob * L + pos) * ISS_QROW;
-                uint32_t distinct = 1;
+                uint32_t distinct = (src[0] >> 16) ? 1u : 0u;  // the value 0 is not stored (see q8_search2)
                 for (int j = 1; j < ISS_QROW; ++j) distinct += (src[j] >> 16) != (src[j - 1] >> 16) ? 1u : 0u;
                 if (distinct > 8) h.q8_ok = 0;
             }
@@ -921,8 +921,8 @@ int iss_ctx_set_model(iss_ctx *c, const iss_model *m) {
                     uint32_t k = 0;
                     for (uint32_t j = 0; j < ISS_QROW; ++j) {
                         const uint16_t e = (uint16_t)(src[j] >> 16);
-                        if (j && e == (uint16_t)(src[j - 1] >> 16)) continue;
-                        memcpy(row + 2 * k, &e, 2);   // the k-th distinct value ...
+                        if (e == 0 || (j && e == (uint16_t)(src[j - 1] >> 16))) continue;
+                        memcpy(row + 2 * k, &e, 2);   // the k-th distinct non-zero value ...
                         row[16 + k] = (uint8_t)j;     // ... and the entries of the full row below it
                         ++k;
                     }
@@ -1114,10 +1114,11 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         // short reads: 128-pair tiles (512 threads, 2 CTAs/SM) with TWO blocks per stage.  Half as many CTAs per SM hold
         // half as many stages, so a stage can be twice as long in the same shared memory; every wait, hand-back and
         // cp.async.bulk of the row pipeline then serves four positions instead of two.
-        const Lay w = layout(128, 1, 2);
+        const uint32_t qb = short_of(128, 1) && !getenv("ISS_QB2") ? 4u : 2u;  // short rows: four blocks are 768 B (ISS_QB2: A/B switch)
+        const Lay w = layout(128, 1, qb);
         int b = 0;
-        if (w.total <= kMaxSmem && iss_occupancy(128, 1, 2, short_of(128, 1), w.total, &b) == cudaSuccess && b >= 2) {
-            wide = true; T = 128; q_blocks = 2; lay = w; smem = w.total; bps = b;
+        if (w.total <= kMaxSmem && iss_occupancy(128, 1, qb, short_of(128, 1), w.total, &b) == cudaSuccess && b >= 2) {
+            wide = true; T = 128; q_blocks = qb; lay = w; smem = w.total; bps = b;
             img_cap = (uint32_t)align_up(32 + (uint64_t)T * max_rec, 16);
         }
     }
