@@ -1040,8 +1040,9 @@ size_t iss_tile_smem_bytes(const Lay &l) { return l.total; }
 
 // Builds of the one kernel template <threads, CTAs/SM, Philox blocks per quality-row stage, entries per staged row>:
 // 256 x 4 (64-pair tiles), 512 x 2 with one block per stage (long reads, each read split over 4 threads) and 512 x 2 with two
-// blocks per stage (128-pair tiles of short reads); the 512-thread ones also for short (8-entry) rows, which are small
-// enough for four blocks per stage.
+// blocks per stage (128-pair tiles of short reads); the 512-thread ones also for short (8-entry) rows.  (Four blocks per
+// stage, which the short rows have room for, measured 6 % slower than two: 7.89e8 against 8.41e8 pairs/s on configs[2] --
+// the loop body is unrolled per block and stage, and the kernel is 120 KB of code as it is.)
 template <typename F>
 static cudaError_t for_each_build(F f) {
     cudaError_t e = f(iss_generate_kernel<256, 4, 1, 64>);
@@ -1052,9 +1053,7 @@ static cudaError_t for_each_build(F f) {
     if (e != cudaSuccess) return e;
     e = f(iss_generate_kernel<512, 2, 1, 8>);
     if (e != cudaSuccess) return e;
-    e = f(iss_generate_kernel<512, 2, 2, 8>);
-    if (e != cudaSuccess) return e;
-    return f(iss_generate_kernel<512, 2, 4, 8>);
+    return f(iss_generate_kernel<512, 2, 2, 8>);
 }
 
 cudaError_t iss_kernel_configure(size_t max_smem) {  // once per device
@@ -1069,9 +1068,7 @@ bool iss_has_short_row_build(uint32_t T, uint32_t split_shift) { return (2u << s
 
 cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, cudaStream_t stream) {
     const uint32_t threads = (2u << p.split_shift) * p.tile_pairs;
-    if (threads > 256 && p.q_blocks == 4 && p.q_short) {
-        iss_generate_kernel<512, 2, 4, 8><<<grid, threads, smem, stream>>>(p);
-    } else if (threads > 256 && p.q_blocks == 2) {
+    if (threads > 256 && p.q_blocks == 2) {
         if (p.q_short) iss_generate_kernel<512, 2, 2, 8><<<grid, threads, smem, stream>>>(p);
         else iss_generate_kernel<512, 2, 2, 64><<<grid, threads, smem, stream>>>(p);
     } else if (threads > 256) {
@@ -1085,8 +1082,6 @@ cudaError_t iss_launch_generate(const GenParams &p, uint32_t grid, size_t smem, 
 
 cudaError_t iss_occupancy(uint32_t T, uint32_t split_shift, uint32_t q_blocks, uint32_t q_short, size_t smem, int *blocks_per_sm) {
     const int threads = (int)((2u << split_shift) * T);
-    if (threads > 256 && q_blocks == 4 && q_short)
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 4, 8>, threads, smem);
     if (threads > 256 && q_blocks == 2)
         return q_short ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2, 8>, threads, smem)
                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, iss_generate_kernel<512, 2, 2, 64>, threads, smem);

@@ -1114,7 +1114,7 @@ int iss_ctx_submit(iss_ctx *c, const iss_work_item *items, uint64_t n_items, con
         // short reads: 128-pair tiles (512 threads, 2 CTAs/SM) with TWO blocks per stage.  Half as many CTAs per SM hold
         // half as many stages, so a stage can be twice as long in the same shared memory; every wait, hand-back and
         // cp.async.bulk of the row pipeline then serves four positions instead of two.
-        const uint32_t qb = short_of(128, 1) && !getenv("ISS_QB2") ? 4u : 2u;  // short rows: four blocks are 768 B (ISS_QB2: A/B switch)
+        const uint32_t qb = 2u;
         const Lay w = layout(128, 1, qb);
         int b = 0;
         if (w.total <= kMaxSmem && iss_occupancy(128, 1, qb, short_of(128, 1), w.total, &b) == cudaSuccess && b >= 2) {

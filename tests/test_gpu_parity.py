@@ -113,18 +113,15 @@ def test_tile_geometries(name, tile, monkeypatch):
     assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
 
 
-@pytest.mark.parametrize("rows", ["short", "short_qb2", "64"])
+@pytest.mark.parametrize("rows", ["short", "64"])
 @pytest.mark.parametrize("name", ["novaseq_single", "gc_bias_hiseq", "hiseq_multi_short", "nextseq_large_digest", "fragment_length_novaseq",
                                   "ecoli_kde_vcf"])
 def test_short_quality_rows(name, rows, monkeypatch):
     """Models whose quality rows have at most 8 distinct 16-bit thresholds (binned qualities: NovaSeq, NextSeq, HiSeq) are
-    searched on 8-entry rows + a count byte per entry (three steps instead of six; the <512, 2, *, 8> builds, four Philox blocks
-    per stage by default); ISS_QROWS=64 keeps such a model on the full rows.  All must give the golden bytes -- ties and draws
+    searched on 8-entry rows + a count byte per entry (three steps instead of six; the <512, 2, *, 8> builds); ISS_QROWS=64 keeps such a model on the full rows.  All must give the golden bytes -- ties and draws
     with a zero top half, which go to the exact pass, included."""
     if rows == "64":
         monkeypatch.setenv("ISS_QROWS", "64")
-    if rows == "short_qb2":  # two blocks per stage instead of four: the <512, 2, 2, 8> build
-        monkeypatch.setenv("ISS_QB2", "1")
     case, exp = fixtures.load_case(name)
     r1, r2, _ = run_product(case, batch_pairs=700)
     assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
