@@ -127,6 +127,33 @@ __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t
     qB = (b - rowB) >> 1;
 }
 
+// four positions at once: the two blocks of a stage (four independent chains)
+__device__ __forceinline__ void q16_search4(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t rowC, uint32_t wC, uint32_t rowD, uint32_t wD,
+                                            uint32_t &qA, uint32_t &qB, uint32_t &qC, uint32_t &qD, bool &tieA, bool &tieB, bool &tieC, bool &tieD) {
+    uint32_t a = rowA, b = rowB, c = rowC, d = rowD;
+#define ISS_Q16_STEP4(S)                                                                                             \
+    {                                                                                                                \
+        uint32_t ea, eb, ec, ed;                                                                                     \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ea) : "r"(a));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(eb) : "r"(b));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ec) : "r"(c));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ed) : "r"(d));                                      \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(a) : "r"(wA), "r"(ea)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(b) : "r"(wB), "r"(eb)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(c) : "r"(wC), "r"(ec)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(d) : "r"(wD), "r"(ed)); \
+    }
+    ISS_Q16_STEP4(32) ISS_Q16_STEP4(16) ISS_Q16_STEP4(8) ISS_Q16_STEP4(4) ISS_Q16_STEP4(2) ISS_Q16_STEP4(1)
+#undef ISS_Q16_STEP4
+    uint32_t ea, eb, ec, ed;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ea) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(eb) : "r"(b));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ec) : "r"(c));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ed) : "r"(d));
+    tieA = ea == wA; tieB = eb == wB; tieC = ec == wC; tieD = ed == wD;
+    qA = (a - rowA) >> 1; qB = (b - rowB) >> 1; qC = (c - rowC) >> 1; qD = (d - rowD) >> 1;
+}
+
 // substitution list full: the entry goes to this CTA's stretch of a list in global memory (models with ~ 4 or more errors
 // per read at 64 pairs per tile); only beyond that does the tile fall back to the exact pass
 __device__ __noinline__ void err_overflow(const GenParams &p, uint32_t slot, uint32_t v) {
@@ -786,15 +813,44 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         }
                     }
                 };
+                // two full blocks of a stage at once (full rows): four searches stepped together
+                auto q_emit = [&](uint32_t pos, uint32_t q, bool tie, uint32_t werr) {
+                    if (tie) {
+                        defer_position(l, p.tie_cap, rd, pos, q);
+                    } else {
+                        sts_u8(qual_s + pos, q + 33u);
+                        if (werr > lds_u32(thr_s + 4u * q)) {
+                            const uint32_t slot = atomicAdd(&u32p(l.sCtl)[0], 1u);
+                            if (slot < p.err_cap) u32p(l.sErr)[slot] = (rd << 16) | pos; else err_overflow(p, slot, (rd << 16) | pos);
+                        }
+                    }
+                };
+                auto q_block2 = [&](uint32_t b, uint32_t r0) {
+                    const uint32_t pos = 2u * b;
+                    const Philox4 w0 = philox4x32_10_rk(b, sQ, Plo, Phi, p.rk);
+                    const Philox4 w1 = philox4x32_10_rk(b + 1u, sQ, Plo, Phi, p.rk);
+                    const uint32_t r1 = r0 + p.q_stage_bytes[o], ps = p.q_pos_stride[o];
+                    bool t0, t1, t2, t3;
+                    uint32_t q0, q1, q2, q3;
+                    q16_search4(r0, w0.x >> 16, r0 + ps, w0.z >> 16, r1, w1.x >> 16, r1 + ps, w1.z >> 16, q0, q1, q2, q3, t0, t1, t2, t3);
+                    q_emit(pos, q0, t0, w0.y);
+                    q_emit(pos + 1u, q1, t1, w0.w);
+                    q_emit(pos + 2u, q2, t2, w1.y);
+                    if (pos + 3u < L) q_emit(pos + 3u, q3, t3, w1.w);
+                };
                 // one turn of a stage: wait for its rows, its kQB blocks, hand the stage back
                 auto q_stage = [&](uint32_t b, uint32_t stg) {
                     mbar_wait(bar0 + (stg << 4), (qpar >> stg) & 1u);
                     qpar ^= 1u << stg;
                     if (valid) {
                         const uint32_t r0 = row0 + stg * p.q_stage_cap;
-                        q_block(b, r0);
-                        if constexpr (kQB == 2) {
+                        if constexpr (kQB == 2 && kK == 64) {
+                            if (b + 1u < b_end) q_block2(b, r0); else q_block(b, r0);
+                        } else if constexpr (kQB == 2) {
+                            q_block(b, r0);
                             if (b + 1u < b_end) q_block(b + 1u, r0 + p.q_stage_bytes[o]);
+                        } else if constexpr (kQB == 1) {
+                            q_block(b, r0);
                         } else if constexpr (kQB > 2) {
 #pragma unroll
                             for (uint32_t j = 1; j < (uint32_t)kQB; ++j)
