@@ -128,18 +128,6 @@ def test_short_quality_rows(name, rows, monkeypatch):
     assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
 
 
-@pytest.mark.parametrize("stages,dist", [("4", "1"), ("4", "3")])
-def test_quality_row_ring_depths(stages, dist, monkeypatch):
-    """The quality-row ring with 4 stages and prefetch distance 1 / 3 (default: 2 stages, distance 1)."""
-    monkeypatch.setenv("ISS_QSTAGES", stages)
-    monkeypatch.setenv("ISS_QDIST", dist)
-    for name in ("miseq150_bench_model", "long_reads_906", "read_length_3"):
-        case, exp = fixtures.load_case(name)
-        r1, r2, _ = run_product(case, batch_pairs=500)
-        assert hashlib.sha256(r1).hexdigest() == case["sha256"]["R1"]
-        assert hashlib.sha256(r2).hexdigest() == case["sha256"]["R2"]
-
-
 def test_native_file_writer(tmp_path):
     """Engine.write_files (iss_ctx_write_files): the FASTQ / VCF bytes land in files through the library's pwrite threads,
     at given offsets of a shared final file (two workers, plain text) or appended (gzip members)."""
