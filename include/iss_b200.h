@@ -6,6 +6,9 @@
  *
  *   iss_ctx_set_genome   <- the SeqRecord objects pickled to every worker       iss/app.py:99-106,
  *                           (FASTA records parsed by SeqIO.parse)               iss/generator.py:270
+ *   iss_fasta_index /    <- SeqIO.parse(genome_file, "fasta") + str(record.seq) iss/generator.py:270,468-490,
+ *   iss_ctx_set_genome_fasta   per record: the genome FILE as text, title lines    iss/app.py:74-76
+ *                           found on the host, everything else on the GPU
  *   iss_ctx_set_model    <- the ErrorModel object pickled to every worker       iss/error_models/kde.py:24-50
  *                           (attribute set of KDErrorModel / Basic / Perfect)   iss/error_models/basic.py, perfect.py
  *   iss_ctx_submit       <- pool.starmap(worker_iterator, work chunks)          iss/app.py:99-106
