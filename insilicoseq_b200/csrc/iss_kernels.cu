@@ -127,6 +127,36 @@ __device__ __forceinline__ void q16_search2(uint32_t rowA, uint32_t wA, uint32_t
     qB = (b - rowB) >> 1;
 }
 
+// the same four at once on short rows
+__device__ __forceinline__ void q8_search4(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t rowC, uint32_t wC, uint32_t rowD, uint32_t wD,
+                                           uint32_t &qA, uint32_t &qB, uint32_t &qC, uint32_t &qD, bool &tieA, bool &tieB, bool &tieC, bool &tieD) {
+    uint32_t a = rowA, b = rowB, c = rowC, d = rowD;
+#define ISS_Q8_STEP4(S)                                                                                              \
+    {                                                                                                                \
+        uint32_t ea, eb, ec, ed;                                                                                     \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ea) : "r"(a));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(eb) : "r"(b));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ec) : "r"(c));                                      \
+        asm volatile("ld.shared.u16 %0, [%1+" #S "*2-2];" : "=r"(ed) : "r"(d));                                      \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(a) : "r"(wA), "r"(ea)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(b) : "r"(wB), "r"(eb)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(c) : "r"(wC), "r"(ec)); \
+        asm("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %1, %2;\n\t@p add.u32 %0, %0, " #S "*2;\n\t}" : "+r"(d) : "r"(wD), "r"(ed)); \
+    }
+    ISS_Q8_STEP4(4) ISS_Q8_STEP4(2) ISS_Q8_STEP4(1)
+#undef ISS_Q8_STEP4
+    uint32_t ea, eb, ec, ed;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ea) : "r"(a));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(eb) : "r"(b));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ec) : "r"(c));
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ed) : "r"(d));
+    asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qA) : "r"(rowA + ((a - rowA) >> 1)));
+    asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qB) : "r"(rowB + ((b - rowB) >> 1)));
+    asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qC) : "r"(rowC + ((c - rowC) >> 1)));
+    asm volatile("ld.shared.u8 %0, [%1+16];" : "=r"(qD) : "r"(rowD + ((d - rowD) >> 1)));
+    tieA = (ea == wA) | (wA == 0u); tieB = (eb == wB) | (wB == 0u); tieC = (ec == wC) | (wC == 0u); tieD = (ed == wD) | (wD == 0u);
+    qA = wA ? qA : 0u; qB = wB ? qB : 0u; qC = wC ? qC : 0u; qD = wD ? qD : 0u;
+}
 // four positions at once: the two blocks of a stage (four independent chains)
 __device__ __forceinline__ void q16_search4(uint32_t rowA, uint32_t wA, uint32_t rowB, uint32_t wB, uint32_t rowC, uint32_t wC, uint32_t rowD, uint32_t wD,
                                             uint32_t &qA, uint32_t &qB, uint32_t &qC, uint32_t &qD, bool &tieA, bool &tieB, bool &tieC, bool &tieD) {
@@ -813,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                         }
                     }
                 };
-                // two full blocks of a stage at once (full rows): four searches stepped together
+                // two full blocks of a stage at once: four searches stepped together
                 auto q_emit = [&](uint32_t pos, uint32_t q, bool tie, uint32_t werr) {
                     if (tie) {
                         defer_position(l, p.tie_cap, rd, pos, q);
@@ -832,7 +862,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                     const uint32_t r1 = r0 + p.q_stage_bytes[o], ps = p.q_pos_stride[o];
                     bool t0, t1, t2, t3;
                     uint32_t q0, q1, q2, q3;
-                    q16_search4(r0, w0.x >> 16, r0 + ps, w0.z >> 16, r1, w1.x >> 16, r1 + ps, w1.z >> 16, q0, q1, q2, q3, t0, t1, t2, t3);
+                    if (kK == 8) q8_search4(r0, w0.x >> 16, r0 + ps, w0.z >> 16, r1, w1.x >> 16, r1 + ps, w1.z >> 16, q0, q1, q2, q3, t0, t1, t2, t3);
+                    else q16_search4(r0, w0.x >> 16, r0 + ps, w0.z >> 16, r1, w1.x >> 16, r1 + ps, w1.z >> 16, q0, q1, q2, q3, t0, t1, t2, t3);
                     q_emit(pos, q0, t0, w0.y);
                     q_emit(pos + 1u, q1, t1, w0.w);
                     q_emit(pos + 2u, q2, t2, w1.y);
@@ -844,11 +875,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) iss_generate_kernel(cons
                     qpar ^= 1u << stg;
                     if (valid) {
                         const uint32_t r0 = row0 + stg * p.q_stage_cap;
-                        if constexpr (kQB == 2 && kK == 64) {
+                        if constexpr (kQB == 2) {
                             if (b + 1u < b_end) q_block2(b, r0); else q_block(b, r0);
-                        } else if constexpr (kQB == 2) {
-                            q_block(b, r0);
-                            if (b + 1u < b_end) q_block(b + 1u, r0 + p.q_stage_bytes[o]);
                         } else if constexpr (kQB == 1) {
                             q_block(b, r0);
                         } else if constexpr (kQB > 2) {
