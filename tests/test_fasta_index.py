@@ -60,3 +60,19 @@ def test_index_on_random_text():
         got = c_index(text)
         exp = list(fasta.parse(io.BytesIO(text)))
         assert [(t.decode("ascii", "replace"), b.translate(None, WS)) for t, _, b, _ in got] == [(r.description, r.seq) for r in exp], text
+
+
+def test_text_sequences_read_the_mapping_on_demand():
+    """fasta.TextSeq: what a record's .seq is after Engine.load_fasta -- the base count the device reported, and the bytes
+    cut out of the text (white space removed) only when asked for."""
+    text = b">a x\nAC GT\r\nNN\n\n>b\nacgt\n"
+    (t1, i1, b1, _), (t2, i2, b2, _) = c_index(text)
+    s1 = fasta.TextSeq(text, text.index(b1), len(b1), 6)
+    s2 = fasta.TextSeq(memoryview(text), text.index(b2), len(b2), 4)
+    assert len(s1) == 6 and bytes(s1) == b"ACGTNN" and str(s1) == "ACGTNN" and s1 == "ACGTNN" and s1 == b"ACGTNN"
+    assert len(s2) == 4 and bytes(s2) == b"acgt" and s2[1:3] == b"cg"
+    rec = fasta.Record(s1, id=i1.decode(), description=t1.decode())
+    assert len(rec) == 6 and rec.id == "a" and rec.description == "a x"
+    out = io.StringIO()
+    assert fasta.write([fasta.Record(bytes(s1), id="a", description="a x")], out) == 1
+    assert out.getvalue() == ">a x\nACGTNN\n"
